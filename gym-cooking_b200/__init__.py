@@ -1,0 +1,3 @@
+"""gym-cooking_b200: B200-native batched drop-in for the three hot paths of deletfsi/gym-cooking
+(env step, subtask value/Q, Bayesian-Delegation posterior).  See DESIGN.md."""
+from . import levels  # noqa: F401

@@ -1,0 +1,246 @@
+/*
+ * gymcook.h - C-ABI of libgymcook.so, the B200-native batched drop-in for the three
+ * data-parallel hot paths of deletfsi/gym-cooking:
+ *
+ *   (A) OvercookedEnvironment.step      gym_cooking/envs/overcooked_environment.py:255-306
+ *   (B) E2E_BRTDP subtask value / Q      gym_cooking/navigation_planner/planners/e2e_brtdp.py:987-1076
+ *   (C) BayesianDelegator posterior      gym_cooking/delegation_planner/bayesian_delegator.py:1026-1072
+ *
+ * The reference is pure Python and has no FFI of its own; the binding a maintainer adds is
+ * the ctypes stub shown in INTEGRATION.md.  Conventions (all entry points):
+ *   - plain C, extern "C"; no torch / C++ types in any signature;
+ *   - every array pointer marked "device" is a CUDA device pointer owned by the caller
+ *     (e.g. torch.Tensor.data_ptr()); the library never frees or retains it;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all
+ *     kernels are asynchronous on it, the caller synchronises;
+ *   - return value 0 = success, negative = error (GC_E_*), message via gc_last_error()
+ *     (thread-local);
+ *   - there is NO CPU fallback: if no CUDA device is usable the compute entry points fail
+ *     with GC_E_CUDA.
+ *
+ * Action encoding (World.NAV_ACTIONS order + stay; utils/world.py:16, navigation_planner/utils.py:65,88):
+ *     0=(0,+1)  1=(0,-1)  2=(-1,0)  3=(+1,0)  4=(0,0)
+ *
+ * Packed env state: one 128-bit word per env (uint32[4]), grid <= 8x8, <= 4 agents,
+ * <= 6 movable objects.  cell = y*8 + x.
+ *   w[0]  bits  0-5   agent-1 cell      bits  6-11 agent-2 cell
+ *         bits 12-17  agent-3 cell      bits 18-23 agent-4 cell   (unused agents: 0)
+ *         bits 24-30  t (env.t, saturates at 127)                  bit 31 done (sticky)
+ *   w[1..3]  six 16-bit object slots, slot k = (w[1 + k/2] >> 16*(k%2)) & 0xffff
+ *         bits 0-6   content mask: bit0 Tomato, bit1 Lettuce, bit2 Onion, bit3 Plate present;
+ *                                  bit4/5/6 Tomato/Lettuce/Onion chopped
+ *         bits 7-12  cell of the object when it lies on a counter/cutboard/delivery square,
+ *                    0 while held
+ *         bits 13-15 holder: 0 = not held, 1..4 = held by agent-<holder>, 7 = dead slot
+ *                    (its contents were merged into another object; whole slot = 0xE000)
+ *   Slots are created in level-file scan order (row by row; env.load_level :149-174).  On a
+ *   merge the HELD object absorbs the counter object (SimAgent.acquire, utils/agent.py:408-414)
+ *   so the held slot survives and the counter slot dies.
+ *
+ * Canonical item key (used by the hash and by parity tests, independent of slot order):
+ *   key = mask<<7 | cell<<1 | held, with cell = holder's cell for held objects; live items
+ *   sorted ascending.
+ */
+#ifndef GYMCOOK_H
+#define GYMCOOK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GC_ABI_VERSION 1
+
+#define GC_MAX_AGENTS 4
+#define GC_MAX_OBJECTS 6
+#define GC_MAX_GOALS 4
+#define GC_MAX_CELLS 64
+#define GC_GRID_STRIDE 8
+#define GC_MAX_SUBTASKS 16
+#define GC_MAX_PAIRS 32
+#define GC_MAX_JOINT_ACTIONS 25
+#define GC_MAX_HYPOTHESES 96
+#define GC_MAX_LEVELS 16
+
+/* error codes */
+#define GC_OK 0
+#define GC_E_ARG (-1)    /* bad argument */
+#define GC_E_PARSE (-2)  /* level text not understood / outside the supported envelope */
+#define GC_E_CUDA (-3)   /* CUDA runtime error, or no device */
+#define GC_E_LIMIT (-4)  /* a compile-time limit above was exceeded */
+
+/* cell types (utils/core.py:59-120) */
+#define GC_CELL_FLOOR 0
+#define GC_CELL_COUNTER 1
+#define GC_CELL_CUTBOARD 2
+#define GC_CELL_DELIVERY 3
+
+/* content-mask bits */
+#define GC_M_TOMATO 0x01
+#define GC_M_LETTUCE 0x02
+#define GC_M_ONION 0x04
+#define GC_M_PLATE 0x08
+#define GC_M_CHOP_T 0x10
+#define GC_M_CHOP_L 0x20
+#define GC_M_CHOP_O 0x40
+#define GC_SLOT_DEAD 0xE000u
+
+/* subtask kinds (recipe_planner/utils.py:114-162).  GC_ST_NONE is the `None` subtask. */
+#define GC_ST_NONE 0
+#define GC_ST_CHOP 1
+#define GC_ST_MERGE 2
+#define GC_ST_DELIVER 3
+
+/* reward_done byte written by gc_env_step: bit0 = done(), bit1 = reward() (== successful) */
+#define GC_RD_DONE 0x01
+#define GC_RD_REWARD 0x02
+
+/* One subtask in mask form.  For CHOP: a = fresh mask of the food, goal = chopped mask.
+ * MERGE: a, b = masks of the two start objects (foods in their last state, env:573-584 via
+ * nav_utils.get_subtask_obj :206-229), goal = a|b.  DELIVER: a = goal = mask to deliver. */
+typedef struct gc_subtask {
+  uint8_t kind;
+  uint8_t a;
+  uint8_t b;
+  uint8_t goal;
+} gc_subtask;
+
+/* Static per-level tables.  Produced on the host by gc_level_parse from the reference's
+ * level .txt format (utils/levels/<level>.txt; env.load_level :130-198), POD, 256 bytes. */
+typedef struct gc_level {
+  int32_t width;                         /* world.width  (env:196) */
+  int32_t height;                        /* world.height (env:197) */
+  int32_t n_agent_starts;                /* agent "x y" lines present in the file (<= 4) */
+  int32_t n_objects;                     /* movable objects at reset (<= 6) */
+  int32_t n_goals;                       /* Deliver goals, one per recipe (env.done :344-359) */
+  int32_t delivery_cell;                 /* FIRST Delivery square (env:349), -1 if none */
+  int32_t max_timesteps;                 /* arglist.max_num_timesteps (main.py:24); 0 = no limit */
+  int32_t n_subtasks;                    /* filled by gc_level_set_subtasks (host recipe planner) */
+  uint8_t cell_type[GC_MAX_CELLS];       /* GC_CELL_*, index y*8+x; cells outside the map = COUNTER */
+  uint8_t agent_cell[GC_MAX_AGENTS];     /* start cells (file order) */
+  uint16_t object_init[GC_MAX_OBJECTS];  /* slot encodings at reset; unused = GC_SLOT_DEAD */
+  uint8_t goal_mask[GC_MAX_GOALS];       /* content mask that must lie on delivery_cell */
+  gc_subtask subtask[GC_MAX_SUBTASKS];   /* recipe subtasks in the host's order */
+  uint8_t recipe_code[GC_MAX_GOALS];     /* 1 SimpleTomato 2 SimpleLettuce 3 Salad 4 OnionSalad */
+  uint8_t reserved[64];
+} gc_level;
+
+/* ---- library ------------------------------------------------------------------------ */
+int gc_version(void);
+const char* gc_last_error(void);
+/* number of usable CUDA devices (0 without a GPU; never an error) */
+int gc_device_count(void);
+
+/* ---- level loader (host) -------------------------------------------------------------
+ * Replaces OvercookedEnvironment.load_level (env:130-198) + the Deliver-goal part of done()
+ * (env:344-359).  `txt` is the content of a level file: map rows, blank line, recipe class
+ * names, blank line, agent "x y" lines.  Supported envelope: grid <= 8x8 whose outer ring
+ * has no floor, <= 6 objects with at most one Tomato, one Lettuce and one Onion, recipes
+ * SimpleTomato/SimpleLettuce/Salad/OnionSalad. */
+int gc_level_parse(const char* txt, int len, int max_timesteps, gc_level* out);
+int gc_level_set_subtasks(gc_level* lvl, const gc_subtask* subtasks, int n);
+
+/* ---- (A) env transition --------------------------------------------------------------- */
+/* reset(): every env := the level's initial state (env.reset :201-250).  `level_id` (device,
+ * nullable) selects levels[level_id[i]] per env; NULL = levels[0] for all.  `levels` is a
+ * HOST array; the tables are copied into kernel parameters. */
+int gc_env_reset(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
+                 uint32_t* state /*device uint32[n][4]*/, int64_t n, int n_agents, void* stream);
+
+/* step(): one joint transition for n envs, in place (env.step :255-306: t+=1,
+ * check_collisions :724-762, execute_navigation :767-770 -> interact, done/reward :316-376).
+ * Envs whose done bit is set are left untouched (sticky done) and report their old outcome.
+ *   actions      device uint8[n][n_agents], values 0..4 (>4 is treated as stay)
+ *   reward_done  device uint8[n]        nullable   GC_RD_* bits
+ *   hash         device uint64[n]       nullable   canonical state hash after the step
+ *   collisions   device uint32[n]       nullable   += number of CollisionRepr this step (env:747-752)
+ *   executed     device uint8[n][n_agents] nullable  post-collision actions (env.agent_actions) */
+int gc_env_step(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
+                uint32_t* state /*device*/, const uint8_t* actions /*device*/,
+                uint8_t* reward_done, uint64_t* hash, uint32_t* collisions, uint8_t* executed,
+                int64_t n, int n_agents, void* stream);
+
+/* rollout(): `n_steps` fused transitions with uniform-random actions generated in-kernel:
+ * action[t][env][agent] = philox4x32-10(key=(seed_lo,seed_hi), ctr=(t0+t, env0+env, agent, 0)).x % 5
+ * (SURVEY.md section 8d cfg-2).  State stays in registers between steps.
+ *   hash_trace   device uint64[n_steps][n]  nullable  hash after every step
+ *   stats        device uint64[GC_STATS_LEN] nullable  += episode statistics (see gc_stats_*) */
+int gc_env_rollout(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
+                   uint32_t* state /*device*/, uint8_t* reward_done, uint64_t* hash_trace,
+                   uint32_t* collisions, int64_t n, int n_agents, int n_steps, int t0,
+                   int64_t env0, uint64_t seed, void* stream);
+
+/* the same philox stream, materialised: actions[n_steps][n][n_agents] (device uint8) */
+int gc_fill_random_actions(uint8_t* actions /*device*/, int64_t n, int n_agents, int n_steps,
+                           int t0, int64_t env0, uint64_t seed, void* stream);
+
+/* canonical 64-bit state hash, device uint64[n] */
+int gc_state_hash(const uint32_t* state /*device*/, uint64_t* hash /*device*/, int64_t n,
+                  int n_agents, void* stream);
+
+/* ---- episode statistics (the Bag fields that survive batching; misc/metrics/metrics_bag.py:5-72)
+ * stats[0] episodes  [1] successes  [2] sum of t over done envs  [3] sum collisions
+ * [4] envs still running  [5..5+128) histogram of t over done envs */
+#define GC_STATS_LEN 133
+int gc_stats_reduce(const uint32_t* state /*device*/, const uint32_t* collisions /*device, nullable*/,
+                    const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
+                    uint64_t* stats /*device uint64[GC_STATS_LEN], accumulated into*/,
+                    int64_t n, void* stream);
+
+/* ---- (C) Bayesian-Delegation posterior -------------------------------------------------
+ * One posterior update per (env, observer) row: BayesianDelegator.bayes_update :1045-1072 with
+ * prob_nav_actions :461-689 restated on dumped inputs.
+ *   probs     device float32|float64 [n][H]   in place; entries with alive==0 are ignored and set to 0
+ *   alive     device uint8 [n][H]             nullable (all alive)
+ *   hyp_pair  device uint8 [n][H][n_agents]   for hypothesis h, the pair index (into the P
+ *                                            likelihood rows) of each of its <= n_agents entries;
+ *                                            0xFF = unused entry
+ *   pair_w    device uint8 [n][P]             weight len(subtask_agent_names) (bd:1066), or 1 for greedy
+ *   qdiff     device float [n][P][A]          Q(s,a_taken) - Q(s,a) for each valid action (bd:682);
+ *                                            for a None pair the reference's pseudo-diffs (bd:626)
+ *   n_valid   device uint8 [n][P]             number of valid actions in that row (<= A)
+ *   act_idx   device uint8 [n][P]             index of the taken action among the valid ones (bd:689)
+ * L[p] = softmax(beta*qdiff[p][:n_valid])[act_idx]; probs[h] *= sum_e pair_w*L; normalise
+ * (delegation_planner/utils.py:177-193; total==0 -> uniform). */
+int gc_bd_posterior_f32(float* probs, const uint8_t* alive, const uint8_t* hyp_pair,
+                        const uint8_t* pair_w, const float* qdiff, const uint8_t* n_valid,
+                        const uint8_t* act_idx, float beta, int64_t n, int H, int P, int A,
+                        int n_entries, void* stream);
+int gc_bd_posterior_f64(double* probs, const uint8_t* alive, const uint8_t* hyp_pair,
+                        const uint8_t* pair_w, const double* qdiff, const uint8_t* n_valid,
+                        const uint8_t* act_idx, double beta, int64_t n, int H, int P, int A,
+                        int n_entries, void* stream);
+
+/* ---- (B) navigation planner ------------------------------------------------------------
+ * Distance lower bound of env.get_lower_bound_for_subtask_given_objs (env:594-664) =
+ * World.get_lower_bound_between (utils/world.py:115-264) + holding penalty, for every
+ * (env, pair): pair = (subtask index, agent i, agent j or 0xFF).
+ *   pairs  HOST uint8[n_pairs][3]   lb  device float[n][n_pairs]  (29.0 = perimeter+1 = not doable) */
+int gc_lower_bound(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
+                   const uint32_t* state /*device*/, const uint8_t* pairs /*host*/, int n_pairs,
+                   float* lb /*device*/, int64_t n, int n_agents, void* stream);
+
+/* Exact level-0 subtask values: V*(s) of the deterministic shortest-path MDP the reference's
+ * BRTDP brackets (e2e_brtdp.py:216-352), cost 1 + 0.1*#moving agents (:816-826), transitions =
+ * interact, action set = get_single_actions (+ is_collision filter when joint, :151-206),
+ * goal = "count of goal objects increased" (:435-566), other agents frozen (:360-406).
+ *   v      device float[n][n_pairs]       V*(start); +inf when the goal is unreachable
+ *   q      device float[n][n_pairs][25]   nullable; Q(start, a) = cost + V*(T(start,a)) for the
+ *          joint action a = 5*a_i + a_j (single agent: a in 0..4); +inf for invalid actions
+ *   status device uint8[n][n_pairs]       nullable; 0 ok, 1 goal already satisfied at start,
+ *          2 unreachable, 3 search budget exceeded */
+int gc_subtask_q(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
+                 const uint32_t* state /*device*/, const uint8_t* pairs /*host*/, int n_pairs,
+                 float* v, float* q, uint8_t* status, int64_t n, int n_agents, void* stream);
+
+/* ---- (A') optional image_obs renderer -------------------------------------------------
+ * misc/game/game.py:56-185 geometry (80 px tiles) -> uint8[m][H*80][W*80][3], RGB. */
+int gc_render(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
+              const uint32_t* state /*device*/, const uint8_t* sprites /*device, nullable*/,
+              uint8_t* img /*device*/, int64_t m, int n_agents, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GYMCOOK_H */
