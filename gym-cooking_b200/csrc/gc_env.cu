@@ -1,0 +1,337 @@
+// gc_env.cu - path A kernels: reset, step, fused rollout, action stream, hash, statistics.
+// One thread per env; a warp is a tile of 32 envs whose 128-bit states are read and written
+// with one fully coalesced 512-byte transaction each way.  Static level tables arrive as
+// kernel parameters (constant bank, warp-uniform) when the batch has one level, and are
+// staged through shared memory when envs carry a per-env level id.
+#include "gc_device.cuh"
+#include "gc_host.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int NA>
+__device__ __forceinline__ void load_actions(const uint8_t* __restrict__ actions, int64_t i, uint32_t (&a)[NA]) {
+  if constexpr (NA == 1) {
+    a[0] = actions[i];
+  } else if constexpr (NA == 2) {
+    uint32_t v = reinterpret_cast<const uint16_t*>(actions)[i];
+    a[0] = v & 0xffu;
+    a[1] = v >> 8;
+  } else if constexpr (NA == 4) {
+    uint32_t v = reinterpret_cast<const uint32_t*>(actions)[i];
+    a[0] = v & 0xffu;
+    a[1] = (v >> 8) & 0xffu;
+    a[2] = (v >> 16) & 0xffu;
+    a[3] = v >> 24;
+  } else {
+#pragma unroll
+    for (int k = 0; k < NA; k++) a[k] = actions[i * NA + k];
+  }
+}
+
+template <int NA>
+__device__ __forceinline__ void store_actions(uint8_t* __restrict__ out, int64_t i, const uint32_t (&a)[NA]) {
+#pragma unroll
+  for (int k = 0; k < NA; k++) out[i * NA + k] = (uint8_t)a[k];
+}
+
+// ---------------------------------------------------------------------------------------
+// reset: every env := level.init                                          (env.reset :201-250)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+reset_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restrict__ level_id,
+             uint4* __restrict__ state, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const GcLevelDev& L = levels.lv[level_id ? level_id[i] : 0];
+  state[i] = make_uint4(L.init[0], L.init[1], L.init[2], L.init[3]);
+}
+
+// ---------------------------------------------------------------------------------------
+// step                                                                       (env.step :255-306)
+// ---------------------------------------------------------------------------------------
+template <int NA, int NOBJ, bool MULTI>
+__global__ void __launch_bounds__(kThreads)
+step_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restrict__ level_id,
+            uint4* __restrict__ state, const uint8_t* __restrict__ actions,
+            uint8_t* __restrict__ reward_done, unsigned long long* __restrict__ hash,
+            uint32_t* __restrict__ collisions, uint8_t* __restrict__ executed, int64_t n) {
+  __shared__ GcLevelDev s_levels[MULTI ? GC_MAX_LEVELS : 1];
+  if constexpr (MULTI) {
+    // stage the (<= 1 KB) level tables once per CTA: per-lane level ids would serialise
+    // constant-bank reads, shared memory serves divergent indices at full rate
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&levels);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_levels);
+    for (int k = threadIdx.x; k < (int)(sizeof(GcLevelsDev) / 4); k += kThreads) dst[k] = src[k];
+    __syncthreads();
+  }
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const GcLevelDev& L = MULTI ? s_levels[level_id[i]] : levels.lv[0];
+
+  uint4 s = gc::ld_stream(state + i);
+  uint32_t act[NA];
+  load_actions<NA>(actions, i, act);
+
+  bool done, success;
+  if (s.x >> 31) {
+    // sticky done: the episode is over, nothing mutates; re-report the stored outcome
+    const uint32_t t = (s.x >> 24) & 127u;
+    done = true;
+    success = !(L.max_t != 0u && t >= L.max_t);
+#pragma unroll
+    for (int k = 0; k < NA; k++) act[k] = 4u;
+  } else {
+    gc::Env<NOBJ> e;
+    gc::unpack<NA, NOBJ>(s, e);
+    const uint32_t ncoll = gc::step<NA, NOBJ>(e, act, L, done, success);
+    s = gc::pack<NA, NOBJ>(e, done);
+    gc::st_stream(state + i, s);
+    if (collisions && ncoll) collisions[i] += ncoll;
+  }
+  if (reward_done) reward_done[i] = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
+  if (hash) hash[i] = gc::state_hash<NA>(s);
+  if (executed) store_actions<NA>(executed, i, act);
+}
+
+// ---------------------------------------------------------------------------------------
+// rollout: n_steps fused transitions, state in registers, philox actions in-kernel
+// ---------------------------------------------------------------------------------------
+template <int NA, int NOBJ, bool MULTI>
+__global__ void __launch_bounds__(kThreads)
+rollout_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restrict__ level_id,
+               uint4* __restrict__ state, uint8_t* __restrict__ reward_done,
+               unsigned long long* __restrict__ hash_trace, uint32_t* __restrict__ collisions,
+               int64_t n, int n_steps, uint32_t t0, int64_t env0, unsigned long long seed) {
+  __shared__ GcLevelDev s_levels[MULTI ? GC_MAX_LEVELS : 1];
+  if constexpr (MULTI) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&levels);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_levels);
+    for (int k = threadIdx.x; k < (int)(sizeof(GcLevelsDev) / 4); k += kThreads) dst[k] = src[k];
+    __syncthreads();
+  }
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const GcLevelDev& L = MULTI ? s_levels[level_id[i]] : levels.lv[0];
+
+  uint4 s = gc::ld_stream(state + i);
+  gc::Env<NOBJ> e;
+  gc::unpack<NA, NOBJ>(s, e);
+  bool done = s.x >> 31;
+  bool success = done && !(L.max_t != 0u && e.t >= L.max_t);
+  uint32_t ncoll = 0;
+  for (int k = 0; k < n_steps; k++) {
+    if (!done) {
+      uint32_t r[4], act[NA];
+      gc::philox_actions(seed, t0 + (uint32_t)k, (unsigned long long)(env0 + i), r);
+#pragma unroll
+      for (int a = 0; a < NA; a++) act[a] = r[a];
+      ncoll += gc::step<NA, NOBJ>(e, act, L, done, success);
+    }
+    if (hash_trace) hash_trace[(int64_t)k * n + i] = gc::state_hash<NA>(gc::pack<NA, NOBJ>(e, done));
+  }
+  gc::st_stream(state + i, gc::pack<NA, NOBJ>(e, done));
+  if (reward_done) reward_done[i] = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
+  if (collisions && ncoll) collisions[i] += ncoll;
+}
+
+__global__ void __launch_bounds__(kThreads)
+fill_actions_kernel(uint8_t* __restrict__ actions, int64_t n, int n_agents, int n_steps, uint32_t t0,
+                    int64_t env0, unsigned long long seed) {
+  const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= n * n_steps) return;
+  const int64_t k = idx / n, i = idx % n;
+  uint32_t r[4];
+  gc::philox_actions(seed, t0 + (uint32_t)k, (unsigned long long)(env0 + i), r);
+  for (int a = 0; a < n_agents; a++) actions[idx * n_agents + a] = (uint8_t)r[a];
+}
+
+template <int NA>
+__global__ void __launch_bounds__(kThreads)
+hash_kernel(const uint4* __restrict__ state, unsigned long long* __restrict__ hash, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  hash[i] = gc::state_hash<NA>(state[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// episode statistics: warp-shuffle reduce -> shared-memory histogram -> one atomic per bin
+// per CTA.  stats layout: include/gymcook.h (GC_STATS_LEN).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+stats_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restrict__ level_id,
+             const uint4* __restrict__ state, const uint32_t* __restrict__ collisions,
+             unsigned long long* __restrict__ stats, int64_t n) {
+  __shared__ unsigned int s_hist[128];
+  __shared__ unsigned long long s_acc[5];
+  for (int k = threadIdx.x; k < 128; k += kThreads) s_hist[k] = 0;
+  if (threadIdx.x < 5) s_acc[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned long long v[5] = {0, 0, 0, 0, 0};
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const uint32_t w0 = state[i].x;
+    const GcLevelDev& L = levels.lv[level_id ? level_id[i] : 0];
+    const uint32_t t = (w0 >> 24) & 127u;
+    const bool done = w0 >> 31;
+    v[0] += 1;
+    if (done) {
+      v[1] += !(L.max_t != 0u && t >= L.max_t);
+      v[2] += t;
+      atomicAdd(&s_hist[t], 1u);
+    } else {
+      v[4] += 1;
+    }
+    if (collisions) v[3] += collisions[i];
+  }
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(&s_acc[k], v[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 5 && s_acc[threadIdx.x]) atomicAdd(&stats[threadIdx.x], s_acc[threadIdx.x]);
+  for (int k = threadIdx.x; k < 128; k += kThreads)
+    if (s_hist[k]) atomicAdd(&stats[5 + k], (unsigned long long)s_hist[k]);
+}
+
+inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+template <int NA, int NOBJ>
+int launch_step(bool multi, const GcLevelsDev& lv, const uint8_t* level_id, uint32_t* state,
+                const uint8_t* actions, uint8_t* rd, uint64_t* hash, uint32_t* coll, uint8_t* executed,
+                int64_t n, cudaStream_t st) {
+  auto* s4 = reinterpret_cast<uint4*>(state);
+  auto* h = reinterpret_cast<unsigned long long*>(hash);
+  if (multi)
+    step_kernel<NA, NOBJ, true><<<grid_for(n), kThreads, 0, st>>>(lv, level_id, s4, actions, rd, h, coll, executed, n);
+  else
+    step_kernel<NA, NOBJ, false><<<grid_for(n), kThreads, 0, st>>>(lv, level_id, s4, actions, rd, h, coll, executed, n);
+  return gc_check_launch("gc_env_step");
+}
+
+template <int NA, int NOBJ>
+int launch_rollout(bool multi, const GcLevelsDev& lv, const uint8_t* level_id, uint32_t* state, uint8_t* rd,
+                   uint64_t* hash_trace, uint32_t* coll, int64_t n, int n_steps, int t0, int64_t env0,
+                   uint64_t seed, cudaStream_t st) {
+  auto* s4 = reinterpret_cast<uint4*>(state);
+  auto* h = reinterpret_cast<unsigned long long*>(hash_trace);
+  if (multi)
+    rollout_kernel<NA, NOBJ, true><<<grid_for(n), kThreads, 0, st>>>(lv, level_id, s4, rd, h, coll, n, n_steps,
+                                                                     (uint32_t)t0, env0, seed);
+  else
+    rollout_kernel<NA, NOBJ, false><<<grid_for(n), kThreads, 0, st>>>(lv, level_id, s4, rd, h, coll, n, n_steps,
+                                                                      (uint32_t)t0, env0, seed);
+  return gc_check_launch("gc_env_rollout");
+}
+
+#define GC_DISPATCH_NA_NOBJ(FN, ...)                                   \
+  do {                                                                 \
+    const bool six = max_objs > 4;                                     \
+    switch (n_agents * 2 + (six ? 1 : 0)) {                            \
+      case 2: return FN<1, 4>(__VA_ARGS__);                            \
+      case 3: return FN<1, 6>(__VA_ARGS__);                            \
+      case 4: return FN<2, 4>(__VA_ARGS__);                            \
+      case 5: return FN<2, 6>(__VA_ARGS__);                            \
+      case 6: return FN<3, 4>(__VA_ARGS__);                            \
+      case 7: return FN<3, 6>(__VA_ARGS__);                            \
+      case 8: return FN<4, 4>(__VA_ARGS__);                            \
+      case 9: return FN<4, 6>(__VA_ARGS__);                            \
+    }                                                                  \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int gc_env_reset(const gc_level* levels, int n_levels, const uint8_t* level_id, uint32_t* state, int64_t n,
+                 int n_agents, void* stream) {
+  GcLevelsDev lv;
+  int max_objs = 0;
+  if (int rc = gc_levels_to_dev(levels, n_levels, n_agents, &lv, &max_objs)) return rc;
+  if (!state || n < 0) return gc_fail(GC_E_ARG, "gc_env_reset: bad state/n");
+  if (n == 0) return GC_OK;
+  if (int rc = gc_require_device()) return rc;
+  reset_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(lv, n_levels > 1 ? level_id : nullptr,
+                                                                  reinterpret_cast<uint4*>(state), n);
+  return gc_check_launch("gc_env_reset");
+}
+
+int gc_env_step(const gc_level* levels, int n_levels, const uint8_t* level_id, uint32_t* state,
+                const uint8_t* actions, uint8_t* reward_done, uint64_t* hash, uint32_t* collisions,
+                uint8_t* executed, int64_t n, int n_agents, void* stream) {
+  GcLevelsDev lv;
+  int max_objs = 0;
+  if (int rc = gc_levels_to_dev(levels, n_levels, n_agents, &lv, &max_objs)) return rc;
+  if (!state || !actions || n < 0) return gc_fail(GC_E_ARG, "gc_env_step: null state/actions or n < 0");
+  if (n_levels > 1 && !level_id) return gc_fail(GC_E_ARG, "gc_env_step: n_levels > 1 needs level_id");
+  if (n == 0) return GC_OK;
+  if (int rc = gc_require_device()) return rc;
+  const bool multi = n_levels > 1;
+  GC_DISPATCH_NA_NOBJ(launch_step, multi, lv, level_id, state, actions, reward_done, hash, collisions, executed,
+                      n, (cudaStream_t)stream);
+  return gc_fail(GC_E_ARG, "gc_env_step: n_agents must be 1..4");
+}
+
+int gc_env_rollout(const gc_level* levels, int n_levels, const uint8_t* level_id, uint32_t* state,
+                   uint8_t* reward_done, uint64_t* hash_trace, uint32_t* collisions, int64_t n, int n_agents,
+                   int n_steps, int t0, int64_t env0, uint64_t seed, void* stream) {
+  GcLevelsDev lv;
+  int max_objs = 0;
+  if (int rc = gc_levels_to_dev(levels, n_levels, n_agents, &lv, &max_objs)) return rc;
+  if (!state || n < 0 || n_steps < 0) return gc_fail(GC_E_ARG, "gc_env_rollout: bad state/n/n_steps");
+  if (n_levels > 1 && !level_id) return gc_fail(GC_E_ARG, "gc_env_rollout: n_levels > 1 needs level_id");
+  if (n == 0) return GC_OK;
+  if (int rc = gc_require_device()) return rc;
+  const bool multi = n_levels > 1;
+  GC_DISPATCH_NA_NOBJ(launch_rollout, multi, lv, level_id, state, reward_done, hash_trace, collisions, n, n_steps,
+                      t0, env0, seed, (cudaStream_t)stream);
+  return gc_fail(GC_E_ARG, "gc_env_rollout: n_agents must be 1..4");
+}
+
+int gc_fill_random_actions(uint8_t* actions, int64_t n, int n_agents, int n_steps, int t0, int64_t env0,
+                           uint64_t seed, void* stream) {
+  if (!actions || n < 0 || n_steps < 0 || n_agents < 1 || n_agents > 4)
+    return gc_fail(GC_E_ARG, "gc_fill_random_actions: bad arguments");
+  if (n * n_steps == 0) return GC_OK;
+  if (int rc = gc_require_device()) return rc;
+  fill_actions_kernel<<<grid_for(n * n_steps), kThreads, 0, (cudaStream_t)stream>>>(actions, n, n_agents, n_steps,
+                                                                                    (uint32_t)t0, env0, seed);
+  return gc_check_launch("gc_fill_random_actions");
+}
+
+int gc_state_hash(const uint32_t* state, uint64_t* hash, int64_t n, int n_agents, void* stream) {
+  if (!state || !hash || n < 0) return gc_fail(GC_E_ARG, "gc_state_hash: bad arguments");
+  if (n == 0) return GC_OK;
+  if (int rc = gc_require_device()) return rc;
+  auto* s4 = reinterpret_cast<const uint4*>(state);
+  auto* h = reinterpret_cast<unsigned long long*>(hash);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (n_agents) {
+    case 1: hash_kernel<1><<<grid_for(n), kThreads, 0, st>>>(s4, h, n); break;
+    case 2: hash_kernel<2><<<grid_for(n), kThreads, 0, st>>>(s4, h, n); break;
+    case 3: hash_kernel<3><<<grid_for(n), kThreads, 0, st>>>(s4, h, n); break;
+    case 4: hash_kernel<4><<<grid_for(n), kThreads, 0, st>>>(s4, h, n); break;
+    default: return gc_fail(GC_E_ARG, "gc_state_hash: n_agents must be 1..4");
+  }
+  return gc_check_launch("gc_state_hash");
+}
+
+int gc_stats_reduce(const uint32_t* state, const uint32_t* collisions, const gc_level* levels, int n_levels,
+                    const uint8_t* level_id, uint64_t* stats, int64_t n, void* stream) {
+  GcLevelsDev lv;
+  int max_objs = 0;
+  if (int rc = gc_levels_to_dev(levels, n_levels, 1, &lv, &max_objs)) return rc;
+  if (!state || !stats || n < 0) return gc_fail(GC_E_ARG, "gc_stats_reduce: bad arguments");
+  if (n == 0) return GC_OK;
+  if (int rc = gc_require_device()) return rc;
+  unsigned grid = grid_for(n);
+  if (grid > 148u * 8u) grid = 148u * 8u;  // grid-stride: one resident wave
+  stats_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(lv, n_levels > 1 ? level_id : nullptr,
+                                                            reinterpret_cast<const uint4*>(state), collisions,
+                                                            reinterpret_cast<unsigned long long*>(stats), n);
+  return gc_check_launch("gc_stats_reduce");
+}
+
+}  // extern "C"

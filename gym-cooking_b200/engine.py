@@ -1,0 +1,144 @@
+"""Batched kitchen engine: N independent Overcooked episodes as one uint32[N][4] CUDA tensor.
+
+This is the host mirror of path A (OvercookedEnvironment.reset/step,
+envs/overcooked_environment.py:201-306) for a whole batch; all state mutation happens in the
+kernels behind include/gymcook.h.  `envs.OvercookedEnvironment` wraps it with the reference's
+gym-style single-env surface.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib, levels as _levels
+
+# World.NAV_ACTIONS + stay (utils/world.py:16)
+ACTIONS = ((0, 1), (0, -1), (-1, 0), (1, 0), (0, 0))
+ACTION_INDEX = {a: i for i, a in enumerate(ACTIONS)}
+
+
+class KitchenBatch:
+    """N envs sharing one level (or one of several levels via `level_id`)."""
+
+    def __init__(self, level, num_agents, num_envs, max_num_timesteps=100, device=None, level_id=None,
+                 track_collisions=False):
+        names = [level] if isinstance(level, str) else list(level)
+        if not names:
+            raise ValueError("need at least one level")
+        self.level_names = names
+        self.levels = [_lib.parse_level(_levels.resolve_level(nm), max_num_timesteps) for nm in names]
+        self._level_arr = _lib.level_array(self.levels)
+        self.n_levels = len(names)
+        self.num_agents = int(num_agents)
+        self.num_envs = int(num_envs)
+        self.max_num_timesteps = int(max_num_timesteps)
+        if not torch.cuda.is_available():
+            raise _lib.GcError("gym-cooking_b200 needs a CUDA device: there is no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.lib = _lib.load()
+        with torch.cuda.device(self.device):
+            self.state = torch.empty((self.num_envs, 4), dtype=torch.int32, device=self.device)
+            self.reward_done = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+            self.collisions = (torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+                               if track_collisions else None)
+        if self.n_levels > 1:
+            if level_id is None:
+                raise ValueError("several levels need a per-env level_id tensor")
+            self.level_id = level_id.to(self.device, torch.uint8).contiguous()
+        else:
+            self.level_id = None
+        self.reset()
+
+    # -- marshalling helpers ------------------------------------------------------------
+    def _lv(self):
+        return C.cast(self._level_arr, C.POINTER(_lib.Level))
+
+    def _stream(self):
+        return _lib.stream_ptr(self.device)
+
+    # -- path A ---------------------------------------------------------------------------
+    def reset(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gc_env_reset(self._lv(), self.n_levels, _lib.ptr(self.level_id), _lib.ptr(self.state),
+                                             self.num_envs, self.num_agents, self._stream()))
+            self.reward_done.zero_()
+            if self.collisions is not None:
+                self.collisions.zero_()
+        return self.state
+
+    def step(self, actions, hash_out=None, executed_out=None):
+        """actions: uint8[N][num_agents] CUDA tensor, values 0..4.  In place on self.state."""
+        if actions.shape != (self.num_envs, self.num_agents):
+            raise ValueError("actions must be [%d, %d]" % (self.num_envs, self.num_agents))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gc_env_step(
+                self._lv(), self.n_levels, _lib.ptr(self.level_id), _lib.ptr(self.state),
+                _lib.ptr(actions, torch.uint8), _lib.ptr(self.reward_done), _lib.ptr(hash_out),
+                _lib.ptr(self.collisions), _lib.ptr(executed_out), self.num_envs, self.num_agents, self._stream()))
+        return self.reward_done
+
+    def rollout(self, n_steps, t0=0, env0=0, seed=1234, hash_trace=None):
+        """n_steps fused steps with the philox uniform-random action stream (cfg-2)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gc_env_rollout(
+                self._lv(), self.n_levels, _lib.ptr(self.level_id), _lib.ptr(self.state), _lib.ptr(self.reward_done),
+                _lib.ptr(hash_trace), _lib.ptr(self.collisions), self.num_envs, self.num_agents, int(n_steps),
+                int(t0), int(env0), int(seed), self._stream()))
+        return self.reward_done
+
+    def random_actions(self, n_steps, t0=0, env0=0, seed=1234):
+        """The same action stream materialised: uint8[n_steps][N][num_agents]."""
+        with torch.cuda.device(self.device):
+            out = torch.empty((n_steps, self.num_envs, self.num_agents), dtype=torch.uint8, device=self.device)
+            _lib.check(self.lib.gc_fill_random_actions(_lib.ptr(out), self.num_envs, self.num_agents, int(n_steps),
+                                                       int(t0), int(env0), int(seed), self._stream()))
+        return out
+
+    def hash(self, out=None):
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty(self.num_envs, dtype=torch.int64, device=self.device)
+            _lib.check(self.lib.gc_state_hash(_lib.ptr(self.state), _lib.ptr(out), self.num_envs, self.num_agents,
+                                              self._stream()))
+        return out
+
+    def stats(self, out=None):
+        """Episode statistics vector (int64[133], include/gymcook.h GC_STATS_LEN); `out` is
+        accumulated into, so several shards / calls can share one vector."""
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.zeros(_lib.STATS_LEN, dtype=torch.int64, device=self.device)
+            _lib.check(self.lib.gc_stats_reduce(_lib.ptr(self.state), _lib.ptr(self.collisions), self._lv(),
+                                                self.n_levels, _lib.ptr(self.level_id), _lib.ptr(out),
+                                                self.num_envs, self._stream()))
+        return out
+
+    # -- views --------------------------------------------------------------------------------
+    @property
+    def done(self):
+        return (self.reward_done & 1).bool()
+
+    @property
+    def reward(self):
+        return (self.reward_done >> 1) & 1
+
+
+def decode_state(words, num_agents):
+    """One packed state (4 ints) -> dict(t, done, agents=[(x, y, hold_mask)], objects=[(mask, x, y, holder)])."""
+    w = [int(v) & 0xFFFFFFFF for v in words]
+    slots = [(w[1 + k // 2] >> (16 * (k % 2))) & 0xFFFF for k in range(_lib.MAX_OBJECTS)]
+    cells = [(w[0] >> (6 * i)) & 63 for i in range(num_agents)]
+    agents = []
+    for i, c in enumerate(cells):
+        hold = 0
+        for s in slots:
+            if (s >> 13) == i + 1:
+                hold = s & 0x7F
+        agents.append((c & 7, c >> 3, hold))
+    objects = []
+    for s in slots:
+        holder = s >> 13
+        if holder == 7:
+            continue
+        c = cells[holder - 1] if holder else (s >> 7) & 63
+        objects.append((s & 0x7F, c & 7, c >> 3, holder))
+    return dict(t=(w[0] >> 24) & 127, done=bool(w[0] >> 31), agents=agents, objects=objects)

