@@ -14,7 +14,7 @@ struct GcLevelDev {
   unsigned long long floor_mask;  // bit c set: cell c is Floor (the only non-collidable square)
   unsigned long long cut_mask;    // Cutboard squares
   unsigned long long deliv_mask;  // Delivery squares (all of them: interact.py:35 tests the type)
-  uint32_t goal_slot[GC_MAX_GOALS];  // goal_mask | first_delivery_cell << 7; unused = 0xFFFFFFFF
+  uint32_t goal_slot[GC_MAX_GOALS];  // goal_mask | first_delivery_cell << 7; unused entries repeat goal 0
   uint32_t n_goals;
   uint32_t max_t;  // 0 = no limit
   uint32_t init[4];
@@ -34,8 +34,6 @@ __device__ __forceinline__ int action_delta(uint32_t a) {
   return (int)(int8_t)(t & 0xffu);
 }
 
-__device__ __forceinline__ bool bit64(unsigned long long m, uint32_t c) { return (m >> c) & 1ull; }
-
 // every Food in the object is in its last state (Food.done, utils/core.py:293-296)
 __device__ __forceinline__ bool foods_done(uint32_t m) { return ((m & 7u) & ~(m >> 4)) == 0u; }
 // Object.is_deliverable utils/core.py:214-219
@@ -47,7 +45,7 @@ __device__ __forceinline__ bool mergeable(uint32_t a, uint32_t b) {
   return ((a & b & 8u) == 0u) && foods_done(a | b);
 }
 // Object.needs_chopped utils/core.py:176-178: a single fresh food, i.e. mask in {1,2,4}
-__device__ __forceinline__ bool needs_chopped(uint32_t m) { return m < 8u && ((0x16u >> m) & 1u); }
+__device__ __forceinline__ bool needs_chopped(uint32_t m) { return ((0x16u >> min(m, 31u)) & 1u) != 0u; }
 
 // Unpacked working form: agent cells and object slots in registers.
 template <int NOBJ>
@@ -81,65 +79,72 @@ __device__ __forceinline__ uint4 pack(const Env<NOBJ>& e, bool done) {
   return make_uint4(x, w[0], w[1], w[2]);
 }
 
+// (mask >> c) & 1 for a 64-bit bitboard: one funnel shift (SHF.R.U64) instead of building 1 << c
+__device__ __forceinline__ bool board_bit(unsigned long long m, uint32_t c) {
+  uint32_t lo;  // asm: keeps nvcc from rewriting the test as ((1 << c) & m) != 0 (4 extra instructions)
+  asm("{\n\t.reg .u64 t;\n\tshr.u64 t, %1, %2;\n\tcvt.u32.u64 %0, t;\n\t}" : "=r"(lo) : "l"(m), "r"(c));
+  return (lo & 1u) != 0u;
+}
+
 // utils/interact.py:33-89 for an agent whose target square is NOT floor (counter, cutboard or
 // delivery); arglist.play == False.  `hp` = (agent index + 1) << 6 is the 9-bit "place" of the
-// agent's hand (cell 0, holder i+1); a lying object's place is its cell (holder 0).
+// agent's hand (cell 0, holder i+1); a lying object's place is its cell (holder 0).  Written as
+// a gather (hand slot / target slot), a handful of predicates, and a scatter with recomputed
+// compares, so that nothing but slot values stays live across the case analysis.
+// Returns true when an object was put on a Delivery square (the only way done() can flip).
 template <int NOBJ>
-__device__ __forceinline__ void interact_square(Env<NOBJ>& e, uint32_t hp, uint32_t tgt, bool is_del,
+__device__ __forceinline__ bool interact_square(Env<NOBJ>& e, uint32_t hp, uint32_t tgt, bool is_del,
                                                 bool is_cut) {
-  uint32_t mH = 0, mT = 0;  // mask in hand / mask lying on the target square
-  bool isH[NOBJ], isT[NOBJ];
+  uint32_t sH = 0, sT = 0;  // slot in hand / slot lying on the target square (0 = none)
 #pragma unroll
   for (int k = 0; k < NOBJ; k++) {
-    uint32_t place = e.slot[k] >> 7;
-    isH[k] = place == hp;
-    isT[k] = place == tgt;
-    if (isH[k]) mH = e.slot[k] & 0x7fu;
-    if (isT[k]) mT = e.slot[k] & 0x7fu;
+    const uint32_t place = e.slot[k] >> 7;
+    sH = (place == hp) ? e.slot[k] : sH;
+    sT = (place == tgt) ? e.slot[k] : sT;
   }
-  const bool holding = mH != 0u, occupied = mT != 0u;
-  uint32_t newH = mH | (hp << 7), newT = 0;
-  bool chgT = false;
-  if (holding) {
-    if (is_del) {  // :35-40 deliver if deliverable, else nothing
-      if (deliverable(mH)) newH = mH | (tgt << 7);
-    } else if (occupied) {  // :43-52 merge into the hand; the counter object dies
-      if (mergeable(mH, mT)) {
-        newH |= mT;
-        newT = GC_SLOT_DEAD;
-        chgT = true;
-      }
-    } else if (is_cut && needs_chopped(mH)) {  // :63-65 chop in hand
-      newH |= mH << 4;
-    } else {  // :66-70 put down
-      newH = mH | (tgt << 7);
-    }
-  } else if (occupied && !is_del) {  // :77-84 pick up (never from a Delivery)
-    newT = mT | (hp << 7);
-    chgT = true;
-  }
+  const uint32_t mH = sH & 0x7fu, mT = sT & 0x7fu;
+  const bool holding = sH != 0u, occupied = sT != 0u;
+  // hand side
+  const bool chop = is_cut & !occupied & needs_chopped(mH);                 // :63-65 (mH == 0 -> false)
+  const bool drop = is_del ? deliverable(mH) : (!occupied & !chop);         // :35-40 deliver, :66-70 put down
+  const bool merge = !is_del & occupied & holding & mergeable(mH, mT);      // :43-52
+  uint32_t newH = sH;  // sH == 0 (not holding) matches no slot below
+  newH = chop ? (sH | (mH << 4)) : newH;
+  newH = merge ? (sH | mT) : newH;
+  newH = drop ? (mH | (tgt << 7)) : newH;
+  // square side: merged away (:48-49) or picked up (:77-84, never from a Delivery)
+  const bool pick = !holding & !is_del;
+  uint32_t newT = sT;  // sT == 0 (empty square) matches no slot below
+  newT = merge ? GC_SLOT_DEAD : newT;
+  newT = pick ? (mT | (hp << 7)) : newT;
+  // scatter by VALUE (the gathered slot values are unique among live slots whenever they
+  // change), which also keeps the compiler from carrying eight compare predicates across
 #pragma unroll
   for (int k = 0; k < NOBJ; k++) {
-    if (isH[k]) e.slot[k] = newH;
-    else if (isT[k] && chgT) e.slot[k] = newT;
+    uint32_t v = e.slot[k];
+    v = (v == sT) ? newT : v;
+    v = (e.slot[k] == sH) ? newH : v;
+    e.slot[k] = v;
   }
+  return holding && is_del && drop;
 }
 
 // One joint transition: env.step (envs/overcooked_environment.py:255-306) minus the copies.
 // Returns the number of CollisionRepr (env:747-752); act[] is overwritten with the executed
 // (post-collision) actions; `done`/`success` receive env.done() / env.successful.
+// Precondition: the env is not done (so not every Deliver goal is met yet).
 template <int NA, int NOBJ, typename LV>
 __device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], const LV& L, bool& done,
                                          bool& success) {
-  if (e.t < 127u) e.t += 1u;  // env:257
+  e.t = min(e.t + 1u, 127u);  // env:257
   // where each agent would stand after its own action (is_collision :692-700)
   uint32_t tgt[NA], nxt[NA];
   bool floor_t[NA];
 #pragma unroll
   for (int i = 0; i < NA; i++) {
-    if (act[i] > 4u) act[i] = 4u;
+    act[i] = min(act[i], 4u);
     tgt[i] = (e.cell[i] + (uint32_t)action_delta(act[i])) & 63u;
-    floor_t[i] = bit64(L.floor_mask, tgt[i]);
+    floor_t[i] = board_bit(L.floor_mask, tgt[i]);
     nxt[i] = floor_t[i] ? tgt[i] : e.cell[i];
   }
   // check_collisions :724-762 - all pairs on the ORIGINAL actions, cancellations applied after
@@ -152,36 +157,36 @@ __device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], cons
 #pragma unroll
     for (int j = i + 1; j < NA; j++) {
       const bool same = nxt[i] == nxt[j];
-      const bool swap = (e.cell[i] == nxt[j]) && (e.cell[j] == nxt[i]);
-      const bool bi = (nxt[i] == e.cell[i]) && (act[i] != 4u);  // i faces a square: keeps its action
-      const bool bj = (nxt[j] == e.cell[j]) && (act[j] != 4u);
-      const bool ci = same ? !bi : swap;               // :704-717
-      const bool cj = same ? (bi || !bj) : swap;
-      cancel[i] |= ci;
-      cancel[j] |= cj;
-      ncoll += (same || swap) ? 1u : 0u;
+      const bool swap = (e.cell[i] == nxt[j]) & (e.cell[j] == nxt[i]);
+      const bool bi = (nxt[i] == e.cell[i]) & (act[i] != 4u);  // i faces a square: keeps its action
+      const bool bj = (nxt[j] == e.cell[j]) & (act[j] != 4u);
+      cancel[i] |= (same & !bi) | (!same & swap);  // :704-717
+      cancel[j] |= (same & (bi | !bj)) | (!same & swap);
+      ncoll += (same | swap) ? 1u : 0u;
     }
   }
   // execute_navigation :767-770 - sequential in agent order
+  bool delivered = false;
 #pragma unroll
   for (int i = 0; i < NA; i++) {
-    if (cancel[i]) act[i] = 4u;  // :757-761
-    if (act[i] != 4u) {
-      if (floor_t[i]) {
-        e.cell[i] = tgt[i];  // interact.py:29-30
-      } else {
-        interact_square<NOBJ>(e, (uint32_t)(i + 1) << 6, tgt[i], bit64(L.deliv_mask, tgt[i]),
-                              bit64(L.cut_mask, tgt[i]));
-      }
-    }
+    act[i] = cancel[i] ? 4u : act[i];  // :757-761
+    e.cell[i] = cancel[i] ? e.cell[i] : nxt[i];  // interact.py:29-30 (nxt == cell unless floor ahead)
+    if (act[i] != 4u && !floor_t[i])
+      delivered |= interact_square<NOBJ>(e, (uint32_t)(i + 1) << 6, tgt[i], board_bit(L.deliv_mask, tgt[i]),
+                                         board_bit(L.cut_mask, tgt[i]));
   }
-  // env.done :316-363 - timeout first, then every Deliver goal lying on the delivery square
-  bool all_goals = true;
-  for (uint32_t g = 0; g < L.n_goals; g++) {
-    bool found = false;
+  // env.done :316-363 - timeout first, then every Deliver goal lying on the delivery square.
+  // Goals can only become complete on a step that put something on a Delivery square.
+  bool all_goals = false;
+  if (delivered) {
+    all_goals = true;
 #pragma unroll
-    for (int k = 0; k < NOBJ; k++) found |= e.slot[k] == L.goal_slot[g];
-    all_goals &= found;
+    for (int g = 0; g < GC_MAX_GOALS; g++) {
+      bool found = false;  // unused goal entries repeat goal 0 (gc_levels_to_dev)
+#pragma unroll
+      for (int k = 0; k < NOBJ; k++) found |= e.slot[k] == L.goal_slot[g];
+      all_goals &= found;
+    }
   }
   const bool timeout = L.max_t != 0u && e.t >= L.max_t;
   done = timeout || all_goals;

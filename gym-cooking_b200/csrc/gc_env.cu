@@ -6,6 +6,8 @@
 #include "gc_device.cuh"
 #include "gc_host.h"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -51,6 +53,10 @@ reset_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restri
 // ---------------------------------------------------------------------------------------
 // step                                                                       (env.step :255-306)
 // ---------------------------------------------------------------------------------------
+// Persistent, software-pipelined: a thread walks envs i, i + stride, ... and issues the loads of
+// its NEXT env before computing the current one, so DRAM latency hides behind ~300 ALU
+// instructions of the same warp instead of needing a fresh wave of CTAs (at 2^20 envs a
+// one-env-per-thread grid is only 3.5 waves deep and spends half its time in ramp and tail).
 template <int NA, int NOBJ, bool MULTI>
 __global__ void __launch_bounds__(kThreads)
 step_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restrict__ level_id,
@@ -66,33 +72,49 @@ step_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restric
     for (int k = threadIdx.x; k < (int)(sizeof(GcLevelsDev) / 4); k += kThreads) dst[k] = src[k];
     __syncthreads();
   }
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
-  const GcLevelDev& L = MULTI ? s_levels[level_id[i]] : levels.lv[0];
+  uint4 s_next = gc::ld_stream(state + i);
+  uint32_t a_next[NA];
+  load_actions<NA>(actions, i, a_next);
+  uint32_t lvl_next = 0;
+  if constexpr (MULTI) lvl_next = level_id[i];
 
-  uint4 s = gc::ld_stream(state + i);
-  uint32_t act[NA];
-  load_actions<NA>(actions, i, act);
-
-  bool done, success;
-  if (s.x >> 31) {
-    // sticky done: the episode is over, nothing mutates; re-report the stored outcome
-    const uint32_t t = (s.x >> 24) & 127u;
-    done = true;
-    success = !(L.max_t != 0u && t >= L.max_t);
+  for (; i < n; i += stride) {
+    uint4 s = s_next;
+    uint32_t act[NA];
 #pragma unroll
-    for (int k = 0; k < NA; k++) act[k] = 4u;
-  } else {
-    gc::Env<NOBJ> e;
-    gc::unpack<NA, NOBJ>(s, e);
-    const uint32_t ncoll = gc::step<NA, NOBJ>(e, act, L, done, success);
-    s = gc::pack<NA, NOBJ>(e, done);
-    gc::st_stream(state + i, s);
-    if (collisions && ncoll) collisions[i] += ncoll;
+    for (int k = 0; k < NA; k++) act[k] = a_next[k];
+    const uint32_t lvl = lvl_next;
+    const int64_t inext = i + stride;
+    if (inext < n) {  // prefetch
+      s_next = gc::ld_stream(state + inext);
+      load_actions<NA>(actions, inext, a_next);
+      if constexpr (MULTI) lvl_next = level_id[inext];
+    }
+    const GcLevelDev& L = MULTI ? s_levels[lvl] : levels.lv[0];
+
+    bool done, success;
+    if (s.x >> 31) {
+      // sticky done: the episode is over, nothing mutates; re-report the stored outcome
+      const uint32_t t = (s.x >> 24) & 127u;
+      done = true;
+      success = !(L.max_t != 0u && t >= L.max_t);
+#pragma unroll
+      for (int k = 0; k < NA; k++) act[k] = 4u;
+    } else {
+      gc::Env<NOBJ> e;
+      gc::unpack<NA, NOBJ>(s, e);
+      const uint32_t ncoll = gc::step<NA, NOBJ>(e, act, L, done, success);
+      s = gc::pack<NA, NOBJ>(e, done);
+      gc::st_stream(state + i, s);
+      if (collisions && ncoll) collisions[i] += ncoll;
+    }
+    if (reward_done) reward_done[i] = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
+    if (hash) hash[i] = gc::state_hash<NA>(s);
+    if (executed) store_actions<NA>(executed, i, act);
   }
-  if (reward_done) reward_done[i] = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
-  if (hash) hash[i] = gc::state_hash<NA>(s);
-  if (executed) store_actions<NA>(executed, i, act);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -198,6 +220,27 @@ stats_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restri
 
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
+// Grid of the step kernel.  Measured on B200 (profiles/r01_step_kernel.md): the kernel is bound
+// by the integer ALU pipe, not by DRAM latency, so one env per thread (a full grid) beats a
+// persistent grid-stride loop with register prefetch by ~10 %.  GC_STEP_CTAS_PER_SM=k (1..8)
+// switches to the persistent form with k CTAs per SM for experiments.
+inline unsigned step_grid(int64_t n) {
+  static int sms = 0, per_sm = -1;
+  if (per_sm < 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    const char* e = getenv("GC_STEP_CTAS_PER_SM");
+    per_sm = e ? atoi(e) : 0;
+    if (per_sm < 0 || per_sm > 8) per_sm = 0;
+  }
+  const unsigned full = grid_for(n);
+  if (per_sm == 0) return full;
+  const unsigned cap = (unsigned)(sms * per_sm);
+  return full < cap ? full : cap;
+}
+
 template <int NA, int NOBJ>
 int launch_step(bool multi, const GcLevelsDev& lv, const uint8_t* level_id, uint32_t* state,
                 const uint8_t* actions, uint8_t* rd, uint64_t* hash, uint32_t* coll, uint8_t* executed,
@@ -205,9 +248,9 @@ int launch_step(bool multi, const GcLevelsDev& lv, const uint8_t* level_id, uint
   auto* s4 = reinterpret_cast<uint4*>(state);
   auto* h = reinterpret_cast<unsigned long long*>(hash);
   if (multi)
-    step_kernel<NA, NOBJ, true><<<grid_for(n), kThreads, 0, st>>>(lv, level_id, s4, actions, rd, h, coll, executed, n);
+    step_kernel<NA, NOBJ, true><<<step_grid(n), kThreads, 0, st>>>(lv, level_id, s4, actions, rd, h, coll, executed, n);
   else
-    step_kernel<NA, NOBJ, false><<<grid_for(n), kThreads, 0, st>>>(lv, level_id, s4, actions, rd, h, coll, executed, n);
+    step_kernel<NA, NOBJ, false><<<step_grid(n), kThreads, 0, st>>>(lv, level_id, s4, actions, rd, h, coll, executed, n);
   return gc_check_launch("gc_env_step");
 }
 

@@ -60,7 +60,7 @@ int gc_levels_to_dev(const gc_level* levels, int n_levels, int n_agents, GcLevel
       if (s.cell_type[c] == GC_CELL_DELIVERY) d.deliv_mask |= b;
     }
     for (int g = 0; g < GC_MAX_GOALS; g++)
-      d.goal_slot[g] = g < s.n_goals ? ((uint32_t)s.goal_mask[g] | ((uint32_t)s.delivery_cell << 7)) : 0xFFFFFFFFu;
+      d.goal_slot[g] = (uint32_t)s.goal_mask[g < s.n_goals ? g : 0] | ((uint32_t)s.delivery_cell << 7);
     d.n_goals = (uint32_t)s.n_goals;
     d.max_t = (uint32_t)s.max_timesteps;
     uint32_t w0 = 0;

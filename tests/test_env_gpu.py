@@ -84,7 +84,6 @@ def test_step_matches_oracle_on_random_batches(level, n_agents):
             assert (_u32(kb.state) == ost).all(), "step %d" % s
             assert (kb.reward_done.cpu().numpy() == rd).all(), "step %d" % s
     assert (kb.collisions.cpu().numpy().view(np.uint32) == ocoll).all()
-    assert (kb.hash().cpu().numpy().view(np.uint64) == O.hash_states(ost[:2048], n_agents)[:2048]).all() or True
     h = kb.hash().cpu().numpy().view(np.uint64)
     assert (h[:2048] == O.hash_states(ost[:2048], n_agents)).all()
 
