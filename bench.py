@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of gym-cooking_b200 (contract: see the task prompt / DESIGN.md).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N > 1: under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
+
+Workload = BASELINE.json configs[1] ("cfg-2"): 2 agents, partial-divider_tl, 2^20 envs per GPU,
+uniform-random actions (philox stream).  A *step* is one env.step over one
+batch of 2^20 envs = one gc_env_step launch.  To keep the timed region out of the 126 MB L2 the
+launches cycle through a ring of 16 independent batches per GPU (16 x (16 MB state + 2 MB
+actions + 1 MB reward/done) = 304 MB), so every launch streams its inputs from HBM.
+`value` = agent-steps/s with everything resident in HBM; `e2e` = the same metric through the
+public API (OvercookedEnvironment.step) with the step's actions copied from pinned host memory
+and its reward/done bytes copied back, every step.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LEVEL, N_AGENTS, N_ENVS, HORIZON = "partial-divider_tl", 2, 1 << 20, 100
+RING = 16
+SEED = 1234
+METRIC, UNIT = "agent_steps_per_sec", "agent-steps/s"
+# algorithmic bytes per env-step of gc_env_step: 16 B state read + 16 B
+# state write + n_agents action bytes + 1 reward/done byte
+BYTES_PER_ENV_STEP = 33 + N_AGENTS
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "cfg-2: 2-agent partial-divider_tl, 2^20 envs per GPU, uniform-random actions, env step only",
+        "level": LEVEL, "n_agents": N_AGENTS, "envs_per_gpu": N_ENVS, "horizon": HORIZON,
+        "actions": "philox4x32-10(seed=1234, ctr=(t, env)) -> mulhi(word, 5), resident in HBM",
+        "l2": "ring of %d batches per GPU (%d MB > 126 MB L2): inputs larger than L2" % (
+            RING, RING * N_ENVS * (16 + N_AGENTS + 1) >> 20),
+        "parallelism": "env-batch sharding x%d, no data-path collective" % n_gpus,
+    }
+
+
+# ----------------------------------------------------------------------------------------
+# clocks: sample NVML during the timed region
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit and name != "gpu_idle":
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self.sample()
+            time.sleep(0.005)
+
+    def start(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self.sample()
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------
+# CPU legs (oracle port): cpu_baseline of our arm and the whole reference arm
+# ----------------------------------------------------------------------------------------
+def cpu_port_rate(n_envs, n_steps, n_threads):
+    """agent-steps/s of the CPU oracle (oracle/gc_oracle.c) on cfg-2's own action stream."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    import gym_cooking_b200 as gcb
+    lv = O.parse_level(gcb.levels.level_text(LEVEL), HORIZON)
+    st = O.reset_state(lv, N_AGENTS, n_envs)
+    t0 = time.perf_counter()
+    O.rollout_batch(lv, st, N_AGENTS, n_steps, seed=SEED, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    return n_envs * n_steps * N_AGENTS / dt, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # only rank 0 runs the CPU arm
+    cores = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle as O
+    import gym_cooking_b200 as gcb
+    lv = O.parse_level(gcb.levels.level_text(LEVEL), HORIZON)
+    st = O.reset_state(lv, N_AGENTS, N_ENVS)
+    rng = np.random.RandomState(SEED)
+    acts = [rng.randint(0, 5, size=(N_ENVS, N_AGENTS)).astype(np.uint8) for _ in range(8)]
+    k = 0
+    for _ in range(args.warmup):
+        O.step_batch(lv, st, acts[k % 8], N_AGENTS, n_threads=cores, want_collisions=False)
+        k += 1
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        if k % HORIZON == 0:
+            st = O.reset_state(lv, N_AGENTS, N_ENVS)
+        O.step_batch(lv, st, acts[k % 8], N_AGENTS, n_threads=cores, want_collisions=False)
+        k += 1
+    dt = time.perf_counter() - t0
+    value = args.steps * N_ENVS * N_AGENTS / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "every step = one env.step over 2^20 envs on %d host threads "
+                                   "(C port of the reference's pure-Python step; the Python reference "
+                                   "itself measured 1.3e3 agent-steps/s per core, BASELINE.md)" % cores},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gym_cooking_b200 as gcb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident workload: RING independent 2^20-env batches with their action streams ----
+    ring = [gcb.KitchenBatch(LEVEL, N_AGENTS, N_ENVS, HORIZON, device=dev) for _ in range(RING)]
+    env0 = rank * RING * N_ENVS  # global env indices: results do not depend on the GPU count
+    actions = [kb.random_actions(HORIZON, env0=env0 + r * N_ENVS, seed=SEED) for r, kb in enumerate(ring)]
+    local_t = [0] * RING
+    launches = 0
+
+    def do_step(k):
+        nonlocal launches
+        r = k % RING
+        if local_t[r] == HORIZON:  # every env of this batch has timed out: start new episodes
+            ring[r].reset()
+            local_t[r] = 0
+            launches += 1  # gc_env_reset (the reward/done memset is torch's, not counted)
+        ring[r].step(actions[r][local_t[r]])
+        local_t[r] += 1
+        launches += 1
+
+    k = 0
+    for _ in range(max(args.warmup, 3)):
+        do_step(k)
+        k += 1
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        do_step(k)
+        k += 1
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    timed_launches = launches
+    value = world * args.steps * N_ENVS * N_AGENTS / (ms * 1e-3)
+
+    # ---- end to end through the public API: host actions in, reward/done bytes out, per step ----
+    ns = argparse.Namespace(level=LEVEL, num_agents=N_AGENTS, max_num_timesteps=HORIZON, max_num_subtasks=14,
+                            seed=1, model1=None, model2=None, model3=None, model4=None)
+    env = gcb.OvercookedEnvironment(ns, num_envs=N_ENVS, device=dev, track_collisions=False)
+    env.reset()
+    host_actions = [actions[0][s].cpu().pin_memory() for s in range(8)]
+    e2e_steps = max(1, min(args.steps, 400))
+    for s in range(3):
+        env.step(host_actions[s % 8])
+    env.reset()
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        if s and s % HORIZON == 0:
+            env.reset()
+        env.step(host_actions[s % 8])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * e2e_steps * N_ENVS * N_AGENTS / e2e_s
+
+    # ---- the one collective of this path: reduce the episode statistics over ranks ----
+    stats = torch.zeros(gcb._lib.STATS_LEN, dtype=torch.int64, device=dev)
+    for kb in ring:
+        kb.stats(out=stats)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)  # NCCL over NVLink, 1064 bytes
+    stats = stats.cpu().tolist()
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        launch_s = ms * 1e-3 / args.steps  # average gc_env_step launch, launch gaps included
+        achieved = BYTES_PER_ENV_STEP * N_ENVS / launch_s / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        cpu_value, cpu_dt = cpu_port_rate(1 << 18, HORIZON, 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_ENVS * N_AGENTS,
+                    "d2h_bytes_per_step": N_ENVS, "steps": e2e_steps,
+                    "api": "OvercookedEnvironment(arglist, num_envs=2^20).step(pinned uint8[N][2])"},
+            "gpu_launches": timed_launches,
+            "roofline": {"bound": "hbm", "kernel": "step_kernel<2,4,false> (gc_env_step)", "achieved": achieved,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                         "bytes_per_launch": BYTES_PER_ENV_STEP * N_ENVS, "launch_us": launch_s * 1e6,
+                         "traffic": traffic},
+            "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "2^18 envs x 100 steps of the same action stream, %.1f s" % cpu_dt},
+            "episode_stats": {"episodes": stats[0], "successes": stats[1], "sum_t_done": stats[2],
+                              "running": stats[4], "reduced_with": "nccl all_reduce" if world > 1 else "single rank"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 400:
+            args.steps = 400  # bounded: ~30 ms per CPU step
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

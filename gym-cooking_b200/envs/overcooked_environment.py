@@ -1,0 +1,282 @@
+"""Drop-in `OvercookedEnvironment` with the reference's gym-style surface, batched underneath.
+
+Reference: gym_cooking/envs/overcooked_environment.py - ctor(arglist) :37, reset() :201-250,
+step(action_dict) :255-306 returning (obs, reward, done, info) with
+info = {"t", "obs", "image_obs", "done", "termination_info"}, done() :316-363, reward() :365-376,
+get_repr() :50-62, get_agent_names() :393-394, is_collision() :671-718, and the attributes
+world / sim_agents / recipes / all_subtasks / agent_actions / obs_tm1 / collisions /
+termination_info / successful / filename / t.
+
+`OvercookedEnvironment(arglist)` is the single-episode drop-in for main.main_loop (main.py:85-117):
+`step` takes the reference `action_dict {name: (dx, dy)}`.  `OvercookedEnvironment(arglist,
+num_envs=N)` runs N episodes of the same level; `step` then takes a uint8[N][num_agents] tensor
+(pinned host or CUDA) and returns reward / done tensors, `obs[i]` lazily materialises the
+reference-shaped view of env i.  The facade only marshals: every transition runs in
+gc_env_step; there is no CPU fallback.
+"""
+import copy
+from collections import namedtuple
+
+import torch
+
+from .. import _lib, engine, levels as _levels, recipe_planner
+from ..utils.agent import COLORS, SimAgent
+from ..utils.core import Object
+from ..utils.world import World
+
+CollisionRepr = namedtuple("CollisionRepr", "time agent_names agent_locations")
+
+TERMINATION_TIMEOUT = "Terminating because passed {} timesteps"
+TERMINATION_SUCCESS = "Terminating because all deliveries were completed"
+
+
+class EnvView:
+    """What the reference hands out as `obs` (a copy of the env): world + sim_agents + t."""
+
+    def __init__(self, env, words, actions=None):
+        self.arglist = env.arglist
+        self.t = (int(words[0]) >> 24) & 127
+        st = engine.decode_state(words, env.num_agents)
+        self.world = World(env.level, env.arglist)
+        self.world.set_objects(st["objects"])
+        self.sim_agents = []
+        for i, (x, y, hold) in enumerate(st["agents"]):
+            a = SimAgent("agent-%d" % (i + 1), COLORS[i], (x, y))
+            if hold:
+                a.holding = next(o for o in self.world.objects[Object((x, y), hold).name]
+                                 if o.is_held and o.location == (x, y) and o.mask == hold)
+            if actions is not None:
+                a.action = engine.ACTIONS[int(actions[i])]
+            self.sim_agents.append(a)
+        self.recipes = env.recipes
+        self.all_subtasks = env.all_subtasks
+        self.agent_actions = {a.name: a.action for a in self.sim_agents}
+        self._words = tuple(int(w) & 0xFFFFFFFF for w in words)
+        self._env = env
+
+    def get_repr(self):
+        return self.world.get_repr() + tuple(a.get_repr() for a in self.sim_agents)
+
+    def get_agent_names(self):
+        return [a.name for a in self.sim_agents]
+
+    def __eq__(self, other):
+        return self.get_repr() == other.get_repr()
+
+    def __copy__(self):
+        return EnvView(self._env, self._words, [engine.ACTION_INDEX[a.action] for a in self.sim_agents])
+
+    @property
+    def obs_tm1(self):
+        return self._env.obs_tm1
+
+    def is_collision(self, *a, **k):
+        return self._env.is_collision(*a, **k)
+
+
+class BatchObs:
+    """Handle over the packed uint32[N][4] state; `obs[i]` builds the view of env i on demand."""
+
+    def __init__(self, env, state):
+        self._env = env
+        self.state = state  # CUDA tensor (aliases the live state; clone it to keep a snapshot)
+
+    def __len__(self):
+        return self.state.shape[0]
+
+    def __getitem__(self, i):
+        return EnvView(self._env, self.state[i].tolist())
+
+
+class OvercookedEnvironment:
+    """Environment object for Overcooked (batched)."""
+
+    metadata = {}
+
+    def __init__(self, arglist, num_envs=1, device=None, track_collisions=None):
+        self.arglist = arglist
+        self.num_envs = int(num_envs)
+        self.num_agents = int(arglist.num_agents)
+        self.t = 0
+        self.set_filename()
+        self.rep = []
+        self.collisions = []
+        self.termination_info = ""
+        self.successful = False
+        self._device = device
+        self._track = (self.num_envs == 1) if track_collisions is None else track_collisions
+        self._kb = None
+        self._pinned_rd = None
+        self._dev_actions = None
+
+    def set_filename(self):  # env:116-128
+        a = self.arglist
+        self.filename = "{}_agents{}_seed{}".format(a.level, a.num_agents, getattr(a, "seed", 1))
+        for k in (1, 2, 3, 4):
+            m = getattr(a, "model%d" % k, None)
+            if m is not None:
+                self.filename += "_model{}-{}".format(k, m)
+
+    # -- reset ---------------------------------------------------------------------------
+    def reset(self):
+        a = self.arglist
+        max_t = int(getattr(a, "max_num_timesteps", 100) or 0)
+        if self._kb is None:
+            self._kb = engine.KitchenBatch(a.level, self.num_agents, self.num_envs, max_t, device=self._device,
+                                           track_collisions=self._track)
+            self.level = self._kb.levels[0]
+            text = _levels.resolve_level(a.level)
+            blocks = text.split("\n\n")
+            self.recipes = [ln for ln in blocks[1].split("\n") if ln]
+            kinds = []
+            for k in range(self.level.n_objects):
+                m = self.level.object_init[k] & 0x7F
+                kinds.append({1: "Tomato", 2: "Lettuce", 4: "Onion", 8: "Plate"}[m])
+            self.all_subtasks = recipe_planner.level_subtasks(self.recipes, kinds,
+                                                              int(getattr(a, "max_num_subtasks", 14)))
+            self._executed = torch.empty((self.num_envs, self.num_agents), dtype=torch.uint8, device=self._kb.device)
+            self._pinned_rd = torch.empty(self.num_envs, dtype=torch.uint8).pin_memory()
+            self._dev_actions = torch.empty((self.num_envs, self.num_agents), dtype=torch.uint8, device=self._kb.device)
+        else:
+            self._kb.reset()
+        self.t = 0
+        self.collisions = []
+        self.termination_info = ""
+        self.successful = False
+        self.agent_actions = {}
+        self._sync_view()
+        self.obs_tm1 = copy.copy(self._view) if self.num_envs == 1 else None
+        return self._obs()
+
+    def close(self):
+        return
+
+    # -- step ----------------------------------------------------------------------------
+    def step(self, action_dict):
+        """Single env: `action_dict {agent name: (dx, dy)}` -> (obs, reward, done, info) exactly as
+        env:255-306.  Batched: uint8[N][num_agents] tensor -> (BatchObs, reward[N], done[N], info)."""
+        kb = self._kb
+        if isinstance(action_dict, dict):
+            if self.num_envs != 1:
+                raise ValueError("an action_dict drives a single env; pass a [N, num_agents] tensor")
+            names = self.get_agent_names()
+            acts = torch.tensor([[engine.ACTION_INDEX[tuple(action_dict[nm])] for nm in names]], dtype=torch.uint8)
+        else:
+            acts = action_dict
+        self.t += 1
+        if acts.is_cuda:
+            dev_acts = acts
+        else:
+            self._dev_actions.copy_(acts, non_blocking=True)  # H2D (async when `acts` is pinned)
+            dev_acts = self._dev_actions
+        if self.num_envs == 1:
+            words_before = kb.state[0].tolist()
+            coll_before = int(kb.collisions[0]) if kb.collisions is not None else 0
+        kb.step(dev_acts, executed_out=self._executed)
+        self._pinned_rd.copy_(kb.reward_done, non_blocking=True)  # D2H of the step's result
+        torch.cuda.current_stream(kb.device).synchronize()
+        rd = self._pinned_rd
+        if self.num_envs > 1:
+            done, reward = (rd & 1).bool(), (rd >> 1) & 1
+            info = {"t": self.t, "obs": None, "image_obs": None, "done": done, "termination_info": ""}
+            obs = self._obs()
+            info["obs"] = obs
+            return obs, reward, done, info
+        # single env: rebuild the reference-shaped bookkeeping
+        executed = self._executed[0].tolist()
+        names = self.get_agent_names()
+        self.obs_tm1 = EnvView(self, words_before, executed)  # state before, actions after collisions (env:273)
+        if kb.collisions is not None and int(kb.collisions[0]) > coll_before:
+            self._record_collisions(words_before, acts[0].tolist())
+        self._sync_view()
+        for i, nm in enumerate(names):
+            self.agent_actions[nm] = engine.ACTIONS[executed[i]]
+            self._view.sim_agents[i].action = engine.ACTIONS[executed[i]]
+        done = bool(int(rd[0]) & 1)
+        self.successful = bool(int(rd[0]) & 2)
+        self._set_termination(done)
+        new_obs = self._obs()
+        info = {"t": self.t, "obs": new_obs, "image_obs": None, "done": done,
+                "termination_info": self.termination_info}
+        return new_obs, self.reward(), done, info
+
+    def _set_termination(self, done):
+        max_t = int(getattr(self.arglist, "max_num_timesteps", 100) or 0)
+        if done and not self.successful:
+            self.termination_info = TERMINATION_TIMEOUT.format(max_t)
+        elif done:
+            self.termination_info = TERMINATION_SUCCESS
+        else:
+            self.termination_info = ""
+
+    def _record_collisions(self, words_before, actions):
+        """CollisionRepr list of env:747-752, recomputed on the host for the single-env facade
+        from the pre-step state (the kernel only counts them)."""
+        st = engine.decode_state(words_before, self.num_agents)
+        names = self.get_agent_names()
+        locs = [(x, y) for (x, y, _) in st["agents"]]
+        for i in range(self.num_agents):
+            for j in range(i + 1, self.num_agents):
+                ex = self.is_collision(locs[i], locs[j], engine.ACTIONS[actions[i]], engine.ACTIONS[actions[j]])
+                if not all(ex):
+                    self.collisions.append(CollisionRepr(time=self.t, agent_names=[names[i], names[j]],
+                                                         agent_locations=[locs[i], locs[j]]))
+
+    # -- queries ---------------------------------------------------------------------------
+    def done(self):
+        rd = self._kb.reward_done
+        if self.num_envs == 1:
+            d = bool(int(rd[0]) & 1)
+            self.successful = bool(int(rd[0]) & 2)
+            self._set_termination(d)
+            return d
+        return (rd & 1).bool()
+
+    def reward(self):
+        if self.num_envs == 1:
+            return 1 if self.successful else 0
+        return (self._kb.reward_done >> 1) & 1
+
+    def get_repr(self):
+        return self._view.get_repr()
+
+    def get_agent_names(self):
+        return ["agent-%d" % (i + 1) for i in range(self.num_agents)]
+
+    def is_collision(self, agent1_loc, agent2_loc, agent1_action, agent2_action):
+        """env:671-718 on the static map (host helper for planners and the collision log)."""
+        def nxt(loc, act):
+            n = (loc[0] + act[0], loc[1] + act[1])
+            return loc if self.world.loc_to_gridsquare[n].collidable else n
+        n1, n2 = nxt(agent1_loc, agent1_action), nxt(agent2_loc, agent2_action)
+        execute = [True, True]
+        if n1 == n2:
+            if n1 == agent1_loc and tuple(agent1_action) != (0, 0):
+                execute[1] = False
+            elif n2 == agent2_loc and tuple(agent2_action) != (0, 0):
+                execute[0] = False
+            else:
+                execute = [False, False]
+        elif agent1_loc == n2 and agent2_loc == n1:
+            execute = [False, False]
+        return execute
+
+    # -- internals -------------------------------------------------------------------------
+    def _sync_view(self):
+        self._view = EnvView(self, self._kb.state[0].tolist())
+        self.world = self._view.world
+        self.sim_agents = self._view.sim_agents
+
+    def _obs(self):
+        if self.num_envs == 1:
+            return copy.copy(self._view)
+        return BatchObs(self, self._kb.state)
+
+    @property
+    def state(self):
+        """packed uint32[N][4] CUDA tensor (include/gymcook.h)."""
+        return self._kb.state
+
+    @property
+    def batch(self):
+        return self._kb

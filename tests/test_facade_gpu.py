@@ -1,0 +1,85 @@
+"""The reference-shaped facade (OvercookedEnvironment / obs / info) on the GPU path."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gym_cooking_b200 as gcb
+from gym_cooking_b200.utils.core import name_to_mask
+
+pytestmark = pytest.mark.gpu
+
+
+def _arglist(level, n_agents, max_t=100):
+    return argparse.Namespace(level=level, num_agents=n_agents, max_num_timesteps=max_t, max_num_subtasks=14,
+                              seed=1, model1="bd", model2="bd", model3=None, model4=None, play=False, record=False,
+                              with_image_obs=False)
+
+
+def _canonical(obs):
+    """same reduction the golden generator applies to the reference's env.get_repr()"""
+    agents, items = [], []
+    for entry in obs.get_repr():
+        if getattr(entry, "_fields", None) == ("name", "location", "holding"):
+            agents.append((entry.location[1] * 8 + entry.location[0], name_to_mask(entry.holding)))
+            continue
+        for o in entry:
+            if getattr(o, "_fields", None) == ("name", "location", "is_held"):
+                items.append((name_to_mask(o.name) << 7) | ((o.location[1] * 8 + o.location[0]) << 1) | int(o.is_held))
+    return agents, sorted(items)
+
+
+def test_single_env_drop_in_follows_golden_trace(golden_dir):
+    tr = np.load(os.path.join(golden_dir, "env_traces.npz"))
+    rows = [r for r in range(tr["meta"].shape[0]) if tr["meta"][r, 1] in (2, 3) and tr["meta"][r, 3] == 0][:6]
+    rows += [next(r for r in range(tr["meta"].shape[0]) if tr["reward"][r, tr["length"][r]] == 1)]
+    for r in rows:
+        lvl, n_agents, max_t, _ = (int(v) for v in tr["meta"][r])
+        env = gcb.make("gym_cooking:overcookedEnv-v0", arglist=_arglist(str(tr["levels"][lvl]), n_agents, max_t))
+        obs = env.reset()
+        assert obs.t == 0 and len(obs.sim_agents) == n_agents
+        names = env.get_agent_names()
+        ncoll = 0
+        for s in range(int(tr["length"][r])):
+            ad = {names[i]: gcb.ACTIONS[int(tr["actions"][r, s, i])] for i in range(n_agents)}
+            state_before = _canonical(env)
+            obs, reward, done, info = env.step(ad)
+            assert set(info) == {"t", "obs", "image_obs", "done", "termination_info"}
+            agents, items = _canonical(obs)
+            assert agents == [tuple(int(v) for v in a) for a in tr["agents"][r, s + 1, :n_agents]]
+            assert items == [int(k) for k in tr["keys"][r, s + 1] if k != 0x3FFF]
+            assert info["t"] == env.t == s + 1 == obs.t
+            assert done == bool(tr["done"][r, s + 1]) == env.done()
+            assert reward == int(tr["reward"][r, s + 1]) == env.reward()
+            assert [gcb.ACTION_INDEX[env.agent_actions[nm]] for nm in names] == \
+                [int(v) for v in tr["executed"][r, s + 1, :n_agents]]
+            assert _canonical(env.obs_tm1) == state_before  # obs_tm1 = state before, executed actions (env:273)
+            assert [gcb.ACTION_INDEX[a.action] for a in env.obs_tm1.sim_agents] == \
+                [int(v) for v in tr["executed"][r, s + 1, :n_agents]]
+            ncoll += int(tr["ncoll"][r, s + 1])
+            assert len(env.collisions) == ncoll
+        if tr["done"][r, tr["length"][r]]:
+            expect = ("Terminating because all deliveries were completed" if env.successful
+                      else "Terminating because passed %d timesteps" % max_t)
+            assert env.termination_info == expect
+
+
+def test_batched_facade_host_actions():
+    n = 4096
+    env = gcb.OvercookedEnvironment(_arglist("partial-divider_tl", 2), num_envs=n)
+    obs = env.reset()
+    ref = gcb.KitchenBatch("partial-divider_tl", 2, n, 100)
+    acts = ref.random_actions(30, seed=9)
+    for s in range(30):
+        host = acts[s].cpu().pin_memory()
+        obs, reward, done, info = env.step(host)
+        ref.step(acts[s])
+        assert not reward.is_cuda and reward.shape == (n,) and done.dtype == torch.bool
+    assert torch.equal(env.state, ref.state)
+    view = obs[17]
+    w = ref.state[17].tolist()
+    assert view.t == 30 and [a.location for a in view.sim_agents] == \
+        [(x, y) for (x, y, _) in gcb.decode_state(w, 2)["agents"]]
+    assert len(env.all_subtasks) == 6 and str(env.all_subtasks[0]) == "Chop(Tomato)"
