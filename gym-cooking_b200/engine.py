@@ -26,6 +26,7 @@ class KitchenBatch:
             raise ValueError("need at least one level")
         self.level_names = names
         self.levels = [_lib.parse_level(_levels.resolve_level(nm), max_num_timesteps) for nm in names]
+        self.subtasks = [self._attach_subtasks(lv) for lv in self.levels]
         self._level_arr = _lib.level_array(self.levels)
         self.n_levels = len(names)
         self.num_agents = int(num_agents)
@@ -47,6 +48,22 @@ class KitchenBatch:
         else:
             self.level_id = None
         self.reset()
+
+    @staticmethod
+    def _attach_subtasks(lv):
+        """Run the host recipe planner for this level and store the subtasks, in mask form, in the
+        level tables (gc_level_set_subtasks) so that pairs can name them by index."""
+        from . import recipe_planner as rp
+        recipes = [{1: "SimpleTomato", 2: "SimpleLettuce", 3: "Salad", 4: "OnionSalad"}[lv.recipe_code[g]]
+                   for g in range(lv.n_goals)]
+        kinds = [{1: "Tomato", 2: "Lettuce", 4: "Onion", 8: "Plate"}[lv.object_init[k] & 0x7F]
+                 for k in range(lv.n_objects)]
+        subtasks = rp.level_subtasks(recipes, kinds)
+        arr = (_lib.Subtask * len(subtasks))()
+        for k, st in enumerate(subtasks):
+            arr[k].kind, arr[k].a, arr[k].b, arr[k].goal = rp.subtask_masks(st)
+        _lib.check(_lib.load().gc_level_set_subtasks(C.byref(lv), arr, len(subtasks)))
+        return subtasks
 
     # -- marshalling helpers ------------------------------------------------------------
     def _lv(self):

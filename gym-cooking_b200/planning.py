@@ -1,0 +1,64 @@
+"""Batched planner entry points (paths B and C) over CUDA tensors - thin marshalling of
+gc_bd_posterior_*, gc_lower_bound and gc_subtask_q (include/gymcook.h)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PERIMETER_NOT_DOABLE = 28.0  # a 7x7 kitchen: lower bound >= world.perimeter means "not doable" (bd:156)
+
+
+def bd_posterior(probs, alive, hyp_pair, pair_w, qdiff, n_valid, act_idx, beta):
+    """One Bayesian-Delegation posterior update per row, in place on `probs` ([n][H] float32/64).
+    Restates BayesianDelegator.bayes_update (bd:1045-1072) on dumped inputs - see gymcook.h."""
+    lib = _lib.load()
+    n, H = probs.shape
+    P, A = qdiff.shape[1], qdiff.shape[2]
+    E = hyp_pair.shape[2]
+    if qdiff.dtype != probs.dtype:
+        raise _lib.GcError("probs and qdiff must share a dtype")
+    fn = {torch.float32: lib.gc_bd_posterior_f32, torch.float64: lib.gc_bd_posterior_f64}[probs.dtype]
+    u8 = torch.uint8
+    with torch.cuda.device(probs.device):
+        _lib.check(fn(_lib.ptr(probs), _lib.ptr(alive, u8), _lib.ptr(hyp_pair, u8), _lib.ptr(pair_w, u8),
+                      _lib.ptr(qdiff), _lib.ptr(n_valid, u8), _lib.ptr(act_idx, u8), float(beta), n, H, P, A, E,
+                      _lib.stream_ptr(probs.device)))
+    return probs
+
+
+def _pairs_array(pairs):
+    """[(subtask index, agent i, agent j or None)] -> host uint8[n_pairs][3]."""
+    arr = np.array([[s, i, 255 if j is None else j] for (s, i, j) in pairs], dtype=np.uint8).reshape(-1, 3)
+    return np.ascontiguousarray(arr)
+
+
+def lower_bound(batch, pairs, out=None):
+    """env.get_lower_bound_for_subtask_given_objs (env:594-664) for every (env, pair) of a
+    KitchenBatch -> float32[N][n_pairs].  The levels of `batch` must carry their subtasks
+    (KitchenBatch.set_subtasks)."""
+    lib = _lib.load()
+    arr = _pairs_array(pairs)
+    with torch.cuda.device(batch.device):
+        if out is None:
+            out = torch.empty((batch.num_envs, len(pairs)), dtype=torch.float32, device=batch.device)
+        _lib.check(lib.gc_lower_bound(batch._lv(), batch.n_levels, _lib.ptr(batch.level_id), _lib.ptr(batch.state),
+                                      arr.ctypes.data_as(C.c_void_p), len(pairs), _lib.ptr(out), batch.num_envs,
+                                      batch.num_agents, batch._stream()))
+    return out
+
+
+def subtask_q(batch, pairs, want_q=True):
+    """Exact level-0 V* / Q(start, .) for every (env, pair): returns (v[N][P], q[N][P][25] or None,
+    status uint8[N][P])."""
+    lib = _lib.load()
+    arr = _pairs_array(pairs)
+    with torch.cuda.device(batch.device):
+        v = torch.empty((batch.num_envs, len(pairs)), dtype=torch.float32, device=batch.device)
+        q = torch.empty((batch.num_envs, len(pairs), 25), dtype=torch.float32, device=batch.device) if want_q else None
+        status = torch.empty((batch.num_envs, len(pairs)), dtype=torch.uint8, device=batch.device)
+        _lib.check(lib.gc_subtask_q(batch._lv(), batch.n_levels, _lib.ptr(batch.level_id), _lib.ptr(batch.state),
+                                    arr.ctypes.data_as(C.c_void_p), len(pairs), _lib.ptr(v), _lib.ptr(q),
+                                    _lib.ptr(status), batch.num_envs, batch.num_agents, batch._stream()))
+    return v, q, status

@@ -1,0 +1,344 @@
+"""Golden fixtures for paths B and C, produced by running the unmodified reference.
+Invoked through oracle/gen_golden.py (`lb`, `brtdp`, `bd`).  Build container only.
+
+  lb     env.get_lower_bound_for_subtask_given_objs (env:594-664) on sampled states, for every
+         (subtask, agent set)                                  -> tests/golden/lower_bounds.npz
+  brtdp  E2E_BRTDP.get_next_action(..., other_agent_planners={}) (e2e_brtdp.py:987-1076): v_l, v_u at
+         cur_state and Q_l per action                          -> tests/golden/brtdp_values.npz
+  bd     BayesianDelegator.bayes_update (bd:1026-1072): prior, per-(alloc, t) softmax inputs, taken
+         action index, weights -> posterior                    -> tests/golden/bd_posteriors.npz
+"""
+import copy
+import itertools
+import os
+import random
+import sys
+import time
+from multiprocessing import Pool
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, _HERE)
+import ref_harness as H  # noqa: E402
+from gen_golden import GOLDEN, LEVELS, DELTA, walker_actions  # noqa: E402
+
+ST_CHOP, ST_MERGE, ST_DELIVER = 1, 2, 3
+
+
+def pack_env(env):
+    """reference env -> packed uint32[4] (include/gymcook.h) with slots in canonical key order."""
+    t, agents, items = H.canonical(env)
+    w = [0, 0, 0, 0]
+    for i, (x, y, _) in enumerate(agents):
+        w[0] |= (y * 8 + x) << (6 * i)
+    w[0] |= (t & 127) << 24
+    slots = []
+    used = [False] * len(agents)
+    for (m, x, y, held) in sorted(items, key=lambda it: (it[0] << 7) | ((it[2] * 8 + it[1]) << 1) | it[3]):
+        if held:
+            i = next(i for i, (ax, ay, hm) in enumerate(agents) if (ax, ay) == (x, y) and hm == m and not used[i])
+            used[i] = True
+            slots.append(m | ((i + 1) << 13))
+        else:
+            slots.append(m | ((y * 8 + x) << 7))
+    slots += [0xE000] * (6 - len(slots))
+    for k, s in enumerate(slots):
+        w[1 + k // 2] |= s << (16 * (k % 2))
+    return w
+
+
+def subtask_masks(subtask):
+    """reference Action -> (kind, a, b, goal) via the reference's own nav_utils.get_subtask_obj."""
+    ref = H.load_reference()
+    ru, nu = ref["recipe_utils"], ref["nav_utils"]
+    start, goal = nu.get_subtask_obj(subtask)
+    if isinstance(subtask, ru.Chop):
+        return (ST_CHOP, H.name_to_mask(start.full_name), 0, H.name_to_mask(goal.full_name))
+    if isinstance(subtask, ru.Merge):
+        return (ST_MERGE, H.name_to_mask(start[0].full_name), H.name_to_mask(start[1].full_name),
+                H.name_to_mask(goal.full_name))
+    if isinstance(subtask, ru.Deliver):
+        return (ST_DELIVER, H.name_to_mask(start.full_name), 0, H.name_to_mask(goal.full_name))
+    raise ValueError(subtask)
+
+
+def sample_env(level, n_agents, seed, n_steps, eps=0.25):
+    """A reference env advanced n_steps with the goal-directed walker (None if it crashed/ended)."""
+    rng = np.random.RandomState(seed)
+    env = H.make_env(level, n_agents, 100)
+    names = env.get_agent_names()
+    targets = [None] * n_agents
+    for _ in range(n_steps):
+        acts = walker_actions(env, rng, eps, targets)
+        try:
+            with H.quiet():
+                _, _, done, _ = env.step({names[i]: DELTA[a] for i, a in enumerate(acts)})
+        except (AssertionError, AttributeError):
+            return None
+        if done:
+            return None
+    return env
+
+
+def agent_sets(n_agents):
+    names = ["agent-%d" % (i + 1) for i in range(n_agents)]
+    out = [((i,), (names[i],)) for i in range(n_agents)]
+    out += [((i, j), (names[i], names[j])) for i, j in itertools.combinations(range(n_agents), 2)]
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# lb
+# ---------------------------------------------------------------------------------------
+def _lb_job(args):
+    level, n_agents, seed, n_steps = args
+    env = sample_env(level, n_agents, seed, n_steps)
+    if env is None:
+        return []
+    ref = H.load_reference()
+    nu = ref["nav_utils"]
+    rows = []
+    words = pack_env(env)
+    for st in env.all_subtasks:
+        start, goal = nu.get_subtask_obj(st)
+        action_obj = nu.get_subtask_action_obj(st)
+        masks = subtask_masks(st)
+        for idx, names in agent_sets(n_agents):
+            lb = env.get_lower_bound_for_subtask_given_objs(
+                subtask=st, subtask_agent_names=names, start_obj=start, goal_obj=goal, subtask_action_obj=action_obj)
+            rows.append((LEVELS.index(level), n_agents, words, masks, idx[0], idx[1] if len(idx) > 1 else 255, float(lb)))
+    return rows
+
+
+def gen_lb():
+    jobs, seed = [], 5000
+    for level in LEVELS:
+        for n_agents in (1, 2, 3, 4):
+            for n_steps in (0, 3, 8, 15, 25, 40, 60):
+                seed += 1
+                jobs.append((level, n_agents, seed, n_steps))
+    with Pool(8) as pool:
+        res = pool.map(_lb_job, jobs, chunksize=2)
+    rows = [r for rr in res for r in rr]
+    np.savez_compressed(
+        os.path.join(GOLDEN, "lower_bounds.npz"), levels=np.array(LEVELS),
+        level=np.array([r[0] for r in rows], dtype=np.uint8), n_agents=np.array([r[1] for r in rows], dtype=np.uint8),
+        state=np.array([r[2] for r in rows], dtype=np.uint32), subtask=np.array([r[3] for r in rows], dtype=np.uint8),
+        agent_i=np.array([r[4] for r in rows], dtype=np.uint8), agent_j=np.array([r[5] for r in rows], dtype=np.uint8),
+        lb=np.array([r[6] for r in rows], dtype=np.float64))
+    lbs = np.array([r[6] for r in rows])
+    print("lower bounds:", len(rows), "rows; not-doable (>= perimeter):", int((lbs >= 28).sum()),
+          "distinct values:", len(set(lbs.tolist())))
+
+
+# ---------------------------------------------------------------------------------------
+# brtdp
+# ---------------------------------------------------------------------------------------
+def _brtdp_job(args):
+    level, n_agents, seed, n_steps, budget_s = args
+    env = sample_env(level, n_agents, seed, n_steps)
+    if env is None:
+        return []
+    ref = H.load_reference()
+    nu, brtdp = ref["nav_utils"], ref["brtdp"]
+    np.random.seed(seed)
+    random.seed(seed)
+    rows = []
+    words = pack_env(env)
+    t_start = time.time()
+    for st in env.all_subtasks:
+        start, goal = nu.get_subtask_obj(st)
+        action_obj = nu.get_subtask_action_obj(st)
+        masks = subtask_masks(st)
+        for idx, names in agent_sets(n_agents):
+            if time.time() - t_start > budget_s:
+                return rows
+            lb = env.get_lower_bound_for_subtask_given_objs(
+                subtask=st, subtask_agent_names=names, start_obj=start, goal_obj=goal, subtask_action_obj=action_obj)
+            if lb >= env.world.perimeter:  # pruned as not doable in real runs (bd:98-156)
+                continue
+            planner = brtdp.E2E_BRTDP(alpha=0.01, tau=2, cap=75, main_cap=100)
+            t0 = time.time()
+            try:
+                with H.quiet():
+                    action = planner.get_next_action(env=copy.copy(env), subtask=st, subtask_agent_names=names,
+                                                     other_agent_planners={})
+            except (AssertionError, AttributeError, KeyError):
+                continue
+            key = (planner.cur_state.get_repr(), st)
+            v_l, v_u = planner.v_l[key], planner.v_u[key]
+            q = np.full(25, np.inf)
+            if action is not None:
+                with H.quiet():
+                    acts = planner.get_actions(state_repr=planner.cur_state.get_repr())
+                    for a in acts:
+                        qa = planner.Q(state=planner.cur_state, action=a, value_f=planner.v_l)
+                        if len(names) == 1:
+                            q[DELTA.index(tuple(a))] = qa
+                        else:
+                            q[5 * DELTA.index(tuple(a[0])) + DELTA.index(tuple(a[1]))] = qa
+            rows.append((LEVELS.index(level), n_agents, words, masks, idx[0], idx[1] if len(idx) > 1 else 255,
+                         float(lb), float(v_l), float(v_u), q, 1 if action is None else 0, time.time() - t0,
+                         len(planner.v_l)))
+    return rows
+
+
+def gen_brtdp():
+    jobs, seed = [], 9000
+    for level in LEVELS:
+        for n_agents in (2, 3):
+            for n_steps in (0, 6, 14, 24, 36):
+                seed += 1
+                jobs.append((level, n_agents, seed, n_steps, 240.0))
+    with Pool(8) as pool:
+        res = pool.map(_brtdp_job, jobs, chunksize=1)
+    rows = [r for rr in res for r in rr]
+    np.savez_compressed(
+        os.path.join(GOLDEN, "brtdp_values.npz"), levels=np.array(LEVELS),
+        level=np.array([r[0] for r in rows], dtype=np.uint8), n_agents=np.array([r[1] for r in rows], dtype=np.uint8),
+        state=np.array([r[2] for r in rows], dtype=np.uint32), subtask=np.array([r[3] for r in rows], dtype=np.uint8),
+        agent_i=np.array([r[4] for r in rows], dtype=np.uint8), agent_j=np.array([r[5] for r in rows], dtype=np.uint8),
+        lb=np.array([r[6] for r in rows]), v_l=np.array([r[7] for r in rows]), v_u=np.array([r[8] for r in rows]),
+        q_l=np.array([r[9] for r in rows]), at_goal=np.array([r[10] for r in rows], dtype=np.uint8),
+        seconds=np.array([r[11] for r in rows]), n_states=np.array([r[12] for r in rows], dtype=np.int32))
+    conv = sum(1 for r in rows if r[8] - r[7] <= 0.01)
+    print("brtdp rows:", len(rows), "converged:", conv, "joint:", sum(1 for r in rows if r[5] != 255),
+          "total s:", sum(r[11] for r in rows))
+
+
+# ---------------------------------------------------------------------------------------
+# bd
+# ---------------------------------------------------------------------------------------
+def _bd_job(args):
+    level, n_agents, seed, n_steps, model, observer = args
+    env = sample_env(level, n_agents, seed, n_steps)
+    if env is None:
+        return None
+    ref = H.load_reference()
+    bd, brtdp = ref["bd"], ref["brtdp"]
+    np.random.seed(seed)
+    random.seed(seed)
+    rng = np.random.RandomState(seed)
+    names = env.get_agent_names()
+    planner = brtdp.E2E_BRTDP(alpha=0.01, tau=2, cap=75, main_cap=100)
+    dele = bd.BayesianDelegator(agent_name=names[observer], all_agent_names=names, model_type=model,
+                                planner=planner, none_action_prob=0.5)
+    # incomplete subtasks: drop those whose goal object already exists (a crude stand-in for
+    # RealAgent.refresh_subtasks; any subset is a legal input for this path)
+    incomplete = list(env.all_subtasks)
+    with H.quiet():
+        dele.set_priors(obs=copy.copy(env), incomplete_subtasks=incomplete, priors_type="uniform")
+    if not dele.probs.probs:
+        return None
+    # arbitrary (seeded) prior so that the fixture is not all-uniform
+    keys = dele.probs.enumerate_subtask_allocs()
+    pri = rng.rand(len(keys)) + 0.05
+    pri /= pri.sum()
+    for k, p in zip(keys, pri):
+        dele.probs.probs[k] = float(p)
+    # one real env step -> obs_tm1 / actions_tm1 exactly as RealAgent.update_subtasks passes them
+    targets = [None] * n_agents
+    acts = walker_actions(env, rng, 0.3, targets)
+    try:
+        with H.quiet():
+            env.step({names[i]: DELTA[a] for i, a in enumerate(acts)})
+    except (AssertionError, AttributeError):
+        return None
+    calls, soft = [], []
+    real_softmax = bd.sp.special.softmax
+    real_pna = dele.prob_nav_actions
+
+    def rec_softmax(x, *a, **k):
+        out = real_softmax(x, *a, **k)
+        soft.append((np.array(x, dtype=np.float64), np.array(out, dtype=np.float64)))
+        return out
+
+    def rec_pna(**kw):
+        n0 = len(soft)
+        p = real_pna(**kw)
+        assert len(soft) == n0 + 1
+        calls.append((kw["subtask"], tuple(kw["subtask_agent_names"]), float(p), soft[-1]))
+        return p
+
+    bd.sp.special.softmax = rec_softmax
+    dele.prob_nav_actions = rec_pna
+    prior_keys = list(keys)
+    prior = dict(dele.probs.probs)
+    t0 = time.time()
+    try:
+        with H.quiet():
+            dele.bayes_update(obs_tm1=copy.copy(env.obs_tm1), actions_tm1=env.agent_actions, beta=1.3)
+    except (AssertionError, AttributeError, KeyError) as exc:
+        return None
+    finally:
+        bd.sp.special.softmax = real_softmax
+    post = dict(dele.probs.probs)
+    # distinct likelihood rows
+    pair_index, pair_rows = {}, []
+    for (st, agents, p, (x, out)) in calls:
+        key = (str(st), agents)
+        if key in pair_index:
+            continue
+        act_idx = int(np.argmin(np.abs(out - p)))
+        assert abs(out[act_idx] - p) < 1e-15
+        pair_index[key] = len(pair_rows)
+        w = 1 if model == "greedy" else len(agents)
+        pair_rows.append((x / 1.3, act_idx, w))
+    hyps = []
+    for k in prior_keys:
+        alive = k in post
+        entries = []
+        if alive:
+            for t in k:
+                if model == "greedy" and names[observer] not in t.subtask_agent_names:
+                    continue
+                entries.append(pair_index[(str(t.subtask), tuple(t.subtask_agent_names))])
+        hyps.append((prior[k], alive, entries, post.get(k, 0.0)))
+    return dict(level=level, n_agents=n_agents, model=model, observer=observer, hyps=hyps, pairs=pair_rows,
+                seconds=time.time() - t0, n_calls=len(calls))
+
+
+def gen_bd():
+    jobs, seed = [], 13000
+    for level in ("open-divider_tomato", "partial-divider_tl", "open-divider_salad", "full-divider_salad",
+                  "partial-divider_tomato", "full-divider_tl"):
+        for (n_agents, model, reps) in ((2, "bd", 4), (2, "dc", 2), (2, "greedy", 2), (2, "up", 1), (3, "bd", 2),
+                                        (3, "dc", 1), (4, "dc", 1)):
+            for rep in range(reps):
+                seed += 1
+                jobs.append((level, n_agents, seed, [2, 9, 17, 30][rep % 4], model, seed % n_agents))
+    with Pool(8) as pool:
+        res = [r for r in pool.map(_bd_job, jobs, chunksize=1) if r is not None]
+    n = len(res)
+    H_max = max(len(r["hyps"]) for r in res)
+    P_max = max(len(r["pairs"]) for r in res)
+    A_max = max(max(len(p[0]) for p in r["pairs"]) for r in res)
+    E = 4
+    prior = np.zeros((n, H_max)); post = np.zeros((n, H_max))
+    alive = np.zeros((n, H_max), dtype=np.uint8)
+    hyp_pair = np.full((n, H_max, E), 255, dtype=np.uint8)
+    pair_w = np.zeros((n, P_max), dtype=np.uint8)
+    qdiff = np.zeros((n, P_max, A_max))
+    n_valid = np.zeros((n, P_max), dtype=np.uint8)
+    act_idx = np.zeros((n, P_max), dtype=np.uint8)
+    meta = []
+    for r, rec in enumerate(res):
+        for h, (p0, al, entries, p1) in enumerate(rec["hyps"]):
+            prior[r, h], alive[r, h], post[r, h] = p0, al, p1
+            hyp_pair[r, h, :len(entries)] = entries
+        for p, (x, ai, w) in enumerate(rec["pairs"]):
+            qdiff[r, p, :len(x)] = x
+            n_valid[r, p], act_idx[r, p], pair_w[r, p] = len(x), ai, w
+        meta.append("%s|%d|%s|%d|H=%d|P=%d" % (rec["level"], rec["n_agents"], rec["model"], rec["observer"],
+                                                len(rec["hyps"]), len(rec["pairs"])))
+    np.savez_compressed(os.path.join(GOLDEN, "bd_posteriors.npz"), meta=np.array(meta), beta=1.3, prior=prior,
+                        posterior=post, alive=alive, hyp_pair=hyp_pair, pair_w=pair_w, qdiff=qdiff,
+                        n_valid=n_valid, act_idx=act_idx)
+    print("bd posteriors:", n, "updates; H<=%d P<=%d A<=%d; total s %.0f" % (H_max, P_max, A_max,
+                                                                                 sum(r["seconds"] for r in res)))
+
+
+def main(what):
+    os.makedirs(GOLDEN, exist_ok=True)
+    {"lb": gen_lb, "brtdp": gen_brtdp, "bd": gen_bd}[what]()

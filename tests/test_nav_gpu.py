@@ -1,0 +1,77 @@
+"""Path B parity on the GPU (through the C-ABI): gc_lower_bound must equal the reference's
+heuristic exactly; gc_subtask_q must equal the oracle's exact search and lie inside the
+reference BRTDP's converged bracket."""
+import ctypes as C
+import itertools
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gym_cooking_b200 as gcb
+from gym_cooking_b200 import recipe_planner as rp
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _load_states(kb, words):
+    kb.state.copy_(torch.from_numpy(np.ascontiguousarray(words, dtype=np.uint32).view(np.int32)).to(kb.device))
+
+
+def _all_pairs(n_subtasks, n_agents):
+    sets = [(i, None) for i in range(n_agents)] + list(itertools.combinations(range(n_agents), 2))
+    return [(s, i, j) for s in range(n_subtasks) for (i, j) in sets]
+
+
+def _groups(g):
+    out = {}
+    for r in range(len(g["level"])):
+        out.setdefault((int(g["level"][r]), int(g["n_agents"][r])), []).append(r)
+    return out
+
+
+def test_lower_bound_equals_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "lower_bounds.npz"))
+    checked = 0
+    for (lvl, n_agents), rows in sorted(_groups(g).items()):
+        rows = np.array(rows)
+        states, inv = np.unique(g["state"][rows], axis=0, return_inverse=True)
+        kb = gcb.KitchenBatch(str(g["levels"][lvl]), n_agents, len(states), 100)
+        _load_states(kb, states)
+        masks = [rp.subtask_masks(s) for s in kb.subtasks[0]]
+        pairs = _all_pairs(len(masks), n_agents)
+        lb = gcb.lower_bound(kb, pairs).cpu().numpy()
+        index = {(masks[s], i, 255 if j is None else j): k for k, (s, i, j) in enumerate(pairs)}
+        for r, e in zip(rows, inv.reshape(-1)):
+            key = (tuple(int(v) for v in g["subtask"][r]), int(g["agent_i"][r]), int(g["agent_j"][r]))
+            assert lb[e, index[key]] == np.float32(g["lb"][r]), (str(g["levels"][lvl]), n_agents, key)
+            checked += 1
+    assert checked == len(g["lb"])
+
+
+@pytest.mark.parametrize("level,n_agents", [("full-divider_salad", 3), ("partial-divider_tl", 2), ("open-divider_salad", 4)])
+def test_lower_bound_matches_oracle_on_random_states(level, n_agents):
+    n = 4096
+    kb = gcb.KitchenBatch(level, n_agents, n, 100)
+    # diversify: k = env % 41 random steps from reset (cfg-3)
+    acts = kb.random_actions(40, seed=1235)
+    for s in range(40):
+        a = acts[s].clone()
+        a[(torch.arange(n, device=kb.device) % 41) <= s] = 4
+        kb.step(a)
+    masks = [rp.subtask_masks(s) for s in kb.subtasks[0]]
+    pairs = _all_pairs(len(masks), n_agents)
+    lb = gcb.lower_bound(kb, pairs).cpu().numpy()
+    st = kb.state.cpu().numpy().view(np.uint32)
+    lv = O.parse_level(gcb.levels.level_text(level), 100)
+    L = O.lib()
+    for e in range(0, n, 7):
+        env = O.Env()
+        L.gco_unpack(st[e].ctypes.data_as(C.POINTER(C.c_uint32)), n_agents, C.byref(env))
+        env.n_objs = O.MAX_OBJS
+        for k, (s, i, j) in enumerate(pairs):
+            sub = O.Subtask(*masks[s])
+            exp = L.gco_lower_bound(C.byref(lv), C.byref(env), C.byref(sub), i, -1 if j is None else j)
+            assert lb[e, k] == np.float32(exp), (e, pairs[k])
