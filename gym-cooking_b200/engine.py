@@ -65,6 +65,15 @@ class KitchenBatch:
         _lib.check(_lib.load().gc_level_set_subtasks(C.byref(lv), arr, len(subtasks)))
         return subtasks
 
+    def set_subtask_masks(self, masks, level=0):
+        """Replace level `level`'s subtask table by raw (kind, a, b, goal) tuples - e.g. the
+        reference's own list when it kept Merge(Tomato, Lettuce) instead of Merge(Lettuce, Tomato)."""
+        arr = (_lib.Subtask * len(masks))()
+        for k, m in enumerate(masks):
+            arr[k].kind, arr[k].a, arr[k].b, arr[k].goal = (int(v) for v in m)
+        _lib.check(self.lib.gc_level_set_subtasks(C.byref(self.levels[level]), arr, len(masks)))
+        self._level_arr = _lib.level_array(self.levels)
+
     # -- marshalling helpers ------------------------------------------------------------
     def _lv(self):
         return C.cast(self._level_arr, C.POINTER(_lib.Level))

@@ -58,7 +58,7 @@ extern "C" {
 #define GC_MAX_CELLS 64
 #define GC_GRID_STRIDE 8
 #define GC_MAX_SUBTASKS 16
-#define GC_MAX_PAIRS 32
+#define GC_MAX_PAIRS 128
 #define GC_MAX_JOINT_ACTIONS 25
 #define GC_MAX_HYPOTHESES 96
 #define GC_MAX_LEVELS 16
