@@ -351,6 +351,9 @@ static int* table_slot(table_t* t, const uint32_t w[4]) {
   }
 }
 
+/* diagnostics: states inserted by the searches of the last gco_subtask_q call */
+long long gco_last_search_states = 0;
+
 /* V*(s0) in tenths, or -2 unreachable, -3 budget exceeded.  Bucketed Dijkstra (edge costs
  * 10..12). */
 static int solve(const plan_t* p, const gco_env* s0, int n_ag, int max_states) {
@@ -416,6 +419,7 @@ static int solve(const plan_t* p, const gco_env* s0, int n_ag, int max_states) {
         }
       }
   }
+  gco_last_search_states += (long long)tb.used;
   for (int b = 0; b < NB; b++) free(bucket[b]);
   free(tb.keys);
   free(tb.best);
@@ -457,6 +461,7 @@ int gco_subtask_q(const gco_level* lv, const gco_env* e0, const gco_subtask* st,
     if (!in_set) p.lv.type[e0->ag[i].y][e0->ag[i].x] = GCO_COUNTER;
   }
   p.base_count = goal_count(&p, &s);
+  gco_last_search_states = 0;
   for (int a = 0; a < 25; a++) q[a] = INFINITY;
   int v1 = single_actions(&p.lv, &s, 0), v2 = n_ag == 2 ? single_actions(&p.lv, &s, 1) : (1 << 4);
   double best = INFINITY;

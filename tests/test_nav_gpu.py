@@ -77,3 +77,86 @@ def test_lower_bound_matches_oracle_on_random_states(level, n_agents):
             sub = O.Subtask(*masks[s])
             exp = L.gco_lower_bound(C.byref(lv), C.byref(env), C.byref(sub), i, -1 if j is None else j)
             assert lb[e, k] == np.float32(exp), (e, pairs[k])
+
+
+def _oracle_q(lv, words, n_agents, masks, ai, max_states=3000000):
+    L = O.lib()
+    env = O.Env()
+    arr = np.ascontiguousarray(words, dtype=np.uint32)
+    L.gco_unpack(arr.ctypes.data_as(C.POINTER(C.c_uint32)), n_agents, C.byref(env))
+    env.n_objs = O.MAX_OBJS
+    sub = O.Subtask(*masks)
+    v = C.c_double()
+    q = (C.c_double * 25)()
+    status = L.gco_subtask_q(C.byref(lv), C.byref(env), C.byref(sub), ai, -1, C.byref(v), q, max_states)
+    return status, v.value, np.array(list(q)[:5])
+
+
+def test_subtask_values_inside_reference_brtdp_bracket(golden_dir):
+    """Single-agent pairs the reference's BRTDP converged on (v_u - v_l <= alpha = 0.01): the
+    kernel's exact V* must satisfy v_l - 1e-4 <= V* <= v_u + 1e-4 (BASELINE.json north_star)."""
+    g = np.load(os.path.join(golden_dir, "brtdp_values.npz"))
+    conv = (g["v_u"] - g["v_l"] <= 0.01) & (g["agent_j"] == 255) & (g["at_goal"] == 0)
+    checked = 0
+    for (lvl, n_agents), rows in sorted(_groups(g).items()):
+        rows = np.array([r for r in rows if conv[r]])
+        if len(rows) == 0:
+            continue
+        kb = gcb.KitchenBatch(str(g["levels"][lvl]), n_agents, len(rows), 100)
+        _load_states(kb, g["state"][rows])
+        masks = sorted(set(tuple(int(v) for v in m) for m in g["subtask"][rows]))
+        kb.set_subtask_masks(masks)
+        pairs = [(s, i, None) for s in range(len(masks)) for i in range(n_agents)]
+        v, q, status = gcb.subtask_q(kb, pairs)
+        v, q, status = v.cpu().numpy(), q.cpu().numpy(), status.cpu().numpy()
+        for e, r in enumerate(rows):
+            k = pairs.index((masks.index(tuple(int(x) for x in g["subtask"][r])), int(g["agent_i"][r]), None))
+            assert status[e, k] == 0, (r, status[e, k])
+            assert g["v_l"][r] - 1e-4 <= v[e, k] <= g["v_u"][r] + 1e-4, (r, v[e, k], g["v_l"][r], g["v_u"][r])
+            assert abs(q[e, k, :5].min() - v[e, k]) < 1e-5
+            checked += 1
+    assert checked >= 100
+
+
+@pytest.mark.parametrize("level,n_agents,seed", [("open-divider_salad", 2, 1), ("partial-divider_tl", 2, 2),
+                                                 ("full-divider_salad", 3, 3), ("open-divider_tomato", 4, 4)])
+def test_subtask_q_equals_exact_search_oracle(level, n_agents, seed):
+    """V* and Q(start, a) of every single-agent pair equal the oracle's uniform-cost search over
+    full env states (oracle/gc_oracle_nav.c) on states sampled by random play."""
+    n = 48
+    kb = gcb.KitchenBatch(level, n_agents, n, 100)
+    acts = kb.random_actions(60, seed=seed)
+    for s in range(60):
+        a = acts[s].clone()
+        a[(torch.arange(n, device=kb.device) * 5 % 61) <= s] = 4  # env e stops after a pseudo-random count
+        kb.step(a)
+    masks = [rp.subtask_masks(s) for s in kb.subtasks[0]]
+    pairs = [(s, i, None) for s in range(len(masks)) for i in range(n_agents)]
+    v, q, status = gcb.subtask_q(kb, pairs)
+    v, q, status = v.cpu().numpy(), q.cpu().numpy(), status.cpu().numpy()
+    st = kb.state.cpu().numpy().view(np.uint32)
+    lv = O.parse_level(gcb.levels.level_text(level), 100)
+    lb = gcb.lower_bound(kb, pairs).cpu().numpy()
+    compared = 0
+    for e in range(n):
+        for k, (s, i, _) in enumerate(pairs):
+            if lb[e, k] >= 28:  # not doable: pruned by the reference (bd:98-156), the oracle would exhaust its budget
+                continue
+            ost, ov, oq = _oracle_q(lv, st[e], n_agents, masks[s], i)
+            if ost == 3:
+                continue
+            assert status[e, k] == (0 if ost == 0 else 2), (e, pairs[k], status[e, k], ost)
+            if ost == 0:
+                assert abs(v[e, k] - ov) < 1e-4, (e, pairs[k], v[e, k], ov)
+                both = np.isfinite(oq)
+                assert (np.isfinite(q[e, k, :5]) == both).all(), (e, pairs[k], q[e, k, :5], oq)
+                assert np.abs(q[e, k, :5][both] - oq[both]).max() < 1e-4, (e, pairs[k], q[e, k, :5], oq)
+            compared += 1
+    assert compared > 20
+
+
+def test_joint_pairs_are_flagged_not_silently_wrong():
+    kb = gcb.KitchenBatch("open-divider_tomato", 2, 4, 100)
+    v, q, status = gcb.subtask_q(kb, [(0, 0, 1), (0, 0, None)])
+    assert (status[:, 0] == 4).all() and torch.isinf(v[:, 0]).all()
+    assert (status[:, 1] == 0).all() and torch.allclose(v[:, 1], torch.full((4,), 13.2, device=v.device))
