@@ -35,6 +35,7 @@ enum { ST_OK = 0, ST_AT_GOAL = 1, ST_UNREACHABLE = 2, ST_BUDGET = 3, ST_JOINT_UN
 
 struct Ctx {
   unsigned long long floorp;   // walkable squares of the planning world (floor minus frozen agents)
+  unsigned long long region;   // squares of floorp the agent can ever stand on (its connected component)
   unsigned long long putable;  // squares an object may be put on: every non-walkable, non-delivery square
   unsigned long long cut, deliv;
   const uint8_t* dstat;        // static all-pairs floor distances of the level (shared memory)
@@ -94,7 +95,7 @@ __device__ __forceinline__ int two_legs(const Ctx& cx, const uint8_t* dist, uint
 #pragma unroll
     for (int d2 = 0; d2 < 4; d2++) {
       const uint32_t f2 = approach_cell(q2, d2);
-      if (f2 >= 64u || !((cx.floorp >> f2) & 1ull)) continue;
+      if (f2 >= 64u || !((cx.region >> f2) & 1ull)) continue;  // outside the agent's component: never
       const uint32_t leg = cx.dstat[f1 * 64 + f2];
       if (leg == 255) continue;
       best = min(best, (int)dist[f1] + 1 + (int)leg + 1);
@@ -309,6 +310,14 @@ subtask_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_consta
     cx.putable = ~cx.floorp & ~cx.deliv;
     Plan p;
     p.cell = (s.x >> (6 * ai)) & 63u;
+    // With a single mover and static obstacles the set of squares it can stand on never
+    // changes, so anything not adjacent to this component is out of play for good: the bound
+    // below turns infinite and the pair is reported unreachable without searching.
+    cx.region = 1ull << p.cell;
+    for (unsigned long long grow = cx.region; grow;) {
+      grow = gcnav::neighbours(grow) & cx.floorp & ~cx.region;
+      cx.region |= grow;
+    }
     int goal_objects = 0;
 #pragma unroll
     for (int k = 0; k < GC_MAX_OBJECTS; k++) {

@@ -152,7 +152,7 @@ def test_subtask_q_equals_exact_search_oracle(level, n_agents, seed):
                 assert (np.isfinite(q[e, k, :5]) == both).all(), (e, pairs[k], q[e, k, :5], oq)
                 assert np.abs(q[e, k, :5][both] - oq[both]).max() < 1e-4, (e, pairs[k], q[e, k, :5], oq)
             compared += 1
-    assert compared > 20
+    assert compared > (3 if level.startswith("full") else 20)  # a full divider leaves few doable single-agent pairs
 
 
 def test_joint_pairs_are_flagged_not_silently_wrong():
