@@ -102,6 +102,20 @@ class KitchenBatch:
                 _lib.ptr(self.collisions), _lib.ptr(executed_out), self.num_envs, self.num_agents, self._stream()))
         return self.reward_done
 
+    def step_range(self, lo, hi, actions, stream=None):
+        """Step only envs [lo, hi) with actions uint8[hi-lo][num_agents], on `stream` (a
+        torch.cuda.Stream; default: current).  Lets a caller pipeline host copies of one chunk
+        against the kernel of another."""
+        if self.n_levels > 1:
+            raise _lib.GcError("step_range needs a single-level batch")
+        st = stream.cuda_stream if stream is not None else self._stream()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gc_env_step(
+                self._lv(), 1, None, self.state.data_ptr() + 16 * lo, _lib.ptr(actions, torch.uint8),
+                self.reward_done.data_ptr() + lo, None,
+                (self.collisions.data_ptr() + 4 * lo) if self.collisions is not None else None, None,
+                hi - lo, self.num_agents, st))
+
     def rollout(self, n_steps, t0=0, env0=0, seed=1234, hash_trace=None):
         """n_steps fused steps with the philox uniform-random action stream (cfg-2)."""
         with torch.cuda.device(self.device):

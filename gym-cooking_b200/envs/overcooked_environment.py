@@ -74,6 +74,43 @@ class EnvView:
         return self._env.is_collision(*a, **k)
 
 
+class Flag:
+    """Lazy view of one bit of the per-env reward/done byte (GC_RD_*): nothing is computed until
+    the caller asks (`.tensor()`, indexing, `bool(any())`), so a step over millions of envs does
+    not pay a host-side pass it may never need."""
+
+    def __init__(self, rd, bit, as_bool):
+        self.rd, self.bit, self.as_bool = rd, bit, as_bool
+
+    def tensor(self):
+        t = (self.rd >> self.bit) & 1
+        return t.bool() if self.as_bool else t
+
+    def __getitem__(self, i):
+        v = (int(self.rd[i]) >> self.bit) & 1
+        return bool(v) if self.as_bool else v
+
+    def __len__(self):
+        return self.rd.shape[0]
+
+    def any(self):
+        return bool(((self.rd >> self.bit) & 1).any())
+
+    def all(self):
+        return bool(((self.rd >> self.bit) & 1).all())
+
+    def sum(self):
+        return int(((self.rd >> self.bit) & 1).sum())
+
+    @property
+    def shape(self):
+        return self.rd.shape
+
+    def __array__(self, dtype=None):
+        a = self.tensor().numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+
 class BatchObs:
     """Handle over the packed uint32[N][4] state; `obs[i]` builds the view of env i on demand."""
 
@@ -108,6 +145,7 @@ class OvercookedEnvironment:
         self._kb = None
         self._pinned_rd = None
         self._dev_actions = None
+        self._streams = None
 
     def set_filename(self):  # env:116-128
         a = self.arglist
@@ -164,6 +202,8 @@ class OvercookedEnvironment:
         else:
             acts = action_dict
         self.t += 1
+        if self.num_envs > 1:
+            return self._step_batched(acts)
         if acts.is_cuda:
             dev_acts = acts
         else:
@@ -176,12 +216,6 @@ class OvercookedEnvironment:
         self._pinned_rd.copy_(kb.reward_done, non_blocking=True)  # D2H of the step's result
         torch.cuda.current_stream(kb.device).synchronize()
         rd = self._pinned_rd
-        if self.num_envs > 1:
-            done, reward = (rd & 1).bool(), (rd >> 1) & 1
-            info = {"t": self.t, "obs": None, "image_obs": None, "done": done, "termination_info": ""}
-            obs = self._obs()
-            info["obs"] = obs
-            return obs, reward, done, info
         # single env: rebuild the reference-shaped bookkeeping
         executed = self._executed[0].tolist()
         names = self.get_agent_names()
@@ -199,6 +233,45 @@ class OvercookedEnvironment:
         info = {"t": self.t, "obs": new_obs, "image_obs": None, "done": done,
                 "termination_info": self.termination_info}
         return new_obs, self.reward(), done, info
+
+    # chunks of a large batch are pipelined over this many streams: the host->device copy of
+    # chunk k+1, the kernel of chunk k and the device->host copy of chunk k-1 overlap (PCIe is
+    # full duplex and the copy engines run beside the SMs)
+    PIPELINE_CHUNKS = 4
+    PIPELINE_MIN_ENVS = 1 << 16
+
+    def _step_batched(self, acts):
+        kb = self._kb
+        n = self.num_envs
+        rd = self._pinned_rd
+        if acts.is_cuda:
+            kb.step(acts)
+            rd.copy_(kb.reward_done, non_blocking=True)
+            torch.cuda.current_stream(kb.device).synchronize()
+        elif n < self.PIPELINE_MIN_ENVS or kb.n_levels > 1:
+            self._dev_actions.copy_(acts, non_blocking=True)  # H2D (async when `acts` is pinned)
+            kb.step(self._dev_actions)
+            rd.copy_(kb.reward_done, non_blocking=True)        # D2H of the step's result
+            torch.cuda.current_stream(kb.device).synchronize()
+        else:
+            if self._streams is None:
+                self._streams = [torch.cuda.Stream(device=kb.device) for _ in range(self.PIPELINE_CHUNKS)]
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(kb.device))
+            c = self.PIPELINE_CHUNKS
+            for k, st in enumerate(self._streams):
+                lo, hi = n * k // c, n * (k + 1) // c
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    self._dev_actions[lo:hi].copy_(acts[lo:hi], non_blocking=True)
+                    kb.step_range(lo, hi, self._dev_actions[lo:hi], stream=st)
+                    rd[lo:hi].copy_(kb.reward_done[lo:hi], non_blocking=True)
+            for st in self._streams:
+                st.synchronize()
+        done, reward = Flag(rd, 0, True), Flag(rd, 1, False)
+        obs = self._obs()
+        info = {"t": self.t, "obs": obs, "image_obs": None, "done": done, "termination_info": ""}
+        return obs, reward, done, info
 
     def _set_termination(self, done):
         max_t = int(getattr(self.arglist, "max_num_timesteps", 100) or 0)

@@ -76,8 +76,19 @@ def test_batched_facade_host_actions():
         host = acts[s].cpu().pin_memory()
         obs, reward, done, info = env.step(host)
         ref.step(acts[s])
-        assert not reward.is_cuda and reward.shape == (n,) and done.dtype == torch.bool
+        assert reward.shape == (n,) and done.tensor().dtype == torch.bool and not done.tensor().is_cuda
     assert torch.equal(env.state, ref.state)
+    assert torch.equal(done.tensor(), ref.done.cpu()) and reward.sum() == int(ref.reward.sum())
+    # large batches take the chunk-pipelined path (H2D / kernel / D2H of different chunks overlap)
+    big, bref = gcb.OvercookedEnvironment(_arglist("partial-divider_tl", 2, 25), num_envs=1 << 17), \
+        gcb.KitchenBatch("partial-divider_tl", 2, 1 << 17, 25)
+    big.reset()
+    bacts = bref.random_actions(30, seed=3)
+    for s in range(30):
+        _, breward, bdone, _ = big.step(bacts[s].cpu().pin_memory())
+        bref.step(bacts[s])
+    assert torch.equal(big.state, bref.state) and bdone.all() and breward.sum() == 0
+    assert torch.equal(bdone.tensor(), bref.done.cpu())
     view = obs[17]
     w = ref.state[17].tolist()
     assert view.t == 30 and [a.location for a in view.sim_agents] == \
