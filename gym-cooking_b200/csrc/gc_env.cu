@@ -5,6 +5,7 @@
 // staged through shared memory when envs carry a per-env level id.
 #include "gc_device.cuh"
 #include "gc_host.h"
+#include "gc_step_lut.cuh"
 
 #include <stdlib.h>
 
@@ -241,12 +242,92 @@ inline unsigned step_grid(int64_t n) {
   return full < cap ? full : cap;
 }
 
+// ---------------------------------------------------------------------------------------
+// step, table-driven (single-level batches): see gc_step_lut.cuh
+// ---------------------------------------------------------------------------------------
+__device__ const gclut::StaticTables g_static_tables = gclut::make_static_tables();
+
+struct StepLutParams {
+  GcLevelDev lv;
+  gclut::MoveTable mv;
+};
+
+template <int NA, int NOBJ>
+__global__ void __launch_bounds__(kThreads)
+step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ state,
+                const uint8_t* __restrict__ actions, uint8_t* __restrict__ reward_done,
+                unsigned long long* __restrict__ hash, uint32_t* __restrict__ collisions,
+                uint8_t* __restrict__ executed, int64_t n) {
+  __shared__ __align__(16) gclut::Tables T;
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  // issue this thread's global loads before the table fill so both latencies overlap
+  const bool live = i < n;
+  uint4 s = make_uint4(0x80000000u, 0, 0, 0);
+  uint32_t act[NA];
+#pragma unroll
+  for (int k = 0; k < NA; k++) act[k] = 4u;
+  if (live) {
+    s = gc::ld_stream(state + i);
+    load_actions<NA>(actions, i, act);
+  }
+  gclut::load_tables(&T, &g_static_tables, P.mv);
+  __syncthreads();
+  if (!live) return;
+  const GcLevelDev& L = P.lv;
+  bool done, success;
+  if (s.x >> 31) {
+    const uint32_t t = (s.x >> 24) & 127u;
+    done = true;
+    success = !(L.max_t != 0u && t >= L.max_t);
+#pragma unroll
+    for (int k = 0; k < NA; k++) act[k] = 4u;
+  } else {
+    gclut::Env<NOBJ> e;
+    gclut::unpack<NA, NOBJ>(s, e);
+    const uint32_t ncoll = gclut::step<NA, NOBJ>(e, act, T, L, done, success);
+    s = gclut::pack<NA, NOBJ>(e, done);
+    gc::st_stream(state + i, s);
+    if (collisions && ncoll) collisions[i] += ncoll;
+  }
+  if (reward_done) reward_done[i] = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
+  if (hash) hash[i] = gc::state_hash<NA>(s);
+  if (executed) store_actions<NA>(executed, i, act);
+}
+
+// host: move[cell*8 + action] = target | kind(target) << 6 from the level's bitboards
+void fill_move_table(const GcLevelDev& L, gclut::MoveTable* mv) {
+  static const int delta[5] = {8, -8, -1, 1, 0};
+  for (int c = 0; c < 64; c++)
+    for (int a = 0; a < 8; a++) {
+      const int t = (c + delta[a < 5 ? a : 4]) & 63;
+      const unsigned long long b = 1ull << t;
+      const int kind = (L.floor_mask & b) ? 0 : (L.cut_mask & b) ? 2 : (L.deliv_mask & b) ? 3 : 1;
+      mv->v[c * 8 + a] = (uint8_t)(t | (kind << 6));
+    }
+}
+
+inline bool use_generic_step() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GC_STEP_GENERIC");  // 1 = the table-free reference form of the kernel
+    v = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <int NA, int NOBJ>
 int launch_step(bool multi, const GcLevelsDev& lv, const uint8_t* level_id, uint32_t* state,
                 const uint8_t* actions, uint8_t* rd, uint64_t* hash, uint32_t* coll, uint8_t* executed,
                 int64_t n, cudaStream_t st) {
   auto* s4 = reinterpret_cast<uint4*>(state);
   auto* h = reinterpret_cast<unsigned long long*>(hash);
+  if (!multi && !use_generic_step()) {
+    StepLutParams P;
+    P.lv = lv.lv[0];
+    fill_move_table(P.lv, &P.mv);
+    step_lut_kernel<NA, NOBJ><<<grid_for(n), kThreads, 0, st>>>(P, s4, actions, rd, h, coll, executed, n);
+    return gc_check_launch("gc_env_step");
+  }
   if (multi)
     step_kernel<NA, NOBJ, true><<<step_grid(n), kThreads, 0, st>>>(lv, level_id, s4, actions, rd, h, coll, executed, n);
   else

@@ -1,0 +1,223 @@
+// gc_step_lut.cuh - table-driven form of the env transition for single-level batches.
+//
+// ncu on the first (pure ALU) version of step_kernel showed the integer ALU pipe at 83 % of its
+// half-rate peak with the FMA and LSU pipes idle (profiles/r01_step_kernel_v1_ncu.csv): the
+// kernel was bound by ISETP/SEL/LOP3/SHF count, not by HBM.  This version moves work off the
+// ALU pipe:
+//   * square geometry        -> one shared-memory look-up  move[cell*8 + action] = target | kind<<6
+//   * object predicates      -> two look-ups  hprops[mask in hand], tprops[mask on the square]
+//   * interact() case split  -> five 1 KB look-ups of 0/1 flags (chop, merge, drop, pick, delivered)
+//                               indexed by hprops | tprops | kind<<8
+//   * applying the outcome   -> flag * delta + old  (IMAD, FMA pipe), predicated per slot
+// Semantics are those of gc::step (gc_device.cuh), which stays the reference form in the
+// multi-level kernels and is compared bit for bit against this one in the GPU tests.
+#pragma once
+#include "gc_device.cuh"
+
+namespace gclut {
+
+constexpr int kMoveBytes = 512;                          // per level: 64 cells x 8 (5 used)
+constexpr int kPropBytes = 128;                          // per table
+constexpr int kOutcomeBytes = 1024;                      // per table
+constexpr int kStaticBytes = 2 * kPropBytes + 5 * kOutcomeBytes;  // 5376, level independent
+constexpr uint32_t kDeadPlace = 0x1C0u;                  // holder 7, cell 0 (slot 0xE000)
+
+// level-independent tables, built at compile time
+struct StaticTables {
+  uint8_t hprops[kPropBytes];  // b0 holding, b1 foods done, b2 deliverable, b3 needs chopping, b4 plate
+  uint8_t tprops[kPropBytes];  // b5 occupied, b6 foods done, b7 plate
+  uint8_t chop[kOutcomeBytes], merge[kOutcomeBytes], drop[kOutcomeBytes], pick[kOutcomeBytes],
+      delivered[kOutcomeBytes];
+};
+
+constexpr bool c_foods_done(uint32_t m) { return ((m & 7u) & ~(m >> 4)) == 0u; }
+constexpr int c_popc4(uint32_t m) { return (int)((m & 1u) + ((m >> 1) & 1u) + ((m >> 2) & 1u) + ((m >> 3) & 1u)); }
+
+constexpr StaticTables make_static_tables() {
+  StaticTables t{};
+  for (uint32_t m = 0; m < 128; m++) {
+    const bool fd = c_foods_done(m), plate = (m & 8u) != 0u;
+    const bool deliverable = fd && c_popc4(m) > 1;             // utils/core.py:214-219
+    const bool needs_chop = m == 1u || m == 2u || m == 4u;     // utils/core.py:176-178
+    t.hprops[m] = (uint8_t)((m != 0u ? 1u : 0u) | (fd ? 2u : 0u) | (deliverable ? 4u : 0u) | (needs_chop ? 8u : 0u) |
+                            (plate ? 16u : 0u));
+    t.tprops[m] = (uint8_t)((m != 0u ? 32u : 0u) | (fd ? 64u : 0u) | (plate ? 128u : 0u));
+  }
+  for (uint32_t idx = 0; idx < 1024; idx++) {
+    const uint32_t kind = idx >> 8;  // 1 counter, 2 cutboard, 3 delivery (0 = floor: never looked up)
+    const bool holding = idx & 1u, fdH = idx & 2u, delivH = idx & 4u, chopH = idx & 8u, plateH = idx & 16u;
+    const bool occupied = idx & 32u, fdT = idx & 64u, plateT = idx & 128u;
+    uint8_t c = 0, m = 0, d = 0, p = 0, g = 0;
+    if (kind != 0u) {
+      if (holding) {  // utils/interact.py:33-70
+        if (kind == 3u) {
+          if (delivH) d = 1, g = 1;
+        } else if (occupied) {
+          if (!(plateH && plateT) && fdH && fdT) m = 1;  // mergeable, utils/core.py:222-241
+        } else if (kind == 2u && chopH) {
+          c = 1;
+        } else {
+          d = 1;
+        }
+      } else if (occupied && kind != 3u) {  // :73-84
+        p = 1;
+      }
+    }
+    t.chop[idx] = c;
+    t.merge[idx] = m;
+    t.drop[idx] = d;
+    t.pick[idx] = p;
+    t.delivered[idx] = g;
+  }
+  return t;
+}
+
+// per-level geometry: move[cell*8 + action] = target cell | kind(target) << 6
+struct MoveTable {
+  uint8_t v[kMoveBytes];
+};
+
+// shared-memory image used by the kernels
+struct Tables {
+  StaticTables st;
+  MoveTable mv;
+};
+
+template <int NOBJ>
+struct Env {
+  uint32_t cell[GC_MAX_AGENTS];
+  uint32_t place[NOBJ];  // slot >> 7: cell of a lying object, (holder << 6) while held, kDeadPlace when dead
+  uint32_t mask[NOBJ];
+  uint32_t t;
+};
+
+template <int NA, int NOBJ>
+__device__ __forceinline__ void unpack(const uint4& s, Env<NOBJ>& e) {
+#pragma unroll
+  for (int i = 0; i < NA; i++) e.cell[i] = (s.x >> (6 * i)) & 63u;
+  e.t = (s.x >> 24) & 127u;
+  const uint32_t w[3] = {s.y, s.z, s.w};
+#pragma unroll
+  for (int k = 0; k < NOBJ; k++) {
+    const uint32_t sl = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+    e.place[k] = sl >> 7;
+    e.mask[k] = sl & 0x7fu;
+  }
+}
+
+template <int NA, int NOBJ>
+__device__ __forceinline__ uint4 pack(const Env<NOBJ>& e, bool done) {
+  uint32_t x = e.t * 0x1000000u + (done ? 0x80000000u : 0u);
+#pragma unroll
+  for (int i = 0; i < NA; i++) x += e.cell[i] << (6 * i);
+  uint32_t w[3] = {0xE000E000u, 0xE000E000u, 0xE000E000u};
+#pragma unroll
+  for (int k = 0; k < NOBJ; k += 2) {
+    const uint32_t lo = e.place[k] * 128u + e.mask[k];
+    const uint32_t hi = (k + 1 < NOBJ) ? (e.place[k + 1] * 128u + e.mask[k + 1]) : 0xE000u;
+    w[k >> 1] = hi * 65536u + lo;
+  }
+  return make_uint4(x, w[0], w[1], w[2]);
+}
+
+// env.step (envs/overcooked_environment.py:255-306) - same contract as gc::step.
+template <int NA, int NOBJ>
+__device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], const Tables& T,
+                                         const GcLevelDev& L, bool& done, bool& success) {
+  e.t = min(e.t + 1u, 127u);  // env:257
+  uint32_t tgt[NA], nxt[NA], kind8[NA];  // kind8 = kind(target) << 8, 0 for floor
+#pragma unroll
+  for (int i = 0; i < NA; i++) {
+    act[i] = min(act[i], 4u);
+    const uint32_t mv = T.mv.v[e.cell[i] * 8u + act[i]];
+    tgt[i] = mv & 63u;
+    kind8[i] = (mv & 0xC0u) << 2;
+    nxt[i] = kind8[i] ? e.cell[i] : tgt[i];  // is_collision :692-700
+  }
+  // check_collisions :724-762.  "agent i faces a square and keeps its action" (:705-708) is
+  // exactly kind8[i] != 0: a non-stay action that leaves the agent in place.
+  uint32_t ncoll = 0;
+  bool cancel[NA];
+#pragma unroll
+  for (int i = 0; i < NA; i++) cancel[i] = false;
+#pragma unroll
+  for (int i = 0; i < NA; i++) {
+#pragma unroll
+    for (int j = i + 1; j < NA; j++) {
+      const bool same = nxt[i] == nxt[j];
+      const bool swap = (e.cell[i] == nxt[j]) & (e.cell[j] == nxt[i]);
+      const bool bi = kind8[i] != 0u, bj = kind8[j] != 0u;
+      cancel[i] |= (same & !bi) | (!same & swap);
+      cancel[j] |= (same & (bi | !bj)) | (!same & swap);
+      ncoll += (same | swap) ? 1u : 0u;
+    }
+  }
+  // execute_navigation :767-770 - sequential in agent order
+  uint32_t delivered = 0;
+#pragma unroll
+  for (int i = 0; i < NA; i++) {
+    act[i] = cancel[i] ? 4u : act[i];            // :757-761
+    e.cell[i] = cancel[i] ? e.cell[i] : nxt[i];  // interact.py:29-30
+    if (!cancel[i] && kind8[i] != 0u) {          // utils/interact.py:33-89
+      const uint32_t hp = (uint32_t)(i + 1) << 6, tg = tgt[i];
+      uint32_t mH = 0, mT = 0;
+#pragma unroll
+      for (int k = 0; k < NOBJ; k++) {
+        mH = (e.place[k] == hp) ? e.mask[k] : mH;
+        mT = (e.place[k] == tg) ? e.mask[k] : mT;
+      }
+      const uint32_t idx = T.st.hprops[mH] + T.st.tprops[mT] + kind8[i];
+      const uint32_t c = T.st.chop[idx], m = T.st.merge[idx], d = T.st.drop[idx], p = T.st.pick[idx];
+      delivered += T.st.delivered[idx];
+      // Every update is flag * delta + old, i.e. one IMAD on the (idle) FMA pipe, predicated on
+      // the slot being the hand slot / the square slot.
+      //   hand slot:   mask += chop bits | merged contents;   place: hand -> square when dropped
+      //   square slot: picked up (square -> hand) or merged away (mask 0, dead place)
+      const uint32_t chop_bits = mH * 16u, to_square = tg - hp, to_hand = hp - tg;
+      const uint32_t minus_mT = 0u - mT, to_dead = kDeadPlace - tg;
+#pragma unroll
+      for (int k = 0; k < NOBJ; k++) {
+        const bool isH = e.place[k] == hp, isT = e.place[k] == tg;
+        if (isH) {
+          e.mask[k] = c * chop_bits + e.mask[k];
+          e.mask[k] = m * mT + e.mask[k];
+          e.place[k] = d * to_square + e.place[k];
+        }
+        if (isT) {
+          e.mask[k] = m * minus_mT + e.mask[k];
+          e.place[k] = p * to_hand + e.place[k];
+          e.place[k] = m * to_dead + e.place[k];
+        }
+      }
+    }
+  }
+  // env.done :316-363 (goals can only complete on a step that delivered something)
+  bool all_goals = false;
+  if (delivered) {
+    all_goals = true;
+#pragma unroll
+    for (int g = 0; g < GC_MAX_GOALS; g++) {
+      bool found = false;
+#pragma unroll
+      for (int k = 0; k < NOBJ; k++) found |= (e.place[k] * 128u + e.mask[k]) == L.goal_slot[g];
+      all_goals &= found;
+    }
+  }
+  const bool timeout = L.max_t != 0u && e.t >= L.max_t;
+  done = timeout || all_goals;
+  success = all_goals && !timeout;
+  return ncoll;
+}
+
+// cooperative load of the tables into shared memory (call from every thread, then __syncthreads)
+__device__ __forceinline__ void load_tables(Tables* dst, const StaticTables* g_static, const MoveTable& mv_param) {
+  static_assert(sizeof(StaticTables) % 16 == 0, "vector copy");
+  const uint4* src = reinterpret_cast<const uint4*>(g_static);
+  uint4* d4 = reinterpret_cast<uint4*>(&dst->st);
+  for (int k = threadIdx.x; k < (int)(sizeof(StaticTables) / 16); k += blockDim.x) d4[k] = src[k];
+  const uint32_t* ms = reinterpret_cast<const uint32_t*>(&mv_param);
+  uint32_t* md = reinterpret_cast<uint32_t*>(&dst->mv);
+  for (int k = threadIdx.x; k < kMoveBytes / 4; k += blockDim.x) md[k] = ms[k];
+}
+
+}  // namespace gclut

@@ -237,8 +237,11 @@ class OvercookedEnvironment:
     # chunks of a large batch are pipelined over this many streams: the host->device copy of
     # chunk k+1, the kernel of chunk k and the device->host copy of chunk k-1 overlap (PCIe is
     # full duplex and the copy engines run beside the SMs)
-    PIPELINE_CHUNKS = 4
+    # (opt-in: on the measured hosts the extra launches and syncs cost more than the overlap wins,
+    # 202 us vs 99 us per 2^20-env step - scripts/e2e_probe.py - so the default is one stream)
+    PIPELINE_CHUNKS = 1
     PIPELINE_MIN_ENVS = 1 << 16
+    H2D_PIECE_BYTES = 1 << 30  # one copy; splitting into 128 KB-2 MB pieces measured no faster in the full step
 
     def _step_batched(self, acts):
         kb = self._kb
@@ -248,8 +251,12 @@ class OvercookedEnvironment:
             kb.step(acts)
             rd.copy_(kb.reward_done, non_blocking=True)
             torch.cuda.current_stream(kb.device).synchronize()
-        elif n < self.PIPELINE_MIN_ENVS or kb.n_levels > 1:
-            self._dev_actions.copy_(acts, non_blocking=True)  # H2D (async when `acts` is pinned)
+        elif self.PIPELINE_CHUNKS <= 1 or n < self.PIPELINE_MIN_ENVS or kb.n_levels > 1:
+            # H2D (async when `acts` is pinned), optionally in pieces (scripts/e2e_probe2.py)
+            flat_src, flat_dst = acts.view(-1), self._dev_actions.view(-1)
+            total, piece = flat_src.numel(), self.H2D_PIECE_BYTES
+            for lo in range(0, total, piece):
+                flat_dst[lo:lo + piece].copy_(flat_src[lo:lo + piece], non_blocking=True)
             kb.step(self._dev_actions)
             rd.copy_(kb.reward_done, non_blocking=True)        # D2H of the step's result
             torch.cuda.current_stream(kb.device).synchronize()

@@ -85,6 +85,7 @@ def test_batched_facade_host_actions():
     big.reset()
     bacts = bref.random_actions(30, seed=3)
     for s in range(30):
+        big.PIPELINE_CHUNKS = 4 if s % 2 else 1  # alternate the opt-in multi-stream path with the default
         _, breward, bdone, _ = big.step(bacts[s].cpu().pin_memory())
         bref.step(bacts[s])
     assert torch.equal(big.state, bref.state) and bdone.all() and breward.sum() == 0
