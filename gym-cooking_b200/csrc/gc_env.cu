@@ -259,39 +259,35 @@ step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ sta
                 unsigned long long* __restrict__ hash, uint32_t* __restrict__ collisions,
                 uint8_t* __restrict__ executed, int64_t n) {
   __shared__ __align__(16) gclut::Tables T;
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  // issue this thread's global loads before the table fill so both latencies overlap
-  const bool live = i < n;
-  uint4 s = make_uint4(0x80000000u, 0, 0, 0);
-  uint32_t act[NA];
-#pragma unroll
-  for (int k = 0; k < NA; k++) act[k] = 4u;
-  if (live) {
-    s = gc::ld_stream(state + i);
-    load_actions<NA>(actions, i, act);
-  }
+  // Persistent CTAs: the 5.9 KB of tables are loaded once per CTA and reused for every env the
+  // CTA walks (a one-env-per-thread grid spent ~20 % of its instructions refilling them).
   gclut::load_tables(&T, &g_static_tables, P.mv);
   __syncthreads();
-  if (!live) return;
   const GcLevelDev& L = P.lv;
-  bool done, success;
-  if (s.x >> 31) {
-    const uint32_t t = (s.x >> 24) & 127u;
-    done = true;
-    success = !(L.max_t != 0u && t >= L.max_t);
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    uint4 s = gc::ld_stream(state + i);
+    uint32_t act[NA];
+    load_actions<NA>(actions, i, act);
+    bool done, success;
+    if (s.x >> 31) {
+      const uint32_t t = (s.x >> 24) & 127u;
+      done = true;
+      success = !(L.max_t != 0u && t >= L.max_t);
 #pragma unroll
-    for (int k = 0; k < NA; k++) act[k] = 4u;
-  } else {
-    gclut::Env<NOBJ> e;
-    gclut::unpack<NA, NOBJ>(s, e);
-    const uint32_t ncoll = gclut::step<NA, NOBJ>(e, act, T, L, done, success);
-    s = gclut::pack<NA, NOBJ>(e, done);
-    gc::st_stream(state + i, s);
-    if (collisions && ncoll) collisions[i] += ncoll;
+      for (int k = 0; k < NA; k++) act[k] = 4u;
+    } else {
+      gclut::Env<NOBJ> e;
+      gclut::unpack<NA, NOBJ>(s, e);
+      const uint32_t ncoll = gclut::step<NA, NOBJ>(e, act, T, L, done, success);
+      s = gclut::pack<NA, NOBJ>(e, done);
+      gc::st_stream(state + i, s);
+      if (collisions && ncoll) collisions[i] += ncoll;
+    }
+    if (reward_done) reward_done[i] = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
+    if (hash) hash[i] = gc::state_hash<NA>(s);
+    if (executed) store_actions<NA>(executed, i, act);
   }
-  if (reward_done) reward_done[i] = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
-  if (hash) hash[i] = gc::state_hash<NA>(s);
-  if (executed) store_actions<NA>(executed, i, act);
 }
 
 // host: move[cell*8 + action] = target | kind(target) << 6 from the level's bitboards
@@ -304,6 +300,22 @@ void fill_move_table(const GcLevelDev& L, gclut::MoveTable* mv) {
       const int kind = (L.floor_mask & b) ? 0 : (L.cut_mask & b) ? 2 : (L.deliv_mask & b) ? 3 : 1;
       mv->v[c * 8 + a] = (uint8_t)(t | (kind << 6));
     }
+}
+
+// persistent grid of the table-driven kernel: GC_LUT_CTAS_PER_SM (default 8 = full occupancy)
+inline unsigned lut_grid(int64_t n) {
+  static int sms = 0, per_sm = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    const char* e = getenv("GC_LUT_CTAS_PER_SM");
+    per_sm = e ? atoi(e) : 8;
+    if (per_sm < 1 || per_sm > 8) per_sm = 8;
+  }
+  const unsigned full = grid_for(n), cap = (unsigned)(sms * per_sm);
+  return full < cap ? full : cap;
 }
 
 inline bool use_generic_step() {
@@ -325,7 +337,7 @@ int launch_step(bool multi, const GcLevelsDev& lv, const uint8_t* level_id, uint
     StepLutParams P;
     P.lv = lv.lv[0];
     fill_move_table(P.lv, &P.mv);
-    step_lut_kernel<NA, NOBJ><<<grid_for(n), kThreads, 0, st>>>(P, s4, actions, rd, h, coll, executed, n);
+    step_lut_kernel<NA, NOBJ><<<lut_grid(n), kThreads, 0, st>>>(P, s4, actions, rd, h, coll, executed, n);
     return gc_check_launch("gc_env_step");
   }
   if (multi)
