@@ -15,6 +15,7 @@ reference-shaped view of env i.  The facade only marshals: every transition runs
 gc_env_step; there is no CPU fallback.
 """
 import copy
+import os
 from collections import namedtuple
 
 import torch
@@ -146,6 +147,12 @@ class OvercookedEnvironment:
         self._pinned_rd = None
         self._dev_actions = None
         self._streams = None
+        # image_obs only when the reference would have a GameImage (env:240-246)
+        self._atlas = None
+        if getattr(arglist, "with_image_obs", False) or getattr(arglist, "record", False):
+            from .. import render as _render
+            gdir = os.path.join("misc", "game", "graphics")  # cwd-relative like the reference (game.py:7)
+            self._atlas = _render.load_atlas(gdir) if os.path.isdir(gdir) else _render.default_atlas()
 
     def set_filename(self):  # env:116-128
         a = self.arglist
@@ -230,7 +237,7 @@ class OvercookedEnvironment:
         self.successful = bool(int(rd[0]) & 2)
         self._set_termination(done)
         new_obs = self._obs()
-        info = {"t": self.t, "obs": new_obs, "image_obs": None, "done": done,
+        info = {"t": self.t, "obs": new_obs, "image_obs": self.get_image_obs(), "done": done,
                 "termination_info": self.termination_info}
         return new_obs, self.reward(), done, info
 
@@ -279,6 +286,17 @@ class OvercookedEnvironment:
         obs = self._obs()
         info = {"t": self.t, "obs": obs, "image_obs": None, "done": done, "termination_info": ""}
         return obs, reward, done, info
+
+    def get_image_obs(self, envs=None):
+        """GameImage.get_image_obs (misc/game/gameimage.py:31-51): uint8[H*80][W*80][3] of the single
+        env, or uint8[m][...] of `envs` for a batch; None when image observations are off."""
+        if self._atlas is None:
+            return None
+        from .. import render as _render
+        if not isinstance(self._atlas, torch.Tensor):
+            self._atlas = torch.from_numpy(self._atlas).to(self._kb.device)
+        img = _render.render(self._kb, self._atlas, envs)
+        return img[0].cpu().numpy() if (self.num_envs == 1 and envs is None) else img
 
     def _set_termination(self, done):
         max_t = int(getattr(self.arglist, "max_num_timesteps", 100) or 0)

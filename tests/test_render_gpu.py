@@ -81,3 +81,20 @@ def test_render_matches_numpy_compositing(level, n_agents):
         assert diff.max() <= 1, (e, int(diff.max()), int((diff > 1).sum()))  # rounding of the float blend only
     sub = R.render(kb, atlas, envs=torch.tensor([3, 10], device=kb.device)).cpu().numpy()
     assert (sub[0] == img[3]).all() and (sub[1] == img[10]).all()
+
+
+def test_facade_image_obs():
+    import argparse
+    ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=100, max_num_subtasks=14, seed=1,
+                            model1=None, model2=None, model3=None, model4=None, with_image_obs=True, record=False)
+    env = gcb.OvercookedEnvironment(ns)
+    env.reset()
+    _, _, _, info = env.step({"agent-1": (0, 1), "agent-2": (-1, 0)})
+    img = info["image_obs"]
+    assert img.shape == (560, 560, 3) and img.dtype == np.uint8
+    exp = numpy_render(env.level, env.state[0].tolist(), 2, R.default_atlas())
+    assert np.abs(img.astype(np.int32) - exp.astype(np.int32)).max() <= 1
+    ns.with_image_obs = False
+    env2 = gcb.OvercookedEnvironment(ns)
+    env2.reset()
+    assert env2.step({"agent-1": (0, 0), "agent-2": (0, 0)})[3]["image_obs"] is None
