@@ -60,6 +60,9 @@ _SIGNATURES = {
                                  C.c_int64, C.c_int, _VOIDP]),
     "gc_subtask_q": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, C.c_int, _VOIDP, _VOIDP,
                                _VOIDP, C.c_int64, C.c_int, _VOIDP]),
+    "gc_joint_q_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int, C.POINTER(C.c_int)]),
+    "gc_joint_q": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, C.c_int, _VOIDP, _VOIDP, _VOIDP,
+                             _VOIDP, C.c_int64, C.c_int64, C.c_int, _VOIDP]),
     "gc_render": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, C.c_int64, C.c_int, _VOIDP]),
 }
 # entry points declared in include/gymcook.h; tests check that each one is exported

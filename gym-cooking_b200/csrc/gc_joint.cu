@@ -1,0 +1,399 @@
+// gc_joint.cu - path B, part 3: exact level-0 values of JOINT (two-agent) subtask pairs.
+//
+// Same MDP as gc_search.cu, but with two movers the interaction-sequence trick no longer applies
+// (simultaneous moves, the pairwise collision rule of env.is_collision :671-718, hand-overs across
+// counters), so this kernel runs the real thing: uniform-cost search over full planning states
+// with the reference's own transition rules -
+//   actions   get_single_actions per agent (navigation_planner/utils.py:55-90), joint product
+//             filtered by is_collision (e2e_brtdp.get_actions :151-206),
+//   T         interact(agent_1) then interact(agent_2) (e2e_brtdp.T :132-143),
+//   cost      1 + 0.1 per moving agent (:816-826)  -> integer tenths 10 / 11 / 12,
+//   goal      one more goal object than at planning start (:435-566),
+//   level 0   other agents frozen into Agent-Counters, their held object deleted (:360-406).
+// One CTA owns one search = one (env, pair, root joint action): Dial's algorithm over a ring of
+// 16 cost buckets, visited set = open-addressing hash table in a caller-provided global scratch
+// arena keyed by an injective 64-bit packing of the planning state.  Q(start, a) = cost(a) +
+// V*(T(start, a)); V*(start) = min_a Q.  Searches are budgeted (kSlots states); a search that
+// exceeds its budget is reported (status 3), never guessed.
+#include "gc_device.cuh"
+#include "gc_host.h"
+#include "gc_nav.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr uint32_t kSlots = 1u << 16;        // hash capacity per search
+constexpr uint32_t kMaxStates = 48 * 1024;   // state budget per search (load factor 0.75)
+constexpr uint32_t kBucketCap = 16 * 1024;   // entries per cost bucket
+constexpr int kBuckets = 16;                 // ring (edge costs 10..12 < 16)
+constexpr int kMaxCost = 600;                // 60.0
+constexpr unsigned long long kEmpty = ~0ull;
+constexpr uint32_t kInfCost = 0xFFFFFFFFu;
+
+enum { ST_OK = 0, ST_UNREACHABLE = 2, ST_BUDGET = 3, ST_UNSUPPORTED = 4 };
+
+// per-CTA scratch layout
+struct Arena {
+  unsigned long long keys[kSlots];
+  uint4 states[kSlots];
+  uint32_t gcost[kSlots];  // 2*cost (+1 once settled)
+  uint32_t bucket[kBuckets][kBucketCap];
+};
+
+struct World {
+  unsigned long long floorp, nonfloor, cut, deliv;
+  uint32_t goal_mask, goal_kind;
+};
+
+// planning state: two agents, object slots with holder 1 / 2 (the two subtask agents)
+struct PState {
+  uint32_t cell[2];
+  uint32_t slot[4];
+};
+
+__device__ __forceinline__ uint4 pack_state(const PState& p) {
+  return make_uint4(p.cell[0] | (p.cell[1] << 6), p.slot[0] | (p.slot[1] << 16), p.slot[2] | (p.slot[3] << 16), 0u);
+}
+__device__ __forceinline__ PState unpack_state(const uint4& w) {
+  PState p;
+  p.cell[0] = w.x & 63u;
+  p.cell[1] = (w.x >> 6) & 63u;
+  p.slot[0] = w.y & 0xffffu;
+  p.slot[1] = w.y >> 16;
+  p.slot[2] = w.z & 0xffffu;
+  p.slot[3] = w.z >> 16;
+  return p;
+}
+
+// injective 64-bit key: 2 x 6-bit cells + 4 x (7-bit mask + 6-bit place), place = rank of the
+// square among non-walkable squares (<= 60), 60/61 = held by agent 1/2, 63 = dead
+__device__ __forceinline__ unsigned long long compact_key(const World& w, const PState& p) {
+  unsigned long long k = p.cell[0] | (p.cell[1] << 6);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint32_t s = p.slot[i], holder = s >> 13;
+    uint32_t place;
+    if (holder == 0u) place = (uint32_t)__popcll(w.nonfloor & ((1ull << ((s >> 7) & 63u)) - 1ull));
+    else place = holder == 7u ? 63u : 59u + holder;
+    k |= (unsigned long long)((s & 0x7fu) | (place << 7)) << (12 + 13 * i);
+  }
+  return k;
+}
+
+__device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
+  k ^= k >> 31;
+  k *= 0x9E3779B97F4A7C15ull;
+  k ^= k >> 29;
+  return (uint32_t)k & (kSlots - 1u);
+}
+
+__device__ __forceinline__ int lying_at(const PState& p, uint32_t q) {
+  int on = -1;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if ((p.slot[k] >> 13) == 0u && ((p.slot[k] >> 7) & 63u) == q) on = k;
+  return on;
+}
+__device__ __forceinline__ int held_by(const PState& p, int agent) {
+  int h = -1;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if ((p.slot[k] >> 13) == (uint32_t)(agent + 1)) h = k;
+  return h;
+}
+
+// nav_utils.get_single_actions (navigation_planner/utils.py:55-90): bit a = action a offered
+__device__ __forceinline__ uint32_t single_actions(const World& w, const PState& p, int agent) {
+  uint32_t valid = 1u << 4;
+  const int hand = held_by(p, agent);
+  for (uint32_t a = 0; a < 4; a++) {
+    const uint32_t t = (p.cell[agent] + (uint32_t)gc::action_delta(a)) & 63u;
+    if (t == p.cell[0] || t == p.cell[1]) continue;  // :71 not into an agent's current square
+    if (((w.floorp >> t) & 1ull) || ((w.deliv >> t) & 1ull)) {  // :74-78
+      valid |= 1u << a;
+      continue;
+    }
+    const int on = lying_at(p, t);
+    if (on < 0 && hand >= 0) valid |= 1u << a;                    // :80-81 put down / chop
+    else if (on >= 0 && hand < 0) valid |= 1u << a;               // :82-83 pick up
+    else if (on >= 0 && hand >= 0 && gc::mergeable(p.slot[hand] & 0x7fu, p.slot[on] & 0x7fu)) valid |= 1u << a;
+  }
+  return valid;
+}
+
+// env.is_collision :671-718: both agents may execute
+__device__ __forceinline__ bool joint_ok(const World& w, const PState& p, uint32_t a1, uint32_t a2) {
+  uint32_t n1 = (p.cell[0] + (uint32_t)gc::action_delta(a1)) & 63u, n2 = (p.cell[1] + (uint32_t)gc::action_delta(a2)) & 63u;
+  if (!((w.floorp >> n1) & 1ull)) n1 = p.cell[0];
+  if (!((w.floorp >> n2) & 1ull)) n2 = p.cell[1];
+  if (n1 == n2) return false;  // every branch of :704-711 cancels at least one action
+  if (p.cell[0] == n2 && p.cell[1] == n1) return false;
+  return true;
+}
+
+// utils/interact.py:4-89 on the planning world
+__device__ __forceinline__ void interact(const World& w, PState& p, int agent, uint32_t a) {
+  if (a == 4u) return;
+  const uint32_t t = (p.cell[agent] + (uint32_t)gc::action_delta(a)) & 63u;
+  if ((w.floorp >> t) & 1ull) {
+    p.cell[agent] = t;
+    return;
+  }
+  const int hand = held_by(p, agent), on = lying_at(p, t);
+  const bool is_del = (w.deliv >> t) & 1ull, is_cut = (w.cut >> t) & 1ull;
+  if (hand >= 0) {
+    const uint32_t mH = p.slot[hand] & 0x7fu;
+    if (is_del) {
+      if (gc::deliverable(mH)) p.slot[hand] = mH | (t << 7);
+    } else if (on >= 0) {
+      if (gc::mergeable(mH, p.slot[on] & 0x7fu)) {
+        p.slot[hand] |= p.slot[on] & 0x7fu;
+        p.slot[on] = GC_SLOT_DEAD;
+      }
+    } else if (is_cut && gc::needs_chopped(mH)) {
+      p.slot[hand] |= mH << 4;
+    } else {
+      p.slot[hand] = mH | (t << 7);
+    }
+  } else if (on >= 0 && !is_del) {
+    p.slot[on] = (p.slot[on] & 0x7fu) | ((uint32_t)(agent + 1) << 13);
+  }
+}
+
+// e2e_brtdp._define_goal_state :435-566 with a base count of zero
+__device__ __forceinline__ bool is_goal(const World& w, const PState& p) {
+  bool g = false;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t s = p.slot[k];
+    if ((s >> 13) == 7u || (s & 0x7fu) != w.goal_mask) continue;
+    if (w.goal_kind == GC_ST_DELIVER) g |= (s >> 13) == 0u && ((w.deliv >> ((s >> 7) & 63u)) & 1ull);
+    else g = true;
+  }
+  return g;
+}
+
+// insert / relax `p` with cost c (tenths); pushes it into its bucket when it improved
+__device__ __forceinline__ void relax(const World& w, Arena* A, uint32_t* bcount, uint32_t* n_states, int* over,
+                                      const PState& p, uint32_t c) {
+  const unsigned long long k = compact_key(w, p);
+  uint32_t h = hash_key(k);
+  for (uint32_t probe = 0; probe < kSlots; probe++, h = (h + 1u) & (kSlots - 1u)) {
+    const unsigned long long old = atomicCAS(&A->keys[h], kEmpty, k);
+    if (old == kEmpty) {
+      A->states[h] = pack_state(p);
+      if (atomicAdd(n_states, 1u) >= kMaxStates) atomicExch(over, 1);
+    } else if (old != k) {
+      continue;
+    }
+    const uint32_t prev = atomicMin(&A->gcost[h], 2u * c);
+    if (prev > 2u * c) {
+      const uint32_t b = c & (kBuckets - 1);
+      const uint32_t pos = atomicAdd(&bcount[b], 1u);
+      if (pos < kBucketCap) A->bucket[b][pos] = h;
+      else atomicExch(over, 1);
+    }
+    return;
+  }
+  atomicExch(over, 1);
+}
+
+__global__ void __launch_bounds__(kThreads)
+joint_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant__ GcPairs pairs,
+               const uint8_t* __restrict__ level_id, const uint4* __restrict__ state, Arena* __restrict__ arenas,
+               float* __restrict__ q_out, int* __restrict__ flags, int64_t n, int n_agents) {
+  __shared__ uint32_t bcount[kBuckets];
+  __shared__ uint32_t n_states;
+  __shared__ int over, result;
+  __shared__ PState root;
+  __shared__ World w;
+  __shared__ int root_state;  // 0 search, 1 invalid action, 2 goal right away
+  Arena* A = arenas + blockIdx.x;
+  const int64_t n_search = n * pairs.n * 25;
+  for (int64_t sid = blockIdx.x; sid < n_search; sid += gridDim.x) {
+    const int64_t prob = sid / 25;
+    const int act = (int)(sid - prob * 25);
+    const int64_t env = prob / pairs.n;
+    const int pi = (int)(prob - env * pairs.n);
+    const uint32_t a1 = (uint32_t)(act / 5), a2 = (uint32_t)(act % 5);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const GcNavLevel& L = levels.lv[level_id ? level_id[env] : 0];
+      const int sub = pairs.p[pi][0], ai = pairs.p[pi][1], aj = pairs.p[pi][2];
+      const uint4 s = state[env];
+      root_state = 1;
+      if (aj != 0xFF && (uint32_t)sub < L.n_subtasks) {
+        const gc_subtask st = L.st[sub];
+        unsigned long long frozen = 0;
+        for (int i = 0; i < n_agents; i++)
+          if (i != ai && i != aj) frozen |= 1ull << ((s.x >> (6 * i)) & 63u);
+        w.floorp = L.floor_mask & ~frozen;
+        w.nonfloor = ~w.floorp;
+        w.cut = L.cut_mask;
+        w.deliv = L.deliv_mask;
+        w.goal_mask = st.goal;
+        w.goal_kind = st.kind;
+        PState p;
+        p.cell[0] = (s.x >> (6 * ai)) & 63u;
+        p.cell[1] = (s.x >> (6 * aj)) & 63u;
+        bool supported = gcnav::slot_of(s, 4) == GC_SLOT_DEAD && gcnav::slot_of(s, 5) == GC_SLOT_DEAD;
+        bool goal_exists = false;
+        for (int k = 0; k < 4; k++) {
+          uint32_t sl = gcnav::slot_of(s, k);
+          const uint32_t holder = sl >> 13;
+          if (holder >= 1u && holder <= 4u)
+            sl = (int)holder == ai + 1 ? ((sl & 0x7fu) | (1u << 13))
+                 : (int)holder == aj + 1 ? ((sl & 0x7fu) | (2u << 13)) : GC_SLOT_DEAD;
+          p.slot[k] = sl;
+        }
+        goal_exists = is_goal(w, p);  // a goal object is already there: the count can never rise (one food of each kind)
+        supported = supported && __popcll(w.nonfloor) <= 60;  // ranks 60..63 are reserved by compact_key
+        if (!supported) {
+          atomicOr(&flags[prob], 4);
+        } else if (!goal_exists) {
+          const uint32_t v1 = single_actions(w, p, 0), v2 = single_actions(w, p, 1);
+          // (stay, stay) leaves the state unchanged: Q = 1 + V*(start), filled in by the finalize kernel
+          if (act != 24 && ((v1 >> a1) & 1u) && ((v2 >> a2) & 1u) && joint_ok(w, p, a1, a2)) {
+            interact(w, p, 0, a1);
+            interact(w, p, 1, a2);
+            root = p;
+            root_state = is_goal(w, p) ? 2 : 0;
+          }
+        }
+      }
+      n_states = 0;
+      over = 0;
+      result = 0x7fffffff;
+    }
+    if (threadIdx.x < kBuckets) bcount[threadIdx.x] = 0;
+    __syncthreads();
+    const float step_cost = 1.0f + 0.1f * (float)((a1 != 4u) + (a2 != 4u));
+    if (root_state == 1) continue;
+    if (root_state == 2) {
+      if (threadIdx.x == 0) q_out[prob * 25 + act] = step_cost;
+      continue;
+    }
+    // ---- clear the table, seed the root ----
+    for (uint32_t k = threadIdx.x; k < kSlots; k += kThreads) {
+      A->keys[k] = kEmpty;
+      A->gcost[k] = kInfCost;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) relax(w, A, bcount, &n_states, &over, root, 0u);
+    __syncthreads();
+    // ---- Dial's algorithm ----
+    int empty_run = 0;
+    for (int cur = 0; cur <= kMaxCost && empty_run < kBuckets; cur++) {
+      const uint32_t b = (uint32_t)cur & (kBuckets - 1);
+      const uint32_t cnt = min(bcount[b], kBucketCap);
+      if (cnt == 0) {
+        empty_run++;
+        continue;  // uniform: bcount is shared and only changes between barriers
+      }
+      empty_run = 0;
+      for (uint32_t e = threadIdx.x; e < cnt; e += kThreads) {
+        const uint32_t h = A->bucket[b][e];
+        // settle exactly once, and only if this entry still carries the best cost
+        if (atomicCAS(&A->gcost[h], 2u * (uint32_t)cur, 2u * (uint32_t)cur + 1u) != 2u * (uint32_t)cur) continue;
+        const PState p = unpack_state(A->states[h]);
+        if (is_goal(w, p)) {
+          atomicMin(&result, cur);
+          continue;
+        }
+        const uint32_t v1 = single_actions(w, p, 0), v2 = single_actions(w, p, 1);
+        for (uint32_t b1 = 0; b1 < 5; b1++) {
+          if (!((v1 >> b1) & 1u)) continue;
+          for (uint32_t b2 = 0; b2 < 5; b2++) {
+            if (!((v2 >> b2) & 1u) || (b1 == 4u && b2 == 4u) || !joint_ok(w, p, b1, b2)) continue;
+            PState nx = p;
+            interact(w, nx, 0, b1);
+            interact(w, nx, 1, b2);
+            relax(w, A, bcount, &n_states, &over, nx, (uint32_t)cur + 10u + (b1 != 4u) + (b2 != 4u));
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) bcount[b] = 0;
+      __syncthreads();
+      if (result != 0x7fffffff || over) break;
+    }
+    if (threadIdx.x == 0) {
+      if (result != 0x7fffffff) q_out[prob * 25 + act] = step_cost + 0.1f * (float)result;
+      else if (over) atomicOr(&flags[prob], 1);  // budget exceeded: this Q stays +inf and is flagged
+    }
+  }
+}
+
+// per problem: v = min_a q, q(stay, stay) = 1 + v, status
+__global__ void joint_finalize_kernel(const __grid_constant__ GcPairs pairs, float* __restrict__ v_out,
+                                      float* __restrict__ q_out, uint8_t* __restrict__ status_out,
+                                      const int* __restrict__ flags, int64_t n) {
+  const int64_t prob = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (prob >= n * pairs.n) return;
+  if (pairs.p[prob % pairs.n][2] == 0xFF) return;  // single-agent pair: not ours
+  float best = INFINITY;
+  for (int a = 0; a < 24; a++) best = fminf(best, q_out[prob * 25 + a]);
+  if (isfinite(best) && isfinite(q_out[prob * 25 + 24]) == false) {
+    // (stay, stay) changes nothing: Q = 1 + V*(start).  It is offered whenever both agents may stay,
+    // which is always (navigation_planner/utils.py:88), and never collides.
+    q_out[prob * 25 + 24] = 1.0f + best;
+  }
+  v_out[prob] = best;
+  if (status_out)
+    status_out[prob] = (flags[prob] & 4) ? ST_UNSUPPORTED : (flags[prob] & 1) ? ST_BUDGET : isfinite(best) ? ST_OK
+                                                                                                           : ST_UNREACHABLE;
+}
+
+__global__ void joint_init_kernel(const __grid_constant__ GcPairs pairs, float* __restrict__ q_out,
+                                  int* __restrict__ flags, int64_t n) {
+  const int64_t prob = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (prob >= n * pairs.n) return;
+  flags[prob] = 0;
+  if (pairs.p[prob % pairs.n][2] == 0xFF) return;
+  for (int a = 0; a < 25; a++) q_out[prob * 25 + a] = INFINITY;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t gc_joint_q_scratch_bytes(int64_t n, int n_pairs, int* n_ctas_out) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  int64_t ctas = (int64_t)sms * 4;
+  const int64_t searches = n * n_pairs * 25;
+  if (searches < ctas) ctas = searches > 0 ? searches : 1;
+  if (n_ctas_out) *n_ctas_out = (int)ctas;
+  return ctas * (int64_t)sizeof(Arena) + n * n_pairs * (int64_t)sizeof(int);
+}
+
+int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, const uint32_t* state,
+               const uint8_t* pairs, int n_pairs, float* v, float* q, uint8_t* status, void* scratch,
+               int64_t scratch_bytes, int64_t n, int n_agents, void* stream) {
+  GcNavLevels lv;
+  GcPairs pr;
+  if (n_agents < 2 || n_agents > GC_MAX_AGENTS) return gc_fail(GC_E_ARG, "gc_joint_q: n_agents must be 2..4");
+  if (int rc = gc_nav_levels_to_dev(levels, n_levels, &lv)) return rc;
+  if (int rc = gc_pairs_to_dev(pairs, n_pairs, n_agents, &pr)) return rc;
+  if (!state || !v || !q || n < 0) return gc_fail(GC_E_ARG, "gc_joint_q: null state/v/q or n < 0");
+  if (n_levels > 1 && !level_id) return gc_fail(GC_E_ARG, "gc_joint_q: n_levels > 1 needs level_id");
+  if (n == 0) return GC_OK;
+  if (int rc = gc_require_device()) return rc;
+  int n_ctas = 0;
+  const int64_t need = gc_joint_q_scratch_bytes(n, n_pairs, &n_ctas);
+  if (!scratch || scratch_bytes < need)
+    return gc_fail(GC_E_ARG, "gc_joint_q: scratch of %lld bytes needed, %lld given", (long long)need, (long long)scratch_bytes);
+  Arena* arenas = reinterpret_cast<Arena*>(scratch);
+  int* flags = reinterpret_cast<int*>(reinterpret_cast<char*>(scratch) + (int64_t)n_ctas * sizeof(Arena));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t probs = n * n_pairs;
+  const unsigned pgrid = (unsigned)((probs + 255) / 256);
+  joint_init_kernel<<<pgrid, 256, 0, st>>>(pr, q, flags, n);
+  joint_q_kernel<<<(unsigned)n_ctas, kThreads, 0, st>>>(lv, pr, n_levels > 1 ? level_id : nullptr,
+                                                       reinterpret_cast<const uint4*>(state), arenas, q, flags, n, n_agents);
+  joint_finalize_kernel<<<pgrid, 256, 0, st>>>(pr, v, q, status, flags, n);
+  return gc_check_launch("gc_joint_q");
+}
+
+}  // extern "C"

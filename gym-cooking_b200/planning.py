@@ -51,14 +51,26 @@ def lower_bound(batch, pairs, out=None):
 
 def subtask_q(batch, pairs, want_q=True):
     """Exact level-0 V* / Q(start, .) for every (env, pair): returns (v[N][P], q[N][P][25] or None,
-    status uint8[N][P])."""
+    status uint8[N][P]).  Single-agent pairs: gc_subtask_q (interaction-level IDA*); joint pairs:
+    gc_joint_q (budgeted uniform-cost search, scratch arena allocated here as a torch tensor)."""
     lib = _lib.load()
     arr = _pairs_array(pairs)
+    has_joint = bool((arr[:, 2] != 255).any())
     with torch.cuda.device(batch.device):
         v = torch.empty((batch.num_envs, len(pairs)), dtype=torch.float32, device=batch.device)
-        q = torch.empty((batch.num_envs, len(pairs), 25), dtype=torch.float32, device=batch.device) if want_q else None
+        q = (torch.empty((batch.num_envs, len(pairs), 25), dtype=torch.float32, device=batch.device)
+             if (want_q or has_joint) else None)
         status = torch.empty((batch.num_envs, len(pairs)), dtype=torch.uint8, device=batch.device)
         _lib.check(lib.gc_subtask_q(batch._lv(), batch.n_levels, _lib.ptr(batch.level_id), _lib.ptr(batch.state),
                                     arr.ctypes.data_as(C.c_void_p), len(pairs), _lib.ptr(v), _lib.ptr(q),
                                     _lib.ptr(status), batch.num_envs, batch.num_agents, batch._stream()))
-    return v, q, status
+        if has_joint:
+            need = lib.gc_joint_q_scratch_bytes(batch.num_envs, len(pairs), None)
+            scratch = getattr(batch, "_joint_scratch", None)
+            if scratch is None or scratch.numel() < need:
+                scratch = batch._joint_scratch = torch.empty(need, dtype=torch.uint8, device=batch.device)
+            _lib.check(lib.gc_joint_q(batch._lv(), batch.n_levels, _lib.ptr(batch.level_id), _lib.ptr(batch.state),
+                                      arr.ctypes.data_as(C.c_void_p), len(pairs), _lib.ptr(v), _lib.ptr(q),
+                                      _lib.ptr(status), _lib.ptr(scratch), scratch.numel(), batch.num_envs,
+                                      batch.num_agents, batch._stream()))
+    return v, (q if want_q else None), status

@@ -234,6 +234,19 @@ int gc_subtask_q(const gc_level* levels, int n_levels, const uint8_t* level_id /
                  const uint32_t* state /*device*/, const uint8_t* pairs /*host*/, int n_pairs,
                  float* v, float* q, uint8_t* status, int64_t n, int n_agents, void* stream);
 
+/* Joint (two-agent) pairs of the same MDP: budgeted exact uniform-cost search over full planning
+ * states, one CTA per (env, pair, root joint action), visited set in a caller-provided scratch
+ * arena of gc_joint_q_scratch_bytes(n, n_pairs, NULL) bytes.  Only pairs with agent j != 0xFF are
+ * written: v[n][n_pairs], q[n][n_pairs][25] (joint action 5*a_i + a_j), status (0 ok,
+ * 2 unreachable, 3 a search exceeded its 48K-state budget - its Q stays +inf, 4 unsupported:
+ * more than four objects).  Single-agent entries of v/q/status are left untouched, so both
+ * solvers can fill the same arrays. */
+int64_t gc_joint_q_scratch_bytes(int64_t n, int n_pairs, int* n_ctas_out);
+int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
+               const uint32_t* state /*device*/, const uint8_t* pairs /*host*/, int n_pairs, float* v, float* q,
+               uint8_t* status, void* scratch /*device*/, int64_t scratch_bytes, int64_t n, int n_agents,
+               void* stream);
+
 /* ---- (A') optional image_obs renderer -------------------------------------------------
  * misc/game/game.py:56-185 geometry (80 px tiles) -> uint8[m][H*80][W*80][3], RGB. */
 int gc_render(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,

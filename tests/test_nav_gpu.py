@@ -155,8 +155,68 @@ def test_subtask_q_equals_exact_search_oracle(level, n_agents, seed):
     assert compared > (3 if level.startswith("full") else 20)  # a full divider leaves few doable single-agent pairs
 
 
-def test_joint_pairs_are_flagged_not_silently_wrong():
-    kb = gcb.KitchenBatch("open-divider_tomato", 2, 4, 100)
-    v, q, status = gcb.subtask_q(kb, [(0, 0, 1), (0, 0, None)])
-    assert (status[:, 0] == 4).all() and torch.isinf(v[:, 0]).all()
-    assert (status[:, 1] == 0).all() and torch.allclose(v[:, 1], torch.full((4,), 13.2, device=v.device))
+def test_known_answers_from_survey():
+    """open-divider_tomato at reset, Chop(Tomato): agent-1 alone 13.2, agent-2 alone 8.8,
+    both 7.8; full-divider_salad Chop(Lettuce) by (agent-1, agent-2) = 7.7 (hand-over across the divider)."""
+    kb = gcb.KitchenBatch("open-divider_tomato", 2, 3, 100)
+    v, q, status = gcb.subtask_q(kb, [(0, 0, None), (0, 1, None), (0, 0, 1)])
+    assert (status == 0).all()
+    assert torch.allclose(v, torch.tensor([[13.2, 8.8, 7.8]] * 3, device=v.device), atol=1e-5)
+    kb = gcb.KitchenBatch("full-divider_salad", 3, 2, 100)
+    lettuce = [str(s) for s in kb.subtasks[0]].index("Chop(Lettuce)")
+    v, q, status = gcb.subtask_q(kb, [(lettuce, 0, 1), (lettuce, 1, None)])
+    assert torch.allclose(v[:, 0], torch.full((2,), 7.7, device=v.device), atol=1e-5) and (status[:, 0] == 0).all()
+    assert torch.isinf(v[:, 1]).all() and (status[:, 1] == 2).all()  # agent-2 alone cannot reach the lettuce
+
+
+def _oracle_joint(lv, words, n_agents, masks, ai, aj, max_states=1500000):
+    L = O.lib()
+    env = O.Env()
+    arr = np.ascontiguousarray(words, dtype=np.uint32)
+    L.gco_unpack(arr.ctypes.data_as(C.POINTER(C.c_uint32)), n_agents, C.byref(env))
+    env.n_objs = O.MAX_OBJS
+    sub = O.Subtask(*masks)
+    v = C.c_double()
+    q = (C.c_double * 25)()
+    status = L.gco_subtask_q(C.byref(lv), C.byref(env), C.byref(sub), ai, aj, C.byref(v), q, max_states)
+    return status, v.value, np.array(list(q))
+
+
+def test_joint_values_inside_reference_brtdp_bracket_and_equal_oracle(golden_dir):
+    """Joint pairs the reference's BRTDP converged on: V* inside [v_l - 1e-4, v_u + 1e-4]; for the
+    cheaper ones (V <= 8) also V* and every Q(start, a) equal to the oracle's exhaustive search."""
+    g = np.load(os.path.join(golden_dir, "brtdp_values.npz"))
+    conv = (g["v_u"] - g["v_l"] <= 0.01) & (g["agent_j"] != 255) & (g["at_goal"] == 0)
+    checked = compared = budget = 0
+    for (lvl, n_agents), rows in sorted(_groups(g).items()):
+        rows = np.array([r for r in rows if conv[r]])
+        if len(rows) == 0:
+            continue
+        kb = gcb.KitchenBatch(str(g["levels"][lvl]), n_agents, len(rows), 100)
+        _load_states(kb, g["state"][rows])
+        masks = sorted(set(tuple(int(v) for v in m) for m in g["subtask"][rows]))
+        kb.set_subtask_masks(masks)
+        pairs = sorted(set((masks.index(tuple(int(x) for x in g["subtask"][r])), int(g["agent_i"][r]), int(g["agent_j"][r]))
+                           for r in rows))
+        v, q, status = gcb.subtask_q(kb, pairs)
+        v, q, status = v.cpu().numpy(), q.cpu().numpy(), status.cpu().numpy()
+        lv = O.parse_level(gcb.levels.level_text(str(g["levels"][lvl])), 100)
+        for e, r in enumerate(rows):
+            key = (masks.index(tuple(int(x) for x in g["subtask"][r])), int(g["agent_i"][r]), int(g["agent_j"][r]))
+            k = pairs.index(key)
+            if status[e, k] == 3:
+                budget += 1
+                assert v[e, k] >= g["v_l"][r] - 1e-4  # resolved actions only give an upper bound
+                continue
+            assert status[e, k] == 0, (r, status[e, k])
+            assert g["v_l"][r] - 1e-4 <= v[e, k] <= g["v_u"][r] + 1e-4, (r, v[e, k], g["v_l"][r], g["v_u"][r])
+            checked += 1
+            if g["v_l"][r] <= 8.0 and compared < 40:
+                ost, ov, oq = _oracle_joint(lv, g["state"][r], n_agents, masks[key[0]], key[1], key[2])
+                if ost == 0:
+                    assert abs(ov - v[e, k]) < 1e-4
+                    fin = np.isfinite(oq)
+                    assert (np.isfinite(q[e, k]) == fin).all(), (r, q[e, k], oq)
+                    assert np.abs(q[e, k][fin] - oq[fin]).max() < 1e-4, (r, q[e, k], oq)
+                    compared += 1
+    assert checked >= 60 and compared >= 20 and budget <= 10, (checked, compared, budget)
