@@ -42,6 +42,7 @@ struct Arena {
 
 struct World {
   unsigned long long floorp, nonfloor, cut, deliv;
+  unsigned long long blocked;  // level-1 only: squares of the other agents (cannot be faced or entered)
   uint32_t goal_mask, goal_kind;
 };
 
@@ -108,7 +109,7 @@ __device__ __forceinline__ uint32_t single_actions(const World& w, const PState&
   const int hand = held_by(p, agent);
   for (uint32_t a = 0; a < 4; a++) {
     const uint32_t t = (p.cell[agent] + (uint32_t)gc::action_delta(a)) & 63u;
-    if (t == p.cell[0] || t == p.cell[1]) continue;  // :71 not into an agent's current square
+    if (t == p.cell[0] || t == p.cell[1] || ((w.blocked >> t) & 1ull)) continue;  // :71 an agent stands there
     if (((w.floorp >> t) & 1ull) || ((w.deliv >> t) & 1ull)) {  // :74-78
       valid |= 1u << a;
       continue;
@@ -220,6 +221,7 @@ joint_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant
     if (threadIdx.x == 0) {
       const GcNavLevel& L = levels.lv[level_id ? level_id[env] : 0];
       const int sub = pairs.p[pi][0], ai = pairs.p[pi][1], aj = pairs.p[pi][2];
+      const bool level1 = pairs.p[pi][3] != 0;
       const uint4 s = state[env];
       root_state = 1;
       if (aj != 0xFF && (uint32_t)sub < L.n_subtasks) {
@@ -228,6 +230,7 @@ joint_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant
         for (int i = 0; i < n_agents; i++)
           if (i != ai && i != aj) frozen |= 1ull << ((s.x >> (6 * i)) & 63u);
         w.floorp = L.floor_mask & ~frozen;
+        w.blocked = level1 ? frozen : 0ull;
         w.nonfloor = ~w.floorp;
         w.cut = L.cut_mask;
         w.deliv = L.deliv_mask;
@@ -243,7 +246,8 @@ joint_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant
           const uint32_t holder = sl >> 13;
           if (holder >= 1u && holder <= 4u)
             sl = (int)holder == ai + 1 ? ((sl & 0x7fu) | (1u << 13))
-                 : (int)holder == aj + 1 ? ((sl & 0x7fu) | (2u << 13)) : GC_SLOT_DEAD;
+                 : (int)holder == aj + 1 ? ((sl & 0x7fu) | (2u << 13))
+                 : level1 ? ((sl & 0x7fu) | (3u << 13)) : GC_SLOT_DEAD;  // level 1: kept but out of reach
           p.slot[k] = sl;
         }
         goal_exists = is_goal(w, p);  // a goal object is already there: the count can never rise (one food of each kind)

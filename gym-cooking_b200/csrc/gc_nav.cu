@@ -65,7 +65,8 @@ int gc_pairs_to_dev(const uint8_t* pairs, int n_pairs, int n_agents, GcPairs* ou
   memset(out, 0, sizeof(*out));
   out->n = n_pairs;
   for (int k = 0; k < n_pairs; k++) {
-    const uint8_t s = pairs[3 * k], i = pairs[3 * k + 1], j = pairs[3 * k + 2];
+    const uint8_t s = pairs[3 * k] & 0x7F, i = pairs[3 * k + 1], j = pairs[3 * k + 2];
+    out->p[k][3] = pairs[3 * k] >> 7;  // 1 = level-1 planning world (other agents are plain obstacles)
     if (s >= GC_MAX_SUBTASKS || i >= n_agents || (j != 0xFF && (j >= n_agents || j == i)))
       return gc_fail(GC_E_ARG, "pair %d = (%d, %d, %d) is out of range", k, s, i, j);
     out->p[k][0] = s;

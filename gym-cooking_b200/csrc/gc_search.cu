@@ -37,6 +37,7 @@ struct Ctx {
   unsigned long long floorp;   // walkable squares of the planning world (floor minus frozen agents)
   unsigned long long region;   // squares of floorp the agent can ever stand on (its connected component)
   unsigned long long putable;  // squares an object may be put on: every non-walkable, non-delivery square
+  unsigned long long blocked;  // level-1 only: squares of the other agents (obstacles that hold nothing)
   unsigned long long cut, deliv;
   const uint8_t* dstat;        // static all-pairs floor distances of the level (shared memory)
   gc_subtask st;
@@ -116,7 +117,7 @@ __device__ int heuristic(const Ctx& cx, const Plan& p, const uint8_t* dist) {
     const unsigned long long targets = cx.st.kind == GC_ST_CHOP ? cx.cut : cx.deliv;
     // bring the start object (mask a) to a target square
     for (int k = 0; k < GC_MAX_OBJECTS; k++) {
-      if ((p.slot[k] & 0x7fu) != cx.st.a || (p.slot[k] >> 13) == 7u) continue;
+      if ((p.slot[k] & 0x7fu) != cx.st.a || (p.slot[k] >> 13) >= 3u) continue;  // 3 = inert, 7 = dead
       if (held(p.slot[k])) {
         for (unsigned long long t = targets; t; t &= t - 1) {
           const int r = reach(cx, dist, (uint32_t)__ffsll((long long)t) - 1u);
@@ -132,9 +133,9 @@ __device__ int heuristic(const Ctx& cx, const Plan& p, const uint8_t* dist) {
     }
   } else {  // Merge: one of the two parts in hand, facing the other
     for (int ka = 0; ka < GC_MAX_OBJECTS; ka++) {
-      if ((p.slot[ka] & 0x7fu) != cx.st.a || (p.slot[ka] >> 13) == 7u) continue;
+      if ((p.slot[ka] & 0x7fu) != cx.st.a || (p.slot[ka] >> 13) >= 3u) continue;
       for (int kb = 0; kb < GC_MAX_OBJECTS; kb++) {
-        if (kb == ka || (p.slot[kb] & 0x7fu) != cx.st.b || (p.slot[kb] >> 13) == 7u) continue;
+        if (kb == ka || (p.slot[kb] & 0x7fu) != cx.st.b || (p.slot[kb] >> 13) >= 3u) continue;
         const bool a_stuck = lying(p.slot[ka]) && ((cx.deliv >> sq_of(p.slot[ka])) & 1ull);
         const bool b_stuck = lying(p.slot[kb]) && ((cx.deliv >> sq_of(p.slot[kb])) & 1ull);
         if (a_stuck || b_stuck) continue;
@@ -285,6 +286,7 @@ subtask_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_consta
   const int lvl = MULTI ? level_id[env] : 0;
   const GcNavLevel& L = levels.lv[lvl];
   const int sub = pairs.p[pi][0], ai = pairs.p[pi][1], aj = pairs.p[pi][2];
+  const bool level1 = pairs.p[pi][3] != 0;  // e2e_brtdp._configure_planner_level :379-381: nobody is removed
   float* q = q_out ? q_out + idx * 25 : nullptr;
   if (q)
     for (int a = 0; a < 25; a++) q[a] = INFINITY;
@@ -307,7 +309,8 @@ subtask_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_consta
     for (int i = 0; i < NA; i++)
       if (i != ai) frozen |= 1ull << ((s.x >> (6 * i)) & 63u);
     cx.floorp = L.floor_mask & ~frozen;
-    cx.putable = ~cx.floorp & ~cx.deliv;
+    cx.blocked = level1 ? frozen : 0ull;
+    cx.putable = ~cx.floorp & ~cx.deliv & ~cx.blocked;
     Plan p;
     p.cell = (s.x >> (6 * ai)) & 63u;
     // With a single mover and static obstacles the set of squares it can stand on never
@@ -323,7 +326,10 @@ subtask_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_consta
     for (int k = 0; k < GC_MAX_OBJECTS; k++) {
       uint32_t sl = gcnav::slot_of(s, k);
       const uint32_t holder = sl >> 13;
-      if (holder >= 1u && holder <= 4u) sl = (holder == (uint32_t)(ai + 1)) ? ((sl & 0x7fu) | (1u << 13)) : GC_SLOT_DEAD;
+      // level 0 deletes what the frozen agents hold (:397-399); level 1 keeps it, out of reach (holder code 3)
+      if (holder >= 1u && holder <= 4u)
+        sl = (holder == (uint32_t)(ai + 1)) ? ((sl & 0x7fu) | (1u << 13))
+                                            : (level1 ? ((sl & 0x7fu) | (3u << 13)) : GC_SLOT_DEAD);
       p.slot[k] = sl;
       if ((sl >> 13) != 7u && (sl & 0x7fu) == cx.st.goal &&
           (cx.st.kind != GC_ST_DELIVER || (lying(sl) && ((cx.deliv >> sq_of(sl)) & 1ull))))
@@ -337,6 +343,7 @@ subtask_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_consta
       if (v_start < kInf) {
         for (int a = 0; a < 4; a++) {
           const uint32_t tgt = (p.cell + (uint32_t)gc::action_delta((uint32_t)a)) & 63u;
+          if ((cx.blocked >> tgt) & 1ull) continue;  // another agent stands there (navigation_planner/utils.py:71)
           Plan nx = p;
           bool valid = false, goal_now = false;
           if ((cx.floorp >> tgt) & 1ull) {

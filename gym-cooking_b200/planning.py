@@ -29,9 +29,14 @@ def bd_posterior(probs, alive, hyp_pair, pair_w, qdiff, n_valid, act_idx, beta):
 
 
 def _pairs_array(pairs):
-    """[(subtask index, agent i, agent j or None)] -> host uint8[n_pairs][3]."""
-    arr = np.array([[s, i, 255 if j is None else j] for (s, i, j) in pairs], dtype=np.uint8).reshape(-1, 3)
-    return np.ascontiguousarray(arr)
+    """[(subtask index, agent i, agent j or None[, level1])] -> host uint8[n_pairs][3]; a truthy
+    fourth element selects the level-1 planning world (bit 7 of the subtask byte, gymcook.h)."""
+    rows = []
+    for pr in pairs:
+        s, i, j = pr[0], pr[1], pr[2]
+        level1 = len(pr) > 3 and pr[3]
+        rows.append([s | (0x80 if level1 else 0), i, 255 if j is None else j])
+    return np.ascontiguousarray(np.array(rows, dtype=np.uint8).reshape(-1, 3))
 
 
 def lower_bound(batch, pairs, out=None):

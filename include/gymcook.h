@@ -216,7 +216,11 @@ int gc_bd_posterior_f64(double* probs, const uint8_t* alive, const uint8_t* hyp_
  * Distance lower bound of env.get_lower_bound_for_subtask_given_objs (env:594-664) =
  * World.get_lower_bound_between (utils/world.py:115-264) + holding penalty, for every
  * (env, pair): pair = (subtask index, agent i, agent j or 0xFF).
- *   pairs  HOST uint8[n_pairs][3]   lb  device float[n][n_pairs]  (29.0 = perimeter+1 = not doable) */
+ *   pairs  HOST uint8[n_pairs][3]   lb  device float[n][n_pairs]  (29.0 = perimeter+1 = not doable)
+ * For gc_subtask_q / gc_joint_q bit 7 of the subtask index selects the planning world: clear =
+ * level 0 (other agents become Agent-Counters, their held object is deleted, e2e:386-406), set =
+ * level 1 (everybody stays: the other agents are obstacles that can be neither entered nor used
+ * as counters, e2e:379-381 with navigation_planner/utils.py:62-71). */
 int gc_lower_bound(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
                    const uint32_t* state /*device*/, const uint8_t* pairs /*host*/, int n_pairs,
                    float* lb /*device*/, int64_t n, int n_agents, void* stream);

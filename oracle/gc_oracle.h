@@ -109,6 +109,7 @@ double gco_lower_bound(const gco_level* lv, const gco_env* e, const gco_subtask*
 /* exact level-0 V* and Q(start, .) by forward uniform-cost search over full env states with
  * the real transition function.  q has 25 entries (5 used when aj < 0), +inf = invalid.
  * Returns status: 0 ok, 1 goal satisfied at start, 2 unreachable, 3 budget exceeded. */
+void gco_set_planner_level(int level); /* 0 (default) or 1: planning world of the next calls */
 int gco_subtask_q(const gco_level* lv, const gco_env* e, const gco_subtask* st, int ai, int aj,
                   double* v, double* q, int max_states);
 

@@ -13,6 +13,7 @@
 static const int DX[5] = {0, 0, -1, 1, 0};
 static const int DY[5] = {1, -1, 0, 0, 0};
 #define NOPATH 1000000
+#define GCO_BLOCKED 4 /* level-1 planning: square of another agent */
 
 /* ------------------------------------------------------------------------------------ */
 /* World.reachability_graph (utils/world.py:67-107), queried like nx.shortest_path_length  */
@@ -273,6 +274,7 @@ static int single_actions(const gco_level* lv, const gco_env* e, int i) {
     for (int j = 0; j < e->n_agents; j++) blocked |= e->ag[j].x == nx && e->ag[j].y == ny; /* :71 (incl. self) */
     if (blocked) continue;
     int ty = lv->type[ny][nx];
+    if (ty == GCO_BLOCKED) continue; /* level 1: another agent stands there (:71) */
     if (ty == GCO_FLOOR || ty == GCO_DELIVERY) {
       valid |= 1 << act;
       continue;
@@ -350,6 +352,12 @@ static int* table_slot(table_t* t, const uint32_t w[4]) {
     i = (i + 1) & (t->cap - 1);
   }
 }
+
+/* planning world of the next gco_subtask_q calls: 0 = level 0 (other agents become Agent-Counters and
+ * their held object is deleted, e2e_brtdp.py:386-406), 1 = level 1 (everybody stays; the other agents
+ * are obstacles that can be neither entered nor used as counters, :379-381 + nav utils :62-71) */
+static int g_planner_level = 0;
+void gco_set_planner_level(int level) { g_planner_level = level; }
 
 /* diagnostics: states inserted by the searches of the last gco_subtask_q call */
 long long gco_last_search_states = 0;
@@ -445,7 +453,8 @@ int gco_subtask_q(const gco_level* lv, const gco_env* e0, const gco_subtask* st,
       int h = s.ob[k].held_by, idx = -1;
       for (int qq = 0; qq < n_ag; qq++)
         if (ags[qq] == h) idx = qq;
-      if (idx < 0) s.ob[k].alive = 0;
+      if (idx < 0 && g_planner_level == 0) s.ob[k].alive = 0;
+      else if (idx < 0) s.ob[k].held_by = 2; /* level 1: stays in the world, out of reach */
       else s.ob[k].held_by = idx;
     }
   }
@@ -454,11 +463,11 @@ int gco_subtask_q(const gco_level* lv, const gco_env* e0, const gco_subtask* st,
     s.ag[qq].hold = -1;
   }
   for (int k = 0; k < s.n_objs; k++)
-    if (s.ob[k].alive && s.ob[k].held_by >= 0) s.ag[s.ob[k].held_by].hold = k;
+    if (s.ob[k].alive && s.ob[k].held_by >= 0 && s.ob[k].held_by < n_ag) s.ag[s.ob[k].held_by].hold = k;
   for (int i = 0; i < e0->n_agents; i++) {
     int in_set = 0;
     for (int qq = 0; qq < n_ag; qq++) in_set |= ags[qq] == i;
-    if (!in_set) p.lv.type[e0->ag[i].y][e0->ag[i].x] = GCO_COUNTER;
+    if (!in_set) p.lv.type[e0->ag[i].y][e0->ag[i].x] = g_planner_level ? GCO_BLOCKED : GCO_COUNTER;
   }
   p.base_count = goal_count(&p, &s);
   gco_last_search_states = 0;

@@ -136,7 +136,8 @@ def gen_lb():
 # brtdp
 # ---------------------------------------------------------------------------------------
 def _brtdp_job(args):
-    level, n_agents, seed, n_steps, budget_s = args
+    level, n_agents, seed, n_steps, budget_s = args[:5]
+    level1 = len(args) > 5 and args[5]
     env = sample_env(level, n_agents, seed, n_steps)
     if env is None:
         return []
@@ -159,11 +160,23 @@ def _brtdp_job(args):
             if lb >= env.world.perimeter:  # pruned as not doable in real runs (bd:98-156)
                 continue
             planner = brtdp.E2E_BRTDP(alpha=0.01, tau=2, cap=75, main_cap=100)
+            others = {}
+            if level1:
+                # level-1 planning world (e2e_brtdp.py:379-381): any non-empty dict of planners for the
+                # other agents; theirs plan the None subtask, i.e. they stay put
+                for nm in env.get_agent_names():
+                    if nm not in names:
+                        op = brtdp.E2E_BRTDP(alpha=0.01, tau=2, cap=75, main_cap=100)
+                        with H.quiet():
+                            op.set_settings(env=copy.copy(env), subtask=None, subtask_agent_names=(nm,))
+                        others[nm] = op
+                if not others:
+                    continue
             t0 = time.time()
             try:
                 with H.quiet():
                     action = planner.get_next_action(env=copy.copy(env), subtask=st, subtask_agent_names=names,
-                                                     other_agent_planners={})
+                                                     other_agent_planners=others)
             except (AssertionError, AttributeError, KeyError):
                 continue
             key = (planner.cur_state.get_repr(), st)
@@ -184,18 +197,18 @@ def _brtdp_job(args):
     return rows
 
 
-def gen_brtdp():
-    jobs, seed = [], 9000
+def gen_brtdp(level1=False):
+    jobs, seed = [], 9000 + (500 if level1 else 0)
     for level in LEVELS:
-        for n_agents in (2, 3):
-            for n_steps in (0, 6, 14, 24, 36):
+        for n_agents in ((2, 3) if not level1 else (2, 3)):
+            for n_steps in ((0, 6, 14, 24, 36) if not level1 else (0, 10, 22)):
                 seed += 1
-                jobs.append((level, n_agents, seed, n_steps, 240.0))
+                jobs.append((level, n_agents, seed, n_steps, 240.0 if not level1 else 120.0, level1))
     with Pool(8) as pool:
         res = pool.map(_brtdp_job, jobs, chunksize=1)
     rows = [r for rr in res for r in rr]
     np.savez_compressed(
-        os.path.join(GOLDEN, "brtdp_values.npz"), levels=np.array(LEVELS),
+        os.path.join(GOLDEN, "brtdp_values_level1.npz" if level1 else "brtdp_values.npz"), levels=np.array(LEVELS),
         level=np.array([r[0] for r in rows], dtype=np.uint8), n_agents=np.array([r[1] for r in rows], dtype=np.uint8),
         state=np.array([r[2] for r in rows], dtype=np.uint32), subtask=np.array([r[3] for r in rows], dtype=np.uint8),
         agent_i=np.array([r[4] for r in rows], dtype=np.uint8), agent_j=np.array([r[5] for r in rows], dtype=np.uint8),
@@ -341,4 +354,4 @@ def gen_bd():
 
 def main(what):
     os.makedirs(GOLDEN, exist_ok=True)
-    {"lb": gen_lb, "brtdp": gen_brtdp, "bd": gen_bd}[what]()
+    {"lb": gen_lb, "brtdp": gen_brtdp, "brtdp1": lambda: gen_brtdp(level1=True), "bd": gen_bd}[what]()

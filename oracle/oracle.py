@@ -95,6 +95,7 @@ def lib():
         L.gco_subtask_q.argtypes = [C.POINTER(Level), C.POINTER(Env), C.POINTER(Subtask), C.c_int, C.c_int,
                                     f64p, f64p, C.c_int]
         L.gco_subtask_q.restype = C.c_int
+        L.gco_set_planner_level.argtypes = [C.c_int]
     _lib = L
     return L
 
