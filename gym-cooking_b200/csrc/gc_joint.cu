@@ -254,14 +254,17 @@ joint_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant
         supported = supported && __popcll(w.nonfloor) <= 60;  // ranks 60..63 are reserved by compact_key
         if (!supported) {
           atomicOr(&flags[prob], 4);
-        } else if (!goal_exists) {
+        } else {
           const uint32_t v1 = single_actions(w, p, 0), v2 = single_actions(w, p, 1);
-          // (stay, stay) leaves the state unchanged: Q = 1 + V*(start), filled in by the finalize kernel
-          if (act != 24 && ((v1 >> a1) & 1u) && ((v2 >> a2) & 1u) && joint_ok(w, p, a1, a2)) {
-            interact(w, p, 0, a1);
-            interact(w, p, 1, a2);
-            root = p;
-            root_state = is_goal(w, p) ? 2 : 0;
+          if (((v1 >> a1) & 1u) && ((v2 >> a2) & 1u) && joint_ok(w, p, a1, a2)) {
+            q_out[prob * 25 + act] = INFINITY;  // offered (e2e_brtdp.get_actions :151-206)
+            // (stay, stay) leaves the state unchanged: Q = 1 + V*(start), filled in by the finalize kernel
+            if (!goal_exists && act != 24) {
+              interact(w, p, 0, a1);
+              interact(w, p, 1, a2);
+              root = p;
+              root_state = is_goal(w, p) ? 2 : 0;
+            }
           }
         }
       }
@@ -337,7 +340,7 @@ __global__ void joint_finalize_kernel(const __grid_constant__ GcPairs pairs, flo
   if (pairs.p[prob % pairs.n][2] == 0xFF) return;  // single-agent pair: not ours
   float best = INFINITY;
   for (int a = 0; a < 24; a++) best = fminf(best, q_out[prob * 25 + a]);
-  if (isfinite(best) && isfinite(q_out[prob * 25 + 24]) == false) {
+  if (isfinite(best)) {
     // (stay, stay) changes nothing: Q = 1 + V*(start).  It is offered whenever both agents may stay,
     // which is always (navigation_planner/utils.py:88), and never collides.
     q_out[prob * 25 + 24] = 1.0f + best;
@@ -354,7 +357,7 @@ __global__ void joint_init_kernel(const __grid_constant__ GcPairs pairs, float* 
   if (prob >= n * pairs.n) return;
   flags[prob] = 0;
   if (pairs.p[prob % pairs.n][2] == 0xFF) return;
-  for (int a = 0; a < 25; a++) q_out[prob * 25 + a] = INFINITY;
+  for (int a = 0; a < 25; a++) q_out[prob * 25 + a] = NAN;  // NaN = not offered; +inf = offered, goal out of reach
 }
 
 }  // namespace

@@ -289,7 +289,7 @@ subtask_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_consta
   const bool level1 = pairs.p[pi][3] != 0;  // e2e_brtdp._configure_planner_level :379-381: nobody is removed
   float* q = q_out ? q_out + idx * 25 : nullptr;
   if (q)
-    for (int a = 0; a < 25; a++) q[a] = INFINITY;
+    for (int a = 0; a < 25; a++) q[a] = NAN;  // NaN = action not offered; +inf = offered but the goal is out of reach
   float v = INFINITY;
   uint8_t status = ST_UNREACHABLE;
   if (aj != 0xFF) {
@@ -335,48 +335,43 @@ subtask_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_consta
           (cx.st.kind != GC_ST_DELIVER || (lying(sl) && ((cx.deliv >> sq_of(sl)) & 1ull))))
         goal_objects++;
     }
-    if (goal_objects == 0) {  // with one food of each kind a second goal object can never appear
-      // Q(start, a) for the actions get_single_actions offers (navigation_planner/utils.py:55-90)
-      int best_steps = kInf;
-      int q_steps[4] = {kInf, kInf, kInf, kInf};
-      const int v_start = solve(cx, p, 0);
-      if (v_start < kInf) {
-        for (int a = 0; a < 4; a++) {
-          const uint32_t tgt = (p.cell + (uint32_t)gc::action_delta((uint32_t)a)) & 63u;
-          if ((cx.blocked >> tgt) & 1ull) continue;  // another agent stands there (navigation_planner/utils.py:71)
-          Plan nx = p;
-          bool valid = false, goal_now = false;
-          if ((cx.floorp >> tgt) & 1ull) {
-            nx.cell = tgt;
-            valid = true;
-          } else {
-            uint32_t made;
-            bool delivered;
-            const bool changed = apply_interaction(cx, nx, tgt, made, delivered);
-            valid = changed || ((cx.deliv >> tgt) & 1ull);  // a Delivery square may always be faced (:77-78)
-            goal_now = changed && is_goal(cx, made, delivered);
-          }
-          if (!valid) continue;
-          int steps = 0;
-          if (!goal_now) steps = solve(cx, nx, max(0, v_start - 1));
-          if (cx.over) break;
-          if (steps < kInf) {
-            q_steps[a] = steps + 1;
-            best_steps = min(best_steps, steps + 1);
-          }
-        }
+    // Q(start, a) for the actions get_single_actions offers (navigation_planner/utils.py:55-90)
+    int best_steps = kInf;
+    int q_steps[4] = {kInf, kInf, kInf, kInf};
+    bool offered[4];
+    // with one food of each kind a second goal object can never appear: no search then
+    const int v_start = goal_objects == 0 ? solve(cx, p, 0) : kInf;
+    for (int a = 0; a < 4; a++) {
+      const uint32_t tgt = (p.cell + (uint32_t)gc::action_delta((uint32_t)a)) & 63u;
+      offered[a] = false;
+      if ((cx.blocked >> tgt) & 1ull) continue;  // another agent stands there (navigation_planner/utils.py:71)
+      Plan nx = p;
+      bool goal_now = false;
+      if ((cx.floorp >> tgt) & 1ull) {
+        nx.cell = tgt;
+        offered[a] = true;
+      } else {
+        uint32_t made;
+        bool delivered;
+        const bool changed = apply_interaction(cx, nx, tgt, made, delivered);
+        offered[a] = changed || ((cx.deliv >> tgt) & 1ull);  // a Delivery square may always be faced (:77-78)
+        goal_now = changed && is_goal(cx, made, delivered);
       }
-      if (cx.over) {
-        status = ST_BUDGET;
-      } else if (best_steps < kInf) {
-        status = ST_OK;
-        v = 1.1f * (float)best_steps;
-        if (q) {
-          for (int a = 0; a < 4; a++)
-            if (q_steps[a] < kInf) q[a] = 1.1f * (float)q_steps[a];
-          q[4] = 1.0f + v;  // staying costs time only and changes nothing
-        }
+      if (!offered[a] || v_start >= kInf || cx.over) continue;
+      int steps = 0;
+      if (!goal_now) steps = solve(cx, nx, max(0, v_start - 1));
+      if (steps < kInf) {
+        q_steps[a] = steps + 1;
+        best_steps = min(best_steps, steps + 1);
       }
+    }
+    if (cx.over) status = ST_BUDGET;
+    else if (best_steps < kInf) status = ST_OK;
+    if (best_steps < kInf) v = 1.1f * (float)best_steps;
+    if (q) {
+      for (int a = 0; a < 4; a++)
+        if (offered[a]) q[a] = q_steps[a] < kInf ? 1.1f * (float)q_steps[a] : INFINITY;
+      q[4] = 1.0f + v;  // staying is always offered (:88); it costs time only and changes nothing
     }
   }
   v_out[idx] = v;

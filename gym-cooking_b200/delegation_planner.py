@@ -24,6 +24,7 @@ import torch
 from . import navigation_planner, planning, recipe_planner
 
 SubtaskAllocation = namedtuple("SubtaskAllocation", "subtask subtask_agent_names")
+UNREACHABLE_Q = 100.0
 
 
 class SubtaskAllocDistribution:
@@ -250,8 +251,11 @@ class BayesianDelegator:
         if len(names) == 2 and self.agent_name in names:  # :677-679 only joint actions matching the partner's move
             other = 1 - names.index(self.agent_name)
             valid = [a for a in valid if a[other] == action[other]]
-        old_q = self.planner.Q(obs_tm1, action)
-        return [old_q - self.planner.Q(obs_tm1, a) for a in valid], valid.index(action)
+        # an offered action from which the goal is out of reach has Q = +inf; cap it so that the
+        # differences stay finite (the reference's heuristic values are always finite)
+        q = [min(self.planner.Q(obs_tm1, a), UNREACHABLE_Q) for a in valid]
+        old_q = q[valid.index(action)]
+        return [old_q - qa for qa in q], valid.index(action)
 
     def prob_nav_actions(self, obs_tm1, actions_tm1, subtask, subtask_agent_names, beta, no_level_1):
         qd, idx = self.likelihood_row(obs_tm1, actions_tm1, subtask, subtask_agent_names, no_level_1)

@@ -69,14 +69,14 @@ def solve_pair(env, subtask, subtask_agent_names, level1=False):
     pair = (0, idx[0], idx[1] if len(idx) > 1 else None, bool(level1))
     v, q, status = planning.subtask_q(pb, [pair])
     v, q, status = float(v[0, 0]), q[0, 0].tolist(), int(status[0, 0])
-    table = {}
+    table = {}  # NaN = not offered by get_single_actions / is_collision; +inf = offered, goal out of reach
     if len(idx) == 1:
         for a in range(5):
-            if q[a] != _INF:
+            if q[a] == q[a]:
                 table[engine.ACTIONS[a]] = q[a]
     else:
         for a in range(25):
-            if q[a] != _INF:
+            if q[a] == q[a]:
                 table[(engine.ACTIONS[a // 5], engine.ACTIONS[a % 5])] = q[a]
     return v, table, status
 
