@@ -248,6 +248,7 @@ def run_ours(args):
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)  # NCCL over NVLink, 1064 bytes
     stats = stats.cpu().tolist()
 
+    secondary = secondary_metrics(gcb, torch, dev) if rank == 0 else None
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -276,6 +277,7 @@ def run_ours(args):
                          "traffic": traffic},
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": "2^18 envs x 100 steps of the same action stream, %.1f s" % cpu_dt},
+            "secondary": secondary,
             "episode_stats": {"episodes": stats[0], "successes": stats[1], "sum_t_done": stats[2],
                               "running": stats[4], "reduced_with": "nccl all_reduce" if world > 1 else "single rank"},
         }
@@ -283,6 +285,69 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def secondary_metrics(gcb, torch, dev):
+    """The other two hot paths of BASELINE.json's metric, timed on resident synthetic inputs (CUDA events,
+    3 warm-up + 10 timed launches each): BD posterior updates/s (cfg-4 shape) and subtask values/s (cfg-3)."""
+    import itertools
+
+    def timed(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e-3
+
+    out = []
+    # path C: 2 agents open-divider_salad has H = 8 hypotheses over P = 8 likelihood rows of A <= 5 actions
+    n, H, P, A, E = 1 << 21, 8, 8, 5, 2  # 2^21 rows x 248 B = 520 MB > L2
+    g = torch.Generator(device=dev).manual_seed(7)
+    probs = torch.rand((n, H), device=dev, generator=g)
+    hyp = torch.randint(0, P, (n, H, E), device=dev, generator=g, dtype=torch.uint8)
+    w = torch.randint(1, 3, (n, P), device=dev, generator=g, dtype=torch.uint8)
+    qd = torch.randn((n, P, A), device=dev, generator=g)
+    nv = torch.full((n, P), A, device=dev, dtype=torch.uint8)
+    ai = torch.randint(0, A, (n, P), device=dev, generator=g, dtype=torch.uint8)
+    t = timed(lambda: gcb.bd_posterior(probs, None, hyp, w, qd, nv, ai, 1.3), 10)
+    bytes_per = 8 * H + 4 * P * A + 3 * P + H * E
+    out.append({"metric": "bd_posterior_updates_per_sec", "value": n / t, "unit": "updates/s", "dtype": "f32",
+                "config": "cfg-4 shape: H=8 hypotheses, P=8 likelihood rows, A=5 actions, 2^21 rows resident (520 MB)",
+                "bytes_per_update": bytes_per, "achieved_gbs": n * bytes_per / t / 1e9})
+    del probs, hyp, w, qd, nv, ai
+    # path B: cfg-3 (3 agents, full-divider_salad), envs diversified by k = env % 41 random steps
+    n = 1 << 14
+    kb = gcb.KitchenBatch("full-divider_salad", 3, n, HORIZON, device=dev)
+    acts = kb.random_actions(40, seed=1235)
+    idx = torch.arange(n, device=dev) % 41
+    for s_ in range(40):
+        a = acts[s_].clone()
+        a[idx <= s_] = 4
+        kb.step(a)
+    ns = len(kb.subtasks[0])
+    sets = [(i, None) for i in range(3)] + list(itertools.combinations(range(3), 2))
+    pairs = [(s_, i, j) for s_ in range(ns) for (i, j) in sets]
+    t = timed(lambda: gcb.lower_bound(kb, pairs), 5)
+    out.append({"metric": "lower_bounds_per_sec", "value": n * len(pairs) / t, "unit": "(env,pair)/s",
+                "config": "cfg-3: 3-agent full-divider_salad, 2^14 envs x %d pairs" % len(pairs)})
+    lb = gcb.lower_bound(kb, pairs)
+    doable = [p for k, p in enumerate(pairs) if bool((lb[:, k] < 28).any())][:GC_BENCH_MAX_PAIRS]
+    res = {}
+    t = timed(lambda: res.update(r=gcb.subtask_q(kb, doable)), 1)
+    status = res["r"][2]
+    out.append({"metric": "subtask_values_per_sec", "value": n * len(doable) / t, "unit": "(env,pair)/s",
+                "config": "cfg-3: 2^14 envs x %d doable pairs (%d joint), exact V* + Q[25]" % (
+                    len(doable), sum(1 for p in doable if p[2] is not None)),
+                "status_histogram": torch.bincount(status.flatten().long(), minlength=5).tolist()})
+    return out
+
+
+GC_BENCH_MAX_PAIRS = 24
 
 
 def main():
