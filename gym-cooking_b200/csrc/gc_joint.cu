@@ -174,6 +174,55 @@ __device__ __forceinline__ bool is_goal(const World& w, const PState& p) {
   return g;
 }
 
+// Necessary condition for the goal to be reachable at all, from square adjacency alone.  comp_k
+// = floor component of agent k (ignoring the partner), S_k = squares next to it.  An object gets
+// into k's hands only if k holds it, or it lies on a non-delivery square of S_k, or the partner
+// can get hold of it and a non-delivery square lies in both S_1 and S_2 (hand-over).  The final
+// chop / deliver / merge needs the acting agent next to a cutboard / delivery / the other part.
+// Occupancy is ignored, so the test only ever errs towards "maybe reachable"; pairs it rejects
+// (e.g. both agents on the far side of a full divider) are reported unreachable without the
+// exhaustive search that would otherwise burn the whole state budget 25 times.
+__device__ bool maybe_reachable(const World& w, const PState& p, uint32_t a_mask, uint32_t b_mask) {
+  unsigned long long comp[2], S[2];
+  for (int k = 0; k < 2; k++) {
+    comp[k] = 1ull << p.cell[k];
+    for (unsigned long long grow = comp[k]; grow;) {
+      grow = gcnav::neighbours(grow) & w.floorp & ~comp[k];
+      comp[k] |= grow;
+    }
+    S[k] = gcnav::neighbours(comp[k]) & w.nonfloor & ~w.blocked;
+  }
+  const bool handover = (S[0] & S[1] & ~w.deliv) != 0ull;
+  auto direct = [&](int k, uint32_t s) {  // slot s can get into agent k's hands without help
+    const uint32_t holder = s >> 13;
+    if (holder == (uint32_t)(k + 1)) return true;
+    return holder == 0u && ((S[k] & ~w.deliv) >> ((s >> 7) & 63u)) & 1ull;
+  };
+  auto can_hold = [&](int k, uint32_t s) { return direct(k, s) || (handover && direct(1 - k, s)); };
+  bool ok = false;
+  for (int i = 0; i < 4; i++) {
+    const uint32_t sa = p.slot[i];
+    if ((sa >> 13) >= 3u || (sa & 0x7fu) != a_mask) continue;
+    for (int k = 0; k < 2; k++) {
+      if (w.goal_kind == GC_ST_CHOP) ok |= can_hold(k, sa) && (S[k] & w.cut) != 0ull;
+      else if (w.goal_kind == GC_ST_DELIVER) ok |= can_hold(k, sa) && (S[k] & w.deliv) != 0ull;
+      else {
+        for (int j = 0; j < 4; j++) {
+          const uint32_t sb = p.slot[j];
+          if (j == i || (sb >> 13) >= 3u || (sb & 0x7fu) != b_mask) continue;
+          // k ends up holding one part and facing the other, which therefore must be able to lie in S_k
+          auto can_face = [&](uint32_t s) {
+            return ((s >> 13) == 0u && ((S[k] & ~w.deliv) >> ((s >> 7) & 63u)) & 1ull) || can_hold(k, s) ||
+                   (handover && direct(1 - k, s));
+          };
+          ok |= (can_hold(k, sa) && can_face(sb)) || (can_hold(k, sb) && can_face(sa));
+        }
+      }
+    }
+  }
+  return ok;
+}
+
 // insert / relax `p` with cost c (tenths); pushes it into its bucket when it improved
 __device__ __forceinline__ void relax(const World& w, Arena* A, uint32_t* bcount, uint32_t* n_states, int* over,
                                       const PState& p, uint32_t c) {
@@ -250,7 +299,9 @@ joint_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant
                  : level1 ? ((sl & 0x7fu) | (3u << 13)) : GC_SLOT_DEAD;  // level 1: kept but out of reach
           p.slot[k] = sl;
         }
-        goal_exists = is_goal(w, p);  // a goal object is already there: the count can never rise (one food of each kind)
+        // a goal object is already there: the count can never rise (one food of each kind); or the
+        // squares the two agents can touch rule the goal out
+        goal_exists = is_goal(w, p) || !maybe_reachable(w, p, st.a, st.b);
         supported = supported && __popcll(w.nonfloor) <= 60;  // ranks 60..63 are reserved by compact_key
         if (!supported) {
           atomicOr(&flags[prob], 4);

@@ -220,3 +220,34 @@ def test_joint_values_inside_reference_brtdp_bracket_and_equal_oracle(golden_dir
                     assert np.abs(q[e, k][fin] - oq[fin]).max() < 1e-4, (r, q[e, k], oq)
                     compared += 1
     assert checked >= 60 and compared >= 20 and budget <= 10, (checked, compared, budget)
+
+
+def test_level1_values_inside_reference_brtdp_bracket(golden_dir):
+    """Level-1 planning world (other agents stay, as plain obstacles; e2e_brtdp.py:379-381): values for
+    single and joint pairs inside the converged bracket of reference runs made with non-empty
+    other_agent_planners (oracle/gen_golden.py brtdp1)."""
+    g = np.load(os.path.join(golden_dir, "brtdp_values_level1.npz"))
+    conv = (g["v_u"] - g["v_l"] <= 0.01) & (g["at_goal"] == 0)
+    checked = budget = 0
+    for (lvl, n_agents), rows in sorted(_groups(g).items()):
+        rows = np.array([r for r in rows if conv[r]])
+        if len(rows) == 0:
+            continue
+        kb = gcb.KitchenBatch(str(g["levels"][lvl]), n_agents, len(rows), 100)
+        _load_states(kb, g["state"][rows])
+        masks = sorted(set(tuple(int(v) for v in m) for m in g["subtask"][rows]))
+        kb.set_subtask_masks(masks)
+        keys = [(masks.index(tuple(int(x) for x in g["subtask"][r])), int(g["agent_i"][r]),
+                 None if g["agent_j"][r] == 255 else int(g["agent_j"][r])) for r in rows]
+        pairs = sorted(set(keys), key=lambda p: (p[0], p[1], -1 if p[2] is None else p[2]))
+        v, q, status = gcb.subtask_q(kb, [p + (True,) for p in pairs])
+        v, status = v.cpu().numpy(), status.cpu().numpy()
+        for e, r in enumerate(rows):
+            k = pairs.index(keys[e])
+            if status[e, k] == 3:
+                budget += 1
+                continue
+            assert status[e, k] == 0, (r, status[e, k])
+            assert g["v_l"][r] - 1e-4 <= v[e, k] <= g["v_u"][r] + 1e-4, (r, keys[e], v[e, k], g["v_l"][r], g["v_u"][r])
+            checked += 1
+    assert checked >= 100 and budget <= 8, (checked, budget)
