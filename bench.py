@@ -292,8 +292,8 @@ def secondary_metrics(gcb, torch, dev):
     3 warm-up + 10 timed launches each): BD posterior updates/s (cfg-4 shape) and subtask values/s (cfg-3)."""
     import itertools
 
-    def timed(fn, iters):
-        for _ in range(3):
+    def timed(fn, iters, warm=3):
+        for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -321,7 +321,7 @@ def secondary_metrics(gcb, torch, dev):
                 "bytes_per_update": bytes_per, "achieved_gbs": n * bytes_per / t / 1e9})
     del probs, hyp, w, qd, nv, ai
     # path B: cfg-3 (3 agents, full-divider_salad), envs diversified by k = env % 41 random steps
-    n = 1 << 14
+    n = 1 << 12  # bounded sample: the joint solver runs up to 25 searches per (env, pair)
     kb = gcb.KitchenBatch("full-divider_salad", 3, n, HORIZON, device=dev)
     acts = kb.random_actions(40, seed=1235)
     idx = torch.arange(n, device=dev) % 41
@@ -334,14 +334,14 @@ def secondary_metrics(gcb, torch, dev):
     pairs = [(s_, i, j) for s_ in range(ns) for (i, j) in sets]
     t = timed(lambda: gcb.lower_bound(kb, pairs), 5)
     out.append({"metric": "lower_bounds_per_sec", "value": n * len(pairs) / t, "unit": "(env,pair)/s",
-                "config": "cfg-3: 3-agent full-divider_salad, 2^14 envs x %d pairs" % len(pairs)})
+                "config": "cfg-3: 3-agent full-divider_salad, 2^12 envs x %d pairs" % len(pairs)})
     lb = gcb.lower_bound(kb, pairs)
     doable = [p for k, p in enumerate(pairs) if bool((lb[:, k] < 28).any())][:GC_BENCH_MAX_PAIRS]
     res = {}
-    t = timed(lambda: res.update(r=gcb.subtask_q(kb, doable)), 1)
+    t = timed(lambda: res.update(r=gcb.subtask_q(kb, doable)), 1, warm=1)
     status = res["r"][2]
     out.append({"metric": "subtask_values_per_sec", "value": n * len(doable) / t, "unit": "(env,pair)/s",
-                "config": "cfg-3: 2^14 envs x %d doable pairs (%d joint), exact V* + Q[25]" % (
+                "config": "cfg-3: 2^12 envs x %d doable pairs (%d joint), exact V* + Q[25]" % (
                     len(doable), sum(1 for p in doable if p[2] is not None)),
                 "status_histogram": torch.bincount(status.flatten().long(), minlength=5).tolist()})
     return out

@@ -228,7 +228,7 @@ def test_level1_values_inside_reference_brtdp_bracket(golden_dir):
     other_agent_planners (oracle/gen_golden.py brtdp1)."""
     g = np.load(os.path.join(golden_dir, "brtdp_values_level1.npz"))
     conv = (g["v_u"] - g["v_l"] <= 0.01) & (g["at_goal"] == 0)
-    checked = budget = 0
+    checked = budget = below = 0
     for (lvl, n_agents), rows in sorted(_groups(g).items()):
         rows = np.array([r for r in rows if conv[r]])
         if len(rows) == 0:
@@ -248,6 +248,23 @@ def test_level1_values_inside_reference_brtdp_bracket(golden_dir):
                 budget += 1
                 continue
             assert status[e, k] == 0, (r, status[e, k])
-            assert g["v_l"][r] - 1e-4 <= v[e, k] <= g["v_u"][r] + 1e-4, (r, keys[e], v[e, k], g["v_l"][r], g["v_u"][r])
+            assert v[e, k] <= g["v_u"][r] + 1e-4, (r, keys[e], v[e, k], g["v_u"][r])
+            if v[e, k] < g["v_l"][r] - 1e-4:
+                # The reference "converged" ABOVE the optimum: its value_init heuristic only scores
+                # "fetch A, then go to B" for Merge (world.py:181-189), which is not admissible when
+                # fetching B first is shorter, and BRTDP then prunes the better plan.  Accept only if
+                # the exhaustive-search oracle confirms our value, and only for Merge subtasks.
+                assert int(g["subtask"][r][0]) == 2, (r, keys[e])
+                lv = O.parse_level(gcb.levels.level_text(str(g["levels"][lvl])), 100)
+                O.lib().gco_set_planner_level(1)
+                try:
+                    if keys[e][2] is None:
+                        ost, ov, _ = _oracle_q(lv, g["state"][r], n_agents, masks[keys[e][0]], keys[e][1])
+                    else:
+                        ost, ov, _ = _oracle_joint(lv, g["state"][r], n_agents, masks[keys[e][0]], keys[e][1], keys[e][2])
+                finally:
+                    O.lib().gco_set_planner_level(0)
+                assert ost == 0 and abs(ov - v[e, k]) < 1e-4, (r, keys[e], v[e, k], ov)
+                below += 1
             checked += 1
-    assert checked >= 100 and budget <= 8, (checked, budget)
+    assert checked >= 100 and budget <= 8 and below <= checked // 10, (checked, budget, below)
