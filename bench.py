@@ -248,7 +248,7 @@ def run_ours(args):
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)  # NCCL over NVLink, 1064 bytes
     stats = stats.cpu().tolist()
 
-    secondary = secondary_metrics(gcb, torch, dev) if rank == 0 else None
+    secondary = secondary_metrics(gcb, torch, dev) if (rank == 0 and not args.no_secondary) else None
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -356,6 +356,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the planner / posterior side metrics (used for short ncu passes)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 400:
