@@ -259,16 +259,39 @@ step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ sta
                 unsigned long long* __restrict__ hash, uint32_t* __restrict__ collisions,
                 uint8_t* __restrict__ executed, int64_t n) {
   __shared__ __align__(16) gclut::Tables T;
-  // Persistent CTAs: the 5.9 KB of tables are loaded once per CTA and reused for every env the
-  // CTA walks (a one-env-per-thread grid spent ~20 % of its instructions refilling them).
+  __shared__ __align__(16) uint4 s_stage[kThreads];  // each thread's NEXT state, filled by cp.async
+  // Persistent CTAs: the 5.9 KB of tables are loaded once per CTA and reused for every env the CTA
+  // walks (a one-env-per-thread grid spent ~20 % of its instructions refilling them).  DRAM latency
+  // is hidden by software pipelining WITHOUT registers: while a thread computes env i, the 16-byte
+  // state of its next env streams into its private shared-memory slot with cp.async (LDGSTS), and
+  // the next action word waits in one register.  (A register-prefetch variant pushed the kernel
+  // over 32 registers / 100 % occupancy and lost more than it won.)
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const uint32_t slot = (uint32_t)__cvta_generic_to_shared(&s_stage[threadIdx.x]);
+  uint32_t a_next[NA];
+#pragma unroll
+  for (int k = 0; k < NA; k++) a_next[k] = 4u;
+  if (i < n) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + i) : "memory");
+    load_actions<NA>(actions, i, a_next);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   gclut::load_tables(&T, &g_static_tables, P.mv);
   __syncthreads();
   const GcLevelDev& L = P.lv;
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-    uint4 s = gc::ld_stream(state + i);
+  for (; i < n; i += stride) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    uint4 s = s_stage[threadIdx.x];  // written by this thread's own cp.async: no CTA barrier needed
     uint32_t act[NA];
-    load_actions<NA>(actions, i, act);
+#pragma unroll
+    for (int k = 0; k < NA; k++) act[k] = a_next[k];
+    const int64_t inext = i + stride;
+    if (inext < n) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + inext) : "memory");
+      load_actions<NA>(actions, inext, a_next);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     bool done, success;
     if (s.x >> 31) {
       const uint32_t t = (s.x >> 24) & 127u;
