@@ -36,7 +36,8 @@ def build(force=False, verbose=False, extra=()):
     if not force and not is_stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-o", LIB_PATH] + sources()
+    extra = list(extra) + os.environ.get("GC_NVCC_EXTRA", "").split()  # e.g. -DGC_LUT_MIN_CTAS=6 for experiments
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB_PATH] + sources()
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -252,8 +252,11 @@ struct StepLutParams {
   gclut::MoveTable mv;
 };
 
+#ifndef GC_LUT_MIN_CTAS
+#define GC_LUT_MIN_CTAS 4
+#endif
 template <int NA, int NOBJ>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, GC_LUT_MIN_CTAS)
 step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ state,
                 const uint8_t* __restrict__ actions, uint8_t* __restrict__ reward_done,
                 unsigned long long* __restrict__ hash, uint32_t* __restrict__ collisions,
@@ -325,7 +328,8 @@ void fill_move_table(const GcLevelDev& L, gclut::MoveTable* mv) {
     }
 }
 
-// persistent grid of the table-driven kernel: GC_LUT_CTAS_PER_SM (default 8 = full occupancy)
+// persistent grid of the table-driven kernel: GC_LUT_CTAS_PER_SM (default 4 = what fits at 53
+// registers without spilling; measured faster than 6 or 8 CTAs of 40 / 32 registers with spills)
 inline unsigned lut_grid(int64_t n) {
   static int sms = 0, per_sm = 0;
   if (!sms) {
@@ -334,8 +338,8 @@ inline unsigned lut_grid(int64_t n) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
     const char* e = getenv("GC_LUT_CTAS_PER_SM");
-    per_sm = e ? atoi(e) : 8;
-    if (per_sm < 1 || per_sm > 8) per_sm = 8;
+    per_sm = e ? atoi(e) : 4;
+    if (per_sm < 1 || per_sm > 8) per_sm = 4;
   }
   const unsigned full = grid_for(n), cap = (unsigned)(sms * per_sm);
   return full < cap ? full : cap;
