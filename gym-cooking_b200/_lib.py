@@ -8,7 +8,7 @@ import torch
 
 from . import build as _build
 
-MAX_AGENTS, MAX_OBJECTS, MAX_GOALS, MAX_CELLS, MAX_SUBTASKS, MAX_LEVELS = 4, 6, 4, 64, 16, 16
+MAX_AGENTS, MAX_OBJECTS, MAX_GOALS, MAX_CELLS, MAX_SUBTASKS, MAX_LEVELS = 4, 6, 4, 64, 32, 16
 STATS_LEN = 133
 SLOT_DEAD = 0xE000
 
@@ -30,7 +30,7 @@ class Level(C.Structure):
         ("cell_type", C.c_uint8 * MAX_CELLS), ("agent_cell", C.c_uint8 * MAX_AGENTS),
         ("object_init", C.c_uint16 * MAX_OBJECTS), ("goal_mask", C.c_uint8 * MAX_GOALS),
         ("subtask", Subtask * MAX_SUBTASKS), ("recipe_code", C.c_uint8 * MAX_GOALS),
-        ("reserved", C.c_uint8 * 72),
+        ("reserved", C.c_uint8 * 8),
     ]
 
 

@@ -10,7 +10,7 @@ struct GcNavLevel {
   uint32_t n_subtasks;
   gc_subtask st[GC_MAX_SUBTASKS];
 };
-static_assert(sizeof(GcNavLevel) == 96, "GcNavLevel layout");
+static_assert(sizeof(GcNavLevel) == 32 + 4 * GC_MAX_SUBTASKS, "GcNavLevel layout");
 
 struct GcNavLevels {
   GcNavLevel lv[GC_MAX_LEVELS];

@@ -57,7 +57,7 @@ extern "C" {
 #define GC_MAX_GOALS 4
 #define GC_MAX_CELLS 64
 #define GC_GRID_STRIDE 8
-#define GC_MAX_SUBTASKS 16
+#define GC_MAX_SUBTASKS 32
 #define GC_MAX_PAIRS 128
 #define GC_MAX_JOINT_ACTIONS 25
 #define GC_MAX_HYPOTHESES 96
@@ -123,7 +123,7 @@ typedef struct gc_level {
   uint8_t goal_mask[GC_MAX_GOALS];       /* content mask that must lie on delivery_cell */
   gc_subtask subtask[GC_MAX_SUBTASKS];   /* recipe subtasks in the host's order */
   uint8_t recipe_code[GC_MAX_GOALS];     /* 1 SimpleTomato 2 SimpleLettuce 3 Salad 4 OnionSalad */
-  uint8_t reserved[72];
+  uint8_t reserved[8];
 } gc_level;
 
 /* ---- library ------------------------------------------------------------------------ */

@@ -103,8 +103,21 @@ def walker_actions(env, rng, eps, targets):
     return acts
 
 
+CUSTOM_LEVEL_DIR = os.path.join(GOLDEN, "levels")
+
+
+def install_custom_level(level):
+    """Levels that are not among the reference's nine live under tests/golden/levels/; the reference
+    opens `utils/levels/<name>.txt` relative to its cwd (env:146), i.e. inside the scratch copy."""
+    src = os.path.join(CUSTOM_LEVEL_DIR, level + ".txt")
+    if os.path.exists(src):
+        import shutil
+        shutil.copy(src, os.path.join(H.load_reference()["scratch"], "utils", "levels", level + ".txt"))
+
+
 def gen_one_trace(args):
     level, n_agents, seed, eps, max_t = args
+    install_custom_level(level)
     rng = np.random.RandomState(seed)
     env = H.make_env(level, n_agents, max_t)
     names = env.get_agent_names()
@@ -133,10 +146,10 @@ def gen_one_trace(args):
     return rec
 
 
-def gen_env():
+def gen_env(levels=LEVELS, out_name="env_traces.npz", seed0=1000):
     jobs = []
-    seed = 1000
-    for level in LEVELS:
+    seed = seed0
+    for level in levels:
         for n_agents in (1, 2, 3, 4):
             # eps = 1.0 is pure uniform-random (cfg-2 style); small eps is goal-directed
             for eps in (1.0, 1.0, 0.5, 0.3, 0.3, 0.15, 0.15, 0.15, 0.05, 0.05):
@@ -162,7 +175,7 @@ def gen_env():
     for r, rec in enumerate(recs):
         L = len(rec["actions"])
         length[r] = L
-        meta[r] = (LEVELS.index(rec["level"]), rec["n_agents"], rec["max_t"], int(rec["crashed"]))
+        meta[r] = (list(levels).index(rec["level"]), rec["n_agents"], rec["max_t"], int(rec["crashed"]))
         stats["crashed"] += int(rec["crashed"])
         if L:
             actions[r, :L, :rec["n_agents"]] = np.array(rec["actions"], dtype=np.uint8)
@@ -182,7 +195,7 @@ def gen_env():
         stats["merged"] += int(any(bin(m & 15).count("1") > 1 for (m, _, _, _) in last_items))
         stats["chopped"] += int(any(m >> 4 for (m, _, _, _) in last_items))
     os.makedirs(GOLDEN, exist_ok=True)
-    np.savez_compressed(os.path.join(GOLDEN, "env_traces.npz"), levels=np.array(LEVELS), meta=meta,
+    np.savez_compressed(os.path.join(GOLDEN, out_name), levels=np.array(levels), meta=meta,
                         length=length, actions=actions, executed=executed, t=t_arr, done=done,
                         reward=reward, ncoll=ncoll, agents=agents, keys=keys)
     print("env traces:", n, "steps:", int(length.sum()), stats)
@@ -192,6 +205,8 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "env"
     if what == "env":
         gen_env()
+    elif what == "env_custom":  # an 8x8 kitchen with an onion, three plates (6 objects) and OnionSalad
+        gen_env(levels=("onion-8x8",), out_name="env_traces_custom.npz", seed0=3000)
     else:
         import gen_golden_plan  # noqa: F401  (path B / C generators live there)
         gen_golden_plan.main(what)

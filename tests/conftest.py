@@ -35,3 +35,15 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def level_source(name):
+    """(text, KitchenBatch level argument) of a reference level or of a custom one under tests/golden/levels/"""
+    import gym_cooking_b200 as gcb
+    if name in gcb.levels.LEVEL_NAMES:
+        return gcb.levels.level_text(name), name
+    path = os.path.join(GOLDEN, "levels", name + ".txt")
+    return open(path).read(), path
+
+
+TRACE_FILES = ("env_traces.npz", "env_traces_custom.npz")

@@ -16,9 +16,12 @@ def _u32(t):
     return t.cpu().numpy().view(np.uint32)
 
 
-@pytest.fixture(scope="module")
-def traces(golden_dir):
-    return np.load(os.path.join(golden_dir, "env_traces.npz"))
+from conftest import TRACE_FILES, level_source
+
+
+@pytest.fixture(scope="module", params=TRACE_FILES)
+def traces(golden_dir, request):
+    return np.load(os.path.join(golden_dir, request.param))
 
 
 def test_golden_traces_bit_exact(traces):
@@ -31,7 +34,7 @@ def test_golden_traces_bit_exact(traces):
     checked = 0
     for (lvl, n_agents, max_t), rows in sorted(groups.items()):
         rows = np.array(rows)
-        kb = gcb.KitchenBatch(str(traces["levels"][lvl]), n_agents, len(rows), max_t, track_collisions=True)
+        kb = gcb.KitchenBatch(level_source(str(traces["levels"][lvl]))[1], n_agents, len(rows), max_t, track_collisions=True)
         hash_out = torch.empty(len(rows), dtype=torch.int64, device=kb.device)
         executed = torch.empty((len(rows), n_agents), dtype=torch.uint8, device=kb.device)
         L = length[rows]
@@ -60,18 +63,20 @@ def test_golden_traces_bit_exact(traces):
                     ks = [int(k) for k in keys[r] if k != 0x3FFF]
                     assert int(hk[r]) == O.hash_canonical(int(t[r]), ags, ks)
             checked += int(live.sum())
-    assert checked > 30000
+    assert checked > (30000 if meta.shape[0] > 100 else 3000)
 
 
 @pytest.mark.parametrize("level,n_agents", [
+    ("onion-8x8", 2), ("onion-8x8", 4),
     ("partial-divider_tl", 2), ("full-divider_salad", 3), ("open-divider_salad", 2), ("open-divider_salad", 4),
     ("open-divider_tomato", 1), ("full-divider_tl", 4), ("partial-divider_salad", 3),
 ])
 def test_step_matches_oracle_on_random_batches(level, n_agents):
     """65536 envs x 100 uniform-random steps, state compared bit for bit at every step."""
     n = 1 << 16
-    kb = gcb.KitchenBatch(level, n_agents, n, 100, track_collisions=True)
-    lv = O.parse_level(gcb.levels.level_text(level), 100)
+    text, src = level_source(level)
+    kb = gcb.KitchenBatch(src, n_agents, n, 100, track_collisions=True)
+    lv = O.parse_level(text, 100)
     ost = O.reset_state(lv, n_agents, n)
     assert (_u32(kb.state) == ost).all()
     acts = kb.random_actions(100, seed=77)
@@ -140,9 +145,11 @@ def test_multi_level_batch_matches_oracle():
 def test_success_episodes_stay_frozen(traces):
     """A delivered episode reports done|reward forever and its state stops changing."""
     meta = traces["meta"]
-    r = next(r for r in range(meta.shape[0]) if traces["reward"][r, traces["length"][r]] == 1)
+    r = next((r for r in range(meta.shape[0]) if traces["reward"][r, traces["length"][r]] == 1), None)
+    if r is None:
+        pytest.skip("no delivered episode in this fixture")
     lvl, n_agents, max_t = int(meta[r, 0]), int(meta[r, 1]), int(meta[r, 2])
-    kb = gcb.KitchenBatch(str(traces["levels"][lvl]), n_agents, 1, max_t)
+    kb = gcb.KitchenBatch(level_source(str(traces["levels"][lvl]))[1], n_agents, 1, max_t)
     for s in range(int(traces["length"][r])):
         kb.step(torch.from_numpy(traces["actions"][r, s:s + 1, :n_agents].copy()).to(kb.device))
     assert int(kb.reward_done[0]) == 3
