@@ -7,6 +7,7 @@ import torch
 
 from . import _lib
 
+MAX_PAIRS = 128  # GC_MAX_PAIRS
 PERIMETER_NOT_DOABLE = 28.0  # a 7x7 kitchen: lower bound >= world.perimeter means "not doable" (bd:156)
 
 
@@ -44,6 +45,13 @@ def lower_bound(batch, pairs, out=None):
     KitchenBatch -> float32[N][n_pairs].  The levels of `batch` must carry their subtasks
     (KitchenBatch.set_subtasks)."""
     lib = _lib.load()
+    if len(pairs) > MAX_PAIRS:  # GC_MAX_PAIRS per call: larger lists go in chunks
+        parts = [lower_bound(batch, pairs[k:k + MAX_PAIRS]) for k in range(0, len(pairs), MAX_PAIRS)]
+        res = torch.cat(parts, dim=1)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
     arr = _pairs_array(pairs)
     with torch.cuda.device(batch.device):
         if out is None:
@@ -59,6 +67,11 @@ def subtask_q(batch, pairs, want_q=True):
     status uint8[N][P]).  Single-agent pairs: gc_subtask_q (interaction-level IDA*); joint pairs:
     gc_joint_q (budgeted uniform-cost search, scratch arena allocated here as a torch tensor)."""
     lib = _lib.load()
+    if len(pairs) > MAX_PAIRS:
+        parts = [subtask_q(batch, pairs[k:k + MAX_PAIRS], want_q) for k in range(0, len(pairs), MAX_PAIRS)]
+        return (torch.cat([p[0] for p in parts], dim=1),
+                torch.cat([p[1] for p in parts], dim=1) if want_q else None,
+                torch.cat([p[2] for p in parts], dim=1))
     arr = _pairs_array(pairs)
     has_joint = bool((arr[:, 2] != 255).any())
     with torch.cuda.device(batch.device):

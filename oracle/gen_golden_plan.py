@@ -92,7 +92,10 @@ def agent_sets(n_agents):
 # lb
 # ---------------------------------------------------------------------------------------
 def _lb_job(args):
-    level, n_agents, seed, n_steps = args
+    level, n_agents, seed, n_steps = args[:4]
+    levels = args[4] if len(args) > 4 else LEVELS
+    from gen_golden import install_custom_level
+    install_custom_level(level)
     env = sample_env(level, n_agents, seed, n_steps)
     if env is None:
         return []
@@ -107,22 +110,22 @@ def _lb_job(args):
         for idx, names in agent_sets(n_agents):
             lb = env.get_lower_bound_for_subtask_given_objs(
                 subtask=st, subtask_agent_names=names, start_obj=start, goal_obj=goal, subtask_action_obj=action_obj)
-            rows.append((LEVELS.index(level), n_agents, words, masks, idx[0], idx[1] if len(idx) > 1 else 255, float(lb)))
+            rows.append((list(levels).index(level), n_agents, words, masks, idx[0], idx[1] if len(idx) > 1 else 255, float(lb)))
     return rows
 
 
-def gen_lb():
-    jobs, seed = [], 5000
-    for level in LEVELS:
+def gen_lb(levels=LEVELS, out_name="lower_bounds.npz", seed0=5000):
+    jobs, seed = [], seed0
+    for level in levels:
         for n_agents in (1, 2, 3, 4):
             for n_steps in (0, 3, 8, 15, 25, 40, 60):
                 seed += 1
-                jobs.append((level, n_agents, seed, n_steps))
+                jobs.append((level, n_agents, seed, n_steps, tuple(levels)))
     with Pool(8) as pool:
         res = pool.map(_lb_job, jobs, chunksize=2)
     rows = [r for rr in res for r in rr]
     np.savez_compressed(
-        os.path.join(GOLDEN, "lower_bounds.npz"), levels=np.array(LEVELS),
+        os.path.join(GOLDEN, out_name), levels=np.array(levels),
         level=np.array([r[0] for r in rows], dtype=np.uint8), n_agents=np.array([r[1] for r in rows], dtype=np.uint8),
         state=np.array([r[2] for r in rows], dtype=np.uint32), subtask=np.array([r[3] for r in rows], dtype=np.uint8),
         agent_i=np.array([r[4] for r in rows], dtype=np.uint8), agent_j=np.array([r[5] for r in rows], dtype=np.uint8),
@@ -354,4 +357,4 @@ def gen_bd():
 
 def main(what):
     os.makedirs(GOLDEN, exist_ok=True)
-    {"lb": gen_lb, "brtdp": gen_brtdp, "brtdp1": lambda: gen_brtdp(level1=True), "bd": gen_bd}[what]()
+    {"lb": gen_lb, "lb_custom": lambda: gen_lb(("onion-8x8",), "lower_bounds_custom.npz", 7000), "brtdp": gen_brtdp, "brtdp1": lambda: gen_brtdp(level1=True), "bd": gen_bd}[what]()

@@ -32,13 +32,17 @@ def _groups(g):
     return out
 
 
-def test_lower_bound_equals_reference(golden_dir):
-    g = np.load(os.path.join(golden_dir, "lower_bounds.npz"))
+from conftest import level_source
+
+
+@pytest.mark.parametrize("fixture", ["lower_bounds.npz", "lower_bounds_custom.npz"])
+def test_lower_bound_equals_reference(golden_dir, fixture):
+    g = np.load(os.path.join(golden_dir, fixture))
     checked = 0
     for (lvl, n_agents), rows in sorted(_groups(g).items()):
         rows = np.array(rows)
         states, inv = np.unique(g["state"][rows], axis=0, return_inverse=True)
-        kb = gcb.KitchenBatch(str(g["levels"][lvl]), n_agents, len(states), 100)
+        kb = gcb.KitchenBatch(level_source(str(g["levels"][lvl]))[1], n_agents, len(states), 100)
         _load_states(kb, states)
         # the reference's own subtask list (its food-food Merge argument order depends on PYTHONHASHSEED)
         masks = sorted(set(tuple(int(v) for v in m) for m in g["subtask"][rows]))

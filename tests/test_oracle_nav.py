@@ -20,10 +20,14 @@ def _env_from_words(words, n_agents):
     return e
 
 
-def test_lower_bound_equals_reference(golden_dir):
-    g = np.load(os.path.join(golden_dir, "lower_bounds.npz"))
+from conftest import level_source
+
+
+@pytest.mark.parametrize("fixture", ["lower_bounds.npz", "lower_bounds_custom.npz"])
+def test_lower_bound_equals_reference(golden_dir, fixture):
+    g = np.load(os.path.join(golden_dir, fixture))
     L = O.lib()
-    lv = {i: O.parse_level(gcb.levels.level_text(str(n)), 100) for i, n in enumerate(g["levels"])}
+    lv = {i: O.parse_level(level_source(str(n))[0], 100) for i, n in enumerate(g["levels"])}
     bad = 0
     for r in range(len(g["lb"])):
         n_agents = int(g["n_agents"][r])
@@ -39,4 +43,4 @@ def test_lower_bound_equals_reference(golden_dir):
                 print("row", r, "level", g["levels"][g["level"][r]], "subtask", (k, a, b, goal),
                       "agents", g["agent_i"][r], aj, "expected", g["lb"][r], "got", got)
     assert bad == 0
-    assert len(g["lb"]) > 5000
+    assert len(g["lb"]) > 4000
