@@ -138,160 +138,259 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t n
                : "memory");
 }
 
-template <typename T, int G, int AT>
-__global__ void bd_posterior_staged_kernel(T* __restrict__ probs, const uint8_t* __restrict__ alive,
-                                           const uint8_t* __restrict__ hyp_pair, const uint8_t* __restrict__ pair_w,
-                                           const T* __restrict__ qdiff, const uint8_t* __restrict__ n_valid,
-                                           const uint8_t* __restrict__ act_idx, T beta, int64_t n, int H, int P,
-                                           int A_rt, int E, int R) {
-  extern __shared__ __align__(16) unsigned char smem[];
+// shared-memory image of one tile of R rows (offsets in bytes from the stage base)
+struct TileLayout {
+  uint32_t qd, pr, hp, pw, nv, ai, al, bytes;
+};
+
+template <typename T>
+__host__ __device__ inline TileLayout tile_layout(int R, int H, int P, int A, int E) {
+  TileLayout t;
+  t.qd = 0;
+  t.pr = t.qd + (uint32_t)(R * P * A) * (uint32_t)sizeof(T);
+  t.hp = t.pr + (uint32_t)(R * H) * (uint32_t)sizeof(T);
+  t.pw = t.hp + (uint32_t)(R * H * E);
+  t.nv = t.pw + (uint32_t)(R * P);
+  t.ai = t.nv + (uint32_t)(R * P);
+  t.al = t.ai + (uint32_t)(R * P);
+  t.bytes = t.al + (uint32_t)(R * H);  // every section is a multiple of 16 bytes because R is
+  return t;
+}
+
+// one row group's share of a staged tile.  ONE: P <= G and H <= G, so lane `sub` owns at most
+// one likelihood row and one hypothesis and the loops disappear.
+template <typename T, int G, int AT, bool ONE>
+__device__ __forceinline__ void tile_compute(unsigned char* st, const TileLayout& lay, T* s_L, bool has_alive, T beta,
+                                             int rows, int H, int P, int A_rt, int E) {
   const int A = AT ? AT : A_rt;
-  const int64_t row0 = (int64_t)blockIdx.x * R;
-  const int rows = (int)min((int64_t)R, n - row0);
-  // [0,16): mbarrier; every section after it is a multiple of 16 bytes because R is
-  T* s_qd = reinterpret_cast<T*>(smem + 16);
-  T* s_pr = s_qd + R * P * A;
-  T* s_L = s_pr + R * H;
-  uint8_t* s_hp = reinterpret_cast<uint8_t*>(s_L + R * P);
-  uint8_t* s_pw = s_hp + R * H * E;
-  uint8_t* s_nv = s_pw + R * P;
-  uint8_t* s_ai = s_nv + R * P;
-  uint8_t* s_al = s_ai + R * P;
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem);
-
-  if (rows == R) {  // full CTA: seven bulk copies issued by one thread
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      const uint32_t b_qd = (uint32_t)(R * P * A) * (uint32_t)sizeof(T), b_pr = (uint32_t)(R * H) * (uint32_t)sizeof(T);
-      const uint32_t b_hp = (uint32_t)(R * H * E), b_p = (uint32_t)(R * P), b_al = alive ? (uint32_t)(R * H) : 0u;
-      const uint32_t total = b_qd + b_pr + b_hp + 3u * b_p + b_al;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
-      bulk_load(s_qd, qdiff + row0 * P * A, b_qd, bar);
-      bulk_load(s_pr, probs + row0 * H, b_pr, bar);
-      bulk_load(s_hp, hyp_pair + row0 * H * E, b_hp, bar);
-      bulk_load(s_pw, pair_w + row0 * P, b_p, bar);
-      bulk_load(s_nv, n_valid + row0 * P, b_p, bar);
-      bulk_load(s_ai, act_idx + row0 * P, b_p, bar);
-      if (alive) bulk_load(s_al, alive + row0 * H, b_al, bar);
-    }
-    __syncthreads();  // barrier initialised before anyone polls it
-    uint32_t ready = 0;
-    while (!ready) {
-      asm volatile(
-          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
-          : "=r"(ready)
-          : "r"(bar)
-          : "memory");
-    }
-  } else {  // ragged last CTA
-    stage_bytes(reinterpret_cast<unsigned char*>(s_qd), reinterpret_cast<const unsigned char*>(qdiff + row0 * P * A),
-                rows * P * A * (int)sizeof(T));
-    stage_bytes(reinterpret_cast<unsigned char*>(s_pr), reinterpret_cast<const unsigned char*>(probs + row0 * H),
-                rows * H * (int)sizeof(T));
-    stage_bytes(s_hp, hyp_pair + row0 * H * E, rows * H * E);
-    stage_bytes(s_pw, pair_w + row0 * P, rows * P);
-    stage_bytes(s_nv, n_valid + row0 * P, rows * P);
-    stage_bytes(s_ai, act_idx + row0 * P, rows * P);
-    if (alive) stage_bytes(s_al, alive + row0 * H, rows * H);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-  }
-
+  const T* s_qd = reinterpret_cast<const T*>(st + lay.qd);
+  T* s_pr = reinterpret_cast<T*>(st + lay.pr);
+  const uint8_t* s_hp = st + lay.hp;
+  const uint8_t* s_pw = st + lay.pw;
+  const uint8_t* s_nv = st + lay.nv;
+  const uint8_t* s_ai = st + lay.ai;
+  const uint8_t* s_al = st + lay.al;
   const int rl = threadIdx.x / G, sub = threadIdx.x & (G - 1);
   const bool row_ok = rl < rows;
-  // likelihood rows (bd:626-641, 682-689): lane sub takes p = sub, sub+G, ...
-  if (row_ok) {
-    for (int p = sub; p < P; p += G) {
-      const int rp = rl * P + p;
-      const int nv = s_nv[rp];
-      T L = T(0);
-      if (nv > 0) {
-        const T* qd = s_qd + rp * A;
-        const T qa = beta * qd[s_ai[rp]];
-        T mx = beta * qd[0], sum = T(0);
-        if (AT) {
-          T x[AT ? AT : 1];
+  // likelihood rows (bd:626-641, 682-689)
+  for (int p = sub; p < P; p += G) {
+    const int rp = rl * P + p;
+    const int nv = row_ok ? s_nv[rp] : 0;
+    T L = T(0);
+    if (nv > 0) {
+      const T* qd = s_qd + rp * A;
+      const T qa = beta * qd[s_ai[rp]];
+      T mx = beta * qd[0], sum = T(0);
+      if (AT) {
+        T x[AT ? AT : 1];
 #pragma unroll
-          for (int a = 0; a < AT; a++) x[a] = beta * qd[a];
+        for (int a = 0; a < AT; a++) x[a] = beta * qd[a];
 #pragma unroll
-          for (int a = 1; a < AT; a++) mx = a < nv ? max(mx, x[a]) : mx;
+        for (int a = 1; a < AT; a++) mx = a < nv ? max(mx, x[a]) : mx;
 #pragma unroll
-          for (int a = 0; a < AT; a++) sum += a < nv ? exp_t<T>(x[a] - mx) : T(0);
-        } else {
-          for (int a = 1; a < nv; a++) mx = max(mx, beta * qd[a]);
-          for (int a = 0; a < nv; a++) sum += exp_t<T>(beta * qd[a] - mx);
-        }
-        L = exp_t<T>(qa - mx) / sum;
+        for (int a = 0; a < AT; a++) sum += a < nv ? exp_t<T>(x[a] - mx) : T(0);
+      } else {
+        for (int a = 1; a < nv; a++) mx = max(mx, beta * qd[a]);
+        for (int a = 0; a < nv; a++) sum += exp_t<T>(beta * qd[a] - mx);
       }
-      s_L[rp] = L;
+      L = exp_t<T>(qa - mx) / sum;
     }
+    if (row_ok) s_L[rp] = L;
+    if (ONE) break;
   }
   __syncwarp();  // a row's G <= 32 lanes live in one warp
 
   T total = T(0);
   int n_alive = 0;
-  if (row_ok) {
-    for (int h = sub; h < H; h += G) {
-      const int rh = rl * H + h;
-      const bool ok = !alive || s_al[rh];
-      T mine = T(0);
-      if (ok) {
-        T update = T(0);
+  T mine1 = T(0);
+  bool ok1 = false;
+  for (int h = sub; h < H; h += G) {
+    const int rh = rl * H + h;
+    const bool ok = row_ok && (!has_alive || s_al[rh]);
+    T update = T(0);
+    if (ok) {
 #pragma unroll
-        for (int e = 0; e < GC_MAX_AGENTS; e++) {
-          if (e < E) {
-            const int p = s_hp[rh * E + e];
-            if (p != 0xFF) update += T(s_pw[rl * P + p]) * s_L[rl * P + p];
-          }
+      for (int e = 0; e < GC_MAX_AGENTS; e++) {
+        if (e < E) {
+          const int p0 = s_hp[rh * E + e];
+          const int p = p0 == 0xFF ? 0 : p0;
+          const T term = T(s_pw[rl * P + p]) * s_L[rl * P + p];
+          update += p0 == 0xFF ? T(0) : term;
         }
-        mine = s_pr[rh] * update;
-        total += mine;
-        n_alive += 1;
       }
-      s_pr[rh] = mine;
     }
+    const T mine = ok ? s_pr[rh] * update : T(0);
+    total += mine;
+    n_alive += ok ? 1 : 0;
+    if (ONE) {
+      mine1 = mine;
+      ok1 = ok;
+      break;
+    }
+    if (row_ok) s_pr[rh] = mine;
   }
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) {
     total += __shfl_xor_sync(0xffffffffu, total, o);
     n_alive += __shfl_xor_sync(0xffffffffu, n_alive, o);
   }
-  if (row_ok) {
-    const bool zero = total == T(0);
-    const T scale = zero ? T(0) : T(1) / total;
-    const T uni = zero ? T(1) / T(n_alive > 0 ? n_alive : 1) : T(0);
+  const bool zero = total == T(0);
+  const T scale = zero ? T(0) : T(1) / total;
+  const T uni = zero ? T(1) / T(n_alive > 0 ? n_alive : 1) : T(0);
+  if (ONE) {
+    if (row_ok && sub < H) s_pr[rl * H + sub] = ok1 ? mine1 * scale + uni : T(0);
+  } else if (row_ok) {
     for (int h = sub; h < H; h += G) {
       const int rh = rl * H + h;
-      const bool ok = !alive || s_al[rh];
+      const bool ok = !has_alive || s_al[rh];
       s_pr[rh] = ok ? s_pr[rh] * scale + uni : T(0);
     }
   }
-  if (rows == R) {  // posteriors back with one bulk store
+}
+
+// ---- persistent form: full tiles ----------------------------------------------------------
+// Each CTA walks tiles blockIdx.x, +gridDim.x, ... of R consecutive rows with a two-stage
+// pipeline: thread 0 issues the seven bulk copies of tile k+1 (one contiguous byte range per
+// input array) while all threads compute tile k out of shared memory; posteriors go back with
+// one bulk store per tile.
+template <typename T, int G, int AT, bool ONE>
+__global__ void bd_posterior_tiles_kernel(T* __restrict__ probs, const uint8_t* __restrict__ alive,
+                                          const uint8_t* __restrict__ hyp_pair, const uint8_t* __restrict__ pair_w,
+                                          const T* __restrict__ qdiff, const uint8_t* __restrict__ n_valid,
+                                          const uint8_t* __restrict__ act_idx, T beta, int n_tiles, int H, int P,
+                                          int A_rt, int E, int R) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int A = AT ? AT : A_rt;
+  const TileLayout lay = tile_layout<T>(R, H, P, A, E);
+  // [0,16): two mbarriers; then the likelihood exchange row; then two stages
+  T* s_L = reinterpret_cast<T*>(smem + 16);
+  unsigned char* stage0 = smem + 16 + (uint32_t)(R * P) * (uint32_t)sizeof(T);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(smem);
+  const bool has_alive = alive != nullptr;
+  const uint32_t tx = lay.bytes - (has_alive ? 0u : (uint32_t)(R * H));
+
+  auto issue = [&](int tile, int s) {
+    unsigned char* st = stage0 + (size_t)s * lay.bytes;
+    const uint32_t bar = bar0 + 8u * (uint32_t)s;
+    const int64_t row0 = (int64_t)tile * R;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+    bulk_load(st + lay.qd, qdiff + row0 * P * A, lay.pr - lay.qd, bar);
+    bulk_load(st + lay.pr, probs + row0 * H, lay.hp - lay.pr, bar);
+    bulk_load(st + lay.hp, hyp_pair + row0 * H * E, lay.pw - lay.hp, bar);
+    bulk_load(st + lay.pw, pair_w + row0 * P, lay.nv - lay.pw, bar);
+    bulk_load(st + lay.nv, n_valid + row0 * P, lay.ai - lay.nv, bar);
+    bulk_load(st + lay.ai, act_idx + row0 * P, lay.al - lay.ai, bar);
+    if (has_alive) bulk_load(st + lay.al, alive + row0 * H, lay.bytes - lay.al, bar);
+  };
+
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if ((int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+  }
+  __syncthreads();  // barriers initialised before anyone polls them
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+    const int s = it & 1;
+    unsigned char* st = stage0 + (size_t)s * lay.bytes;
+    if (threadIdx.x == 0 && tile + (int)gridDim.x < n_tiles) {
+      // the other stage was last read by tile it-1's compute (all threads passed the barrier at
+      // the end of that iteration) and by its bulk store: wait for the store to have read it
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      issue(tile + gridDim.x, s ^ 1);
+    }
+    const uint32_t bar = bar0 + 8u * (uint32_t)s, parity = (uint32_t)(it >> 1) & 1u;
+    uint32_t ready = 0;
+    while (!ready) {
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+          : "=r"(ready)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    }
+    tile_compute<T, G, AT, ONE>(st, lay, s_L, has_alive, beta, R, H, P, A_rt, E);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) {
-      const uint32_t src = (uint32_t)__cvta_generic_to_shared(s_pr);
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(probs + row0 * H), "r"(src),
-                   "r"((uint32_t)(R * H) * (uint32_t)sizeof(T))
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(st + lay.pr);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(probs + (int64_t)tile * R * H),
+                   "r"(src), "r"(lay.hp - lay.pr)
                    : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-  } else {
-    __syncthreads();
-    for (int i = threadIdx.x; i < rows * H; i += blockDim.x) probs[row0 * H + i] = s_pr[i];
   }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-template <typename T>
-size_t staged_bytes(int R, int H, int P, int A, int E) {
-  return 16u + (size_t)R * ((size_t)P * A * sizeof(T) + (size_t)H * sizeof(T) + (size_t)P * sizeof(T) + (size_t)H * E +
-                      3u * P + (size_t)H);
+// ---- ragged tail (< R rows) and shapes the bulk path does not take: plain staged CTA -------
+template <typename T, int G>
+__global__ void bd_posterior_tail_kernel(T* __restrict__ probs, const uint8_t* __restrict__ alive,
+                                         const uint8_t* __restrict__ hyp_pair, const uint8_t* __restrict__ pair_w,
+                                         const T* __restrict__ qdiff, const uint8_t* __restrict__ n_valid,
+                                         const uint8_t* __restrict__ act_idx, T beta, int64_t row0, int rows, int H,
+                                         int P, int A, int E, int R) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const TileLayout lay = tile_layout<T>(R, H, P, A, E);
+  T* s_L = reinterpret_cast<T*>(smem + 16);
+  unsigned char* st = smem + 16 + (uint32_t)(R * P) * (uint32_t)sizeof(T);
+  stage_bytes(st + lay.qd, reinterpret_cast<const unsigned char*>(qdiff + row0 * P * A), rows * P * A * (int)sizeof(T));
+  stage_bytes(st + lay.pr, reinterpret_cast<const unsigned char*>(probs + row0 * H), rows * H * (int)sizeof(T));
+  stage_bytes(st + lay.hp, hyp_pair + row0 * H * E, rows * H * E);
+  stage_bytes(st + lay.pw, pair_w + row0 * P, rows * P);
+  stage_bytes(st + lay.nv, n_valid + row0 * P, rows * P);
+  stage_bytes(st + lay.ai, act_idx + row0 * P, rows * P);
+  if (alive) stage_bytes(st + lay.al, alive + row0 * H, rows * H);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  tile_compute<T, G, 0, false>(st, lay, s_L, alive != nullptr, beta, rows, H, P, A, E);
+  __syncthreads();
+  const T* s_pr = reinterpret_cast<const T*>(st + lay.pr);
+  for (int i = threadIdx.x; i < rows * H; i += blockDim.x) probs[row0 * H + i] = s_pr[i];
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+template <typename T, int G, int AT, bool ONE>
+bool launch_tiles(T* probs, const uint8_t* alive, const uint8_t* hyp_pair, const uint8_t* pair_w, const T* qdiff,
+                  const uint8_t* n_valid, const uint8_t* act_idx, T beta, int n_tiles, int H, int P, int A, int E,
+                  int R, size_t smem_bytes, cudaStream_t st) {
+  auto kern = bd_posterior_tiles_kernel<T, G, AT, ONE>;
+  static int per_sm = -1;
+  static size_t configured = 0;
+  if (smem_bytes > configured) {
+    if (smem_bytes > 48u * 1024u &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = smem_bytes;
+    per_sm = -1;
+  }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, R * G, smem_bytes) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    return false;
+  }
+  per_sm = occ;
+  const int cap = sm_count() * per_sm;
+  kern<<<n_tiles < cap ? n_tiles : cap, R * G, smem_bytes, st>>>(probs, alive, hyp_pair, pair_w, qdiff, n_valid,
+                                                                 act_idx, beta, n_tiles, H, P, A, E, R);
+  return true;
+}
 
 template <typename T, int G>
 bool launch_staged(T* probs, const uint8_t* alive, const uint8_t* hyp_pair, const uint8_t* pair_w, const T* qdiff,
@@ -303,18 +402,37 @@ bool launch_staged(T* probs, const uint8_t* alive, const uint8_t* hyp_pair, cons
       !aligned16(act_idx) || (alive && !aligned16(alive)))
     return false;
   int R = 32;
-  if (R * G > 1024 || staged_bytes<T>(R, H, P, A, E) > 48u * 1024u) R = 16;
-  const size_t bytes = staged_bytes<T>(R, H, P, A, E);
-  if (bytes > 100u * 1024u) return false;
-  auto kern = A == 5 ? bd_posterior_staged_kernel<T, G, 5>
-                     : (A == 25 ? bd_posterior_staged_kernel<T, G, 25> : bd_posterior_staged_kernel<T, G, 0>);
-  if (bytes > 48u * 1024u &&
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
+  if (R * G > 1024 || tile_layout<T>(R, H, P, A, E).bytes > 24u * 1024u) R = 16;
+  const TileLayout lay = tile_layout<T>(R, H, P, A, E);
+  const size_t head = 16u + (size_t)R * P * sizeof(T);
+  if (head + 2u * lay.bytes > 200u * 1024u) return false;
+  if (n / R > 0x7fffffff) return false;
+  const int n_tiles = (int)(n / R);
+  const bool one = P <= G && H <= G;
+  const int tail = (int)(n - (int64_t)n_tiles * R);
+  if (tail > 0 && head + lay.bytes > 48u * 1024u &&
+      cudaFuncSetAttribute(bd_posterior_tail_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(head + lay.bytes)) != cudaSuccess) {
     cudaGetLastError();
-    return false;
+    return false;  // nothing launched yet: the caller falls back to the unstaged kernel
   }
-  kern<<<(unsigned)((n + R - 1) / R), R * G, bytes, st>>>(probs, alive, hyp_pair, pair_w, qdiff, n_valid, act_idx,
-                                                          beta, n, H, P, A, E, R);
+  if (n_tiles > 0) {
+    const size_t smem_bytes = head + 2u * lay.bytes;
+    bool ok;
+#define GC_BD_TILES(AT)                                                                                              \
+  (one ? launch_tiles<T, G, AT, true>(probs, alive, hyp_pair, pair_w, qdiff, n_valid, act_idx, beta, n_tiles, H, P, \
+                                      A, E, R, smem_bytes, st)                                                      \
+       : launch_tiles<T, G, AT, false>(probs, alive, hyp_pair, pair_w, qdiff, n_valid, act_idx, beta, n_tiles, H,   \
+                                       P, A, E, R, smem_bytes, st))
+    if (A == 5) ok = GC_BD_TILES(5);
+    else if (A == 25) ok = GC_BD_TILES(25);
+    else ok = GC_BD_TILES(0);
+#undef GC_BD_TILES
+    if (!ok) return false;
+  }
+  if (tail > 0)
+    bd_posterior_tail_kernel<T, G><<<1, R * G, head + lay.bytes, st>>>(
+        probs, alive, hyp_pair, pair_w, qdiff, n_valid, act_idx, beta, (int64_t)n_tiles * R, tail, H, P, A, E, R);
   return true;
 }
 
