@@ -275,12 +275,17 @@ step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ sta
   uint32_t a_next[NA];
 #pragma unroll
   for (int k = 0; k < NA; k++) a_next[k] = 4u;
+  // Programmatic dependent launch: the tables do not depend on earlier kernels, so this grid may
+  // start (and fill them) while the previous kernel of the stream drains; everything that can
+  // have been written by it (state, actions) is read only after griddepcontrol.wait.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  gclut::load_tables(&T, &g_static_tables, P.mv);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (i < n) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + i) : "memory");
     load_actions<NA>(actions, i, a_next);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  gclut::load_tables(&T, &g_static_tables, P.mv);
   __syncthreads();
   const GcLevelDev& L = P.lv;
   for (; i < n; i += stride) {
@@ -364,7 +369,18 @@ int launch_step(bool multi, const GcLevelsDev& lv, const uint8_t* level_id, uint
     StepLutParams P;
     P.lv = lv.lv[0];
     fill_move_table(P.lv, &P.mv);
-    step_lut_kernel<NA, NOBJ><<<lut_grid(n), kThreads, 0, st>>>(P, s4, actions, rd, h, coll, executed, n);
+    static const bool pdl = getenv("GC_STEP_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(lut_grid(n));
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, step_lut_kernel<NA, NOBJ>, P, s4, actions, rd, h, coll, executed, n);
+    if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step: launch failed: %s", cudaGetErrorString(err));
     return gc_check_launch("gc_env_step");
   }
   if (multi)
