@@ -1,0 +1,442 @@
+"""Device-resident Bayesian-Delegation loop: `main_loop` (main.py:85-117) for N kitchens at once.
+
+Every env of a `KitchenBatch` carries its own two `RealAgent`s (utils/agent.py:28-368), each with its
+own `BayesianDelegator` (delegation_planner/bayesian_delegator.py) - as tensors instead of Python
+objects:
+
+  reference object state                          here (N = envs, i = observer)
+  ------------------------------------------------------------------------------------------
+  RealAgent.incomplete_subtasks                   incomplete[N][i]   bit s = subtask s still open
+  RealAgent.subtask / subtask_agent_names         cur_sub[N][i], cur_joint[N][i]
+  BayesianDelegator.probs (dict alloc -> p)       probs[N][i][H] + alive[N][i][H] over the STATIC
+                                                  hypothesis table of the level's full subtask list
+  E2E_BRTDP.v_l / v_u dicts keyed by state repr   PlanCache: exact V*/Q rows keyed by planning state
+
+The hypothesis table is `delegation_planner.hypothesis_space` (bd:792-1000) evaluated once on all
+subtasks; what the reference regenerates per step from `incomplete_subtasks` and prunes with
+`subtask_alloc_is_doable` (bd:98-156, 200-256) is the `alive` mask.  Per step and observer the order
+of operations is RealAgent.select_action :82-104: update_subtasks (reset / set_priors / bayes_update,
+:176-203) -> select_subtask (bd:1009-1017) -> plan (:218-281); after env.step, refresh_subtasks
+(:151-171).  Hot numerics are the kernels (gc_lower_bound, gc_subtask_q/gc_joint_q through the
+cache, gc_bd_posterior_f64, gc_env_step); the masks, gathers and arg-max/min around them are torch
+tensor ops on the same device - nothing leaves HBM during an episode.
+"""
+import numpy as np
+import torch
+
+from . import engine, planning, recipe_planner
+from .delegation_planner import UNREACHABLE_Q, SubtaskAllocation, hypothesis_space
+
+_T_MASK = ~0xFF000000  # clears t and done of w[0] inside the low int64 of a packed state
+
+
+class _StateView:
+    """What planning.* needs from a KitchenBatch, over an arbitrary state tensor of the same level."""
+
+    def __init__(self, batch):
+        self._batch = batch
+        self.num_agents, self.n_levels, self.level_id, self.device = batch.num_agents, batch.n_levels, None, batch.device
+        self.state, self.num_envs = None, 0
+
+    def _lv(self):
+        return self._batch._lv()
+
+    def _stream(self):
+        return self._batch._stream()
+
+    def on(self, state):
+        self.state, self.num_envs = state, state.shape[0]
+        return self
+
+
+class PlanCache:
+    """Exact planner answers memoised by planning state (packed state with t and done cleared):
+    the batched form of the reference's `v_l`/`v_u` dicts keyed by `(state.get_repr(), subtask)`
+    (e2e:216-352) - a state reached by many envs, or again on a later step, is solved once."""
+
+    def __init__(self, batch, pairs):
+        self.view = _StateView(batch)
+        self.pairs = list(pairs)
+        dev, P = batch.device, len(self.pairs)
+        self.keys = torch.empty((0, 2), dtype=torch.int64, device=dev)
+        self.row = torch.empty((0,), dtype=torch.int64, device=dev)
+        self.v = torch.empty((0, P), dtype=torch.float32, device=dev)
+        self.q = torch.empty((0, P, 25), dtype=torch.float32, device=dev)
+        self.status = torch.empty((0, P), dtype=torch.uint8, device=dev)
+        self.solved_states = 0
+        self.lookups = 0
+
+    @staticmethod
+    def key_of(state):
+        k = state.contiguous().view(torch.int64).clone()  # [N][2]: (w0 | w1 << 32, w2 | w3 << 32)
+        k[:, 0] &= _T_MASK
+        return k
+
+    def lookup(self, state):
+        """cache row of every env of `state` (int32[N][4]); unseen planning states are solved first.
+        Rows are append-only, so indices returned earlier stay valid."""
+        uk, inv = torch.unique(self.key_of(state), dim=0, return_inverse=True)
+        self.lookups += state.shape[0]
+        C = self.keys.shape[0]
+        merged, pos = torch.unique(torch.cat([self.keys, uk]), dim=0, return_inverse=True)
+        pos_old, pos_new = pos[:C], pos[C:]
+        if merged.shape[0] > C:
+            present = torch.zeros(merged.shape[0], dtype=torch.bool, device=state.device)
+            present[pos_old] = True
+            miss = ~present[pos_new]
+            v, q, status = planning.subtask_q(self.view.on(uk[miss].contiguous().view(torch.int32)), self.pairs)
+            n_miss = v.shape[0]
+            self.solved_states += n_miss
+            row = torch.empty(merged.shape[0], dtype=torch.int64, device=state.device)
+            row[pos_old] = self.row
+            row[pos_new[miss]] = C + torch.arange(n_miss, device=state.device)
+            self.keys, self.row = merged, row  # sorted keys -> data row
+            self.v, self.q, self.status = torch.cat([self.v, v]), torch.cat([self.q, q]), torch.cat([self.status, status])
+        return self.row[pos_new][inv]
+
+
+def alloc_key(alloc, subtasks):
+    """canonical sort key of one subtask allocation (deterministic tie-breaking in tests)"""
+    return str(sorted((len(subtasks) if t.subtask is None else subtasks.index(t.subtask),
+                       tuple(sorted(int(nm.split("-")[1]) - 1 for nm in t.subtask_agent_names))) for t in alloc))
+
+
+class _ObserverTables:
+    """Static hypothesis / likelihood-row tables of one observer (agent index `me`, model type)."""
+
+    def __init__(self, owner, me, model):
+        S, names, dev = owner.S, owner.names, owner.device
+        self.me, self.model = me, model
+        self.spatial = model != "up"  # RealAgent.__init__ :52-55
+        allocs = list(dict.fromkeys(tuple(a) for a in hypothesis_space(model, names[me], names, owner.subtasks)))
+        if model == "dc":  # ensure_at_least_one_subtask (bd:1019-1024): used only when nothing else is alive
+            allocs.append((SubtaskAllocation(None, (names[me],)),))
+        H = len(allocs)
+        E = max(len(a) for a in allocs)
+        sub = np.full((H, E), -1, dtype=np.int64)      # subtask index, S = None, -1 = no entry
+        lid = np.zeros((H, E), dtype=np.int64)          # index into owner.lpairs (doable table)
+        pid0 = np.zeros((H, E), dtype=np.int64)         # level-0 planner pair (priors)
+        hyp_pair = np.full((H, E), 255, dtype=np.uint8)
+        static_ok = np.ones(H, dtype=bool)
+        fallback = np.zeros(H, dtype=bool)
+        sel_sub = np.full(H, S, dtype=np.int64)
+        sel_joint = np.zeros(H, dtype=bool)
+        rows, row_index = [], {}
+        keys = []
+        for h, alloc in enumerate(allocs):
+            ents = []
+            for e, t in enumerate(alloc):
+                ag = tuple(sorted(int(nm.split("-")[1]) - 1 for nm in t.subtask_agent_names))
+                s = S if t.subtask is None else owner.subtasks.index(t.subtask)
+                sub[h, e] = s
+                ents.append((s, ag))
+                if s < S:
+                    lid[h, e] = owner.lid[(s, ag)]
+                    pid0[h, e] = owner.pid[(s, ag, 0)]
+                elif len(ag) > 1:
+                    static_ok[h] = False  # nobody does None together (bd:243-246)
+                if me in ag:
+                    sel_sub[h], sel_joint[h] = s, len(ag) > 1
+                if model == "greedy" and me not in ag:
+                    continue
+                if s == S and len(ag) > 1:
+                    continue
+                if (s, ag) not in row_index:
+                    row_index[(s, ag)] = len(rows)
+                    rows.append((s, ag))
+                hyp_pair[h, e] = row_index[(s, ag)]
+            if all(s == S for s, _ in ents) and len(ents) > 1:
+                static_ok[h] = False  # at least one agent works (bd:249-253)
+            keys.append(alloc_key(alloc, owner.subtasks))
+        if model == "dc":
+            fallback[H - 1] = True
+            static_ok[H - 1] = False
+        self.H, self.E, self.P = H, E, len(rows)
+        self.allocs, self.keys, self.rows = allocs, keys, rows
+        order = sorted(range(H), key=lambda h: keys[h])
+        rank = np.empty(H, dtype=np.int64)
+        rank[order] = np.arange(H)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.ent_sub, self.ent_lid, self.ent_pid0 = t(sub), t(lid), t(pid0)
+        self.ent_has = t((sub >= 0) & (sub < S))
+        self.ent_subc = t(np.clip(sub, 0, S - 1))
+        self.hyp_pair = t(hyp_pair)
+        self.static_ok, self.fallback, self.rank = t(static_ok), t(fallback), t(rank)
+        self.sel_sub, self.sel_joint = t(sel_sub), t(sel_joint)
+        # likelihood rows (bd:461-689): None rows, single-agent rows (level 1 when somebody else is
+        # around, :650-654), joint rows (level 0)
+        kind = np.array([0 if s == S else (1 if len(ag) == 1 else 2) for s, ag in rows], dtype=np.int64)
+        agent = np.array([ag[0] for s, ag in rows], dtype=np.int64)
+        lvl1 = 1 if owner.NA > 1 else 0
+        pid = np.array([0 if s == S else owner.pid[(s, ag, lvl1 if len(ag) == 1 else 0)] for s, ag in rows],
+                       dtype=np.int64)
+        w = np.array([1 if model == "greedy" else len(ag) for s, ag in rows], dtype=np.uint8)
+        self.row_kind, self.row_agent, self.row_pid, self.pair_w = t(kind), t(agent), t(pid), t(w)
+        plan_lvl = 0 if model == "greedy" else lvl1  # RealAgent.plan :252-257
+        self.plan_single = t(np.array([owner.pid[(s, (me,), plan_lvl)] for s in range(S)], dtype=np.int64))
+        if owner.NA > 1:
+            self.plan_joint = t(np.array([owner.pid[(s, (0, 1), 0)] for s in range(S)], dtype=np.int64))
+        else:
+            self.plan_joint = self.plan_single
+
+
+class BatchedDelegation:
+    """N episodes of the reference's main loop with every agent a `RealAgent`, on one GPU."""
+
+    def __init__(self, level, num_envs, models=("bd", "bd"), max_num_timesteps=100, beta=1.3, none_action_prob=0.5,
+                 seed=1, deterministic=False, device=None):
+        self.NA = len(models)
+        if self.NA not in (1, 2):
+            raise NotImplementedError("the batched delegation loop covers 1 or 2 agents")
+        for m in models:
+            if m not in ("bd", "up", "fb", "dc", "greedy"):
+                raise ValueError("unknown model type %r" % (m,))
+        self.models, self.beta, self.none_action_prob = tuple(models), float(beta), float(none_action_prob)
+        self.deterministic = bool(deterministic)
+        self.kb = engine.KitchenBatch(level, self.NA, num_envs, max_num_timesteps, device=device, track_collisions=True)
+        self.device, self.N = self.kb.device, self.kb.num_envs
+        self.names = ["agent-%d" % (i + 1) for i in range(self.NA)]
+        self.subtasks = list(self.kb.subtasks[0])
+        self.S = S = len(self.subtasks)
+        lv = self.kb.levels[0]
+        self.perimeter = float(2 * (lv.width + lv.height))  # world.perimeter, env:198
+        agsets = [(i,) for i in range(self.NA)] + ([(0, 1)] if self.NA == 2 else [])
+        self.lpairs, self.lid, self.cpairs, self.pid = [], {}, [], {}
+        for s in range(S):
+            for ag in agsets:
+                self.lid[(s, ag)] = len(self.lpairs)
+                self.lpairs.append((s, ag[0], ag[1] if len(ag) > 1 else None))
+                for lvl in ((0, 1) if len(ag) == 1 and self.NA > 1 else (0,)):
+                    self.pid[(s, ag, lvl)] = len(self.cpairs)
+                    self.cpairs.append((s, ag[0], ag[1] if len(ag) > 1 else None, bool(lvl)))
+        self.cache = PlanCache(self.kb, self.cpairs)
+        self.tables = [_ObserverTables(self, i, models[i]) for i in range(self.NA)]
+        masks = [recipe_planner.subtask_masks(s) for s in self.subtasks]
+        dev = self.device
+        self.goal_mask = torch.tensor([m[3] for m in masks], dtype=torch.int64, device=dev)
+        self.is_deliver = torch.tensor([m[0] == recipe_planner.ST_DELIVER for m in masks], dtype=torch.bool, device=dev)
+        cell_type = torch.tensor(list(lv.cell_type), dtype=torch.int64, device=dev)
+        self.cell_type = cell_type
+        self.is_delivery = cell_type == 3
+        done_food = lambda m: ((m & 7) & ~(m >> 4)) == 0
+        mg = [[(not (a & b & 8)) and done_food(a | b) for b in range(128)] for a in range(128)]  # core.mergeable
+        self.mergeable = torch.tensor(mg, dtype=torch.bool, device=dev)
+        self.delta = torch.tensor([8, -8, -1, 1], dtype=torch.int64, device=dev)
+        self.gen = torch.Generator(device=dev)
+        self.gen.manual_seed(int(seed))
+        self.reset()
+
+    # -- state -------------------------------------------------------------------------------
+    def reset(self):
+        N, NA, dev = self.N, self.NA, self.device
+        self.kb.reset()
+        self.t = 0
+        self.incomplete = torch.full((N, NA), (1 << self.S) - 1, dtype=torch.int64, device=dev)
+        self.cur_sub = torch.full((N, NA), self.S, dtype=torch.int64, device=dev)
+        self.cur_joint = torch.zeros((N, NA), dtype=torch.bool, device=dev)
+        self.has_probs = torch.zeros((N, NA), dtype=torch.bool, device=dev)
+        self.probs = [torch.zeros((N, T.H), dtype=torch.float64, device=dev) for T in self.tables]
+        self.alive = [torch.zeros((N, T.H), dtype=torch.bool, device=dev) for T in self.tables]
+        self.executed = torch.full((N, NA), 4, dtype=torch.uint8, device=dev)
+        self.prev = None
+        self.posterior_updates = 0
+
+    def _slots(self, state):
+        """(mask, cell, holder) int64[N][6] of the six object slots"""
+        w = state.to(torch.int64) & 0xFFFFFFFF
+        sl = torch.stack([w[:, 1] & 0xFFFF, w[:, 1] >> 16, w[:, 2] & 0xFFFF, w[:, 2] >> 16, w[:, 3] & 0xFFFF,
+                          w[:, 3] >> 16], dim=1)
+        return sl & 0x7F, (sl >> 7) & 63, sl >> 13
+
+    def _agent_cells(self, state):
+        w0 = state[:, 0].to(torch.int64) & 0xFFFFFFFF
+        return torch.stack([(w0 >> (6 * i)) & 63 for i in range(self.NA)], dim=1)
+
+    def single_actions(self, state):
+        """nav_utils.get_single_actions (navigation_planner/utils.py:55-90) on the real env:
+        bool[N][NA][4] for the four moves (stay is always offered)."""
+        N = state.shape[0]
+        mask, cell, holder = self._slots(state)
+        cells = self._agent_cells(state)
+        lying = holder == 0
+        occ = torch.zeros((N, 64), dtype=torch.int64, device=state.device)
+        occ.scatter_add_(1, cell, mask * lying)
+        out = torch.zeros((N, self.NA, 4), dtype=torch.bool, device=state.device)
+        for i in range(self.NA):
+            hold = (mask * (holder == i + 1)).sum(1)
+            for a in range(4):
+                tgt = (cells[:, i] + self.delta[a]) & 63
+                kind = self.cell_type[tgt]
+                blocked = torch.zeros(N, dtype=torch.bool, device=state.device)
+                for j in range(self.NA):
+                    blocked |= cells[:, j] == tgt  # `if new_loc in agent_locs: continue`
+                mT = occ.gather(1, tgt[:, None])[:, 0]
+                counter = ((mT == 0) & (hold != 0)) | ((mT != 0) & (hold == 0)) | (
+                    (mT != 0) & (hold != 0) & self.mergeable[hold, mT])
+                out[:, i, a] = ~blocked & ((kind == 0) | (kind == 3) | counter)
+        return out
+
+    def goal_count(self, state, sub):
+        """RealAgent.def_subtask_completion (agent.py:286-368): objects equal to the subtask's goal
+        (for Deliver: lying on a delivery square), per env for that env's subtask `sub` (< S)"""
+        mask, cell, holder = self._slots(state)
+        goal = self.goal_mask[sub][:, None]
+        match = (holder != 7) & (mask == goal)
+        delivered = match & (holder == 0) & self.is_delivery[cell]
+        return torch.where(self.is_deliver[sub], delivered.sum(1), match.sum(1))
+
+    # -- one observer --------------------------------------------------------------------------
+    def _entries_ok(self, T, doable, inc):
+        ok = doable[:, T.ent_lid]  # [N][H][E]
+        if inc is not None:
+            ok = ok & (((inc[:, None, None] >> T.ent_subc) & 1) != 0)
+        return (ok | ~T.ent_has).all(-1)
+
+    def _pick(self, cand, rank=None):
+        """index of one True per row of `cand`: uniformly random, or lowest rank when deterministic"""
+        if self.deterministic:
+            r = rank if rank is not None else torch.arange(cand.shape[1], device=cand.device)
+            return torch.where(cand, r.expand_as(cand), cand.shape[1] + 1).argmin(1)
+        noise = torch.rand(cand.shape, device=cand.device, generator=self.gen) + 1e-6
+        return (noise * cand).argmax(1)
+
+    def _priors(self, T, alive, ci):
+        cnt = alive.sum(1, keepdim=True).clamp(min=1)
+        p = alive.double() / cnt
+        if T.spatial:  # get_spatial_priors bd:296-369: 4 * sum_t 1 / v_l(t)
+            inv_v = 1.0 / self.cache.v[ci].double().clamp(min=1e-9)
+            w = (inv_v[:, T.ent_pid0] * T.ent_has).sum(-1) * 4.0
+            p = p * w
+        tot = p.sum(1, keepdim=True)
+        return torch.where(tot == 0, alive.double() / cnt, p / tot.clamp(min=1e-300))
+
+    def _bayes_update(self, T, probs, alive):
+        """bayes_update bd:1045-1072 on obs_tm1 = self.prev, actions_tm1 = self.executed"""
+        N, dev, me = self.N, self.device, T.me
+        pv = self.prev
+        ex = self.executed.long()
+        q = self.cache.q[pv["ci"][:, None], T.row_pid[None, :]]  # [N][P][25]
+        taken = ex[:, T.row_agent]  # [N][P] action of the row's (first) agent
+        if self.NA == 2:  # joint rows: only joint actions matching the partner's move (bd:677-679)
+            partner = ex[:, 1 - me][:, None, None]
+            ai = torch.arange(5, device=dev)[None, None, :]
+            jidx = (ai * 5 + partner) if me == 0 else (partner * 5 + ai)
+            qj = q.gather(2, jidx.expand(N, T.P, 5))
+            is_joint = (T.row_kind == 2)[None, :, None]
+            q5 = torch.where(is_joint, qj, q[:, :, :5])
+            taken = torch.where(T.row_kind[None, :] == 2, ex[:, me][:, None].expand(N, T.P), taken)
+        else:
+            q5 = q[:, :, :5]
+        onehot = torch.arange(5, device=dev)[None, None, :] == taken[:, :, None]
+        valid = ~torch.isnan(q5) | onehot
+        qc = torch.nan_to_num(q5, nan=UNREACHABLE_Q, posinf=UNREACHABLE_Q).clamp(max=UNREACHABLE_Q).double()
+        old = (qc * onehot).sum(-1, keepdim=True)
+        qdiff = old - qc
+        # None rows (bd:618-641): [p_none, (1 - p_none) / k, ...] with k = the OBSERVER's move count
+        k = pv["offered"][:, me].sum(-1)  # [N]
+        none_row = torch.cat([torch.full((N, 1), self.none_action_prob, dtype=torch.float64, device=dev),
+                              ((1.0 - self.none_action_prob) / k.clamp(min=1).double())[:, None].expand(N, 4)], dim=1)
+        is_none = (T.row_kind == 0)[None, :, None]
+        none_valid = torch.arange(5, device=dev)[None, :] <= k[:, None]
+        valid = torch.where(is_none, none_valid[:, None, :], valid)
+        qdiff = torch.where(is_none, none_row[:, None, :], qdiff)
+        # compact the valid actions to the front (the kernel reads the first n_valid entries)
+        order = torch.sort((~valid).to(torch.uint8), dim=-1, stable=True).indices
+        qdiff = qdiff.gather(2, order).contiguous()
+        n_valid = valid.sum(-1)
+        pos = valid.cumsum(-1) - 1
+        act_idx = pos.gather(2, taken[:, :, None])[:, :, 0]
+        none_idx = torch.where(taken == 4, 0, 1).clamp(max=(n_valid - 1).clamp(min=0))
+        act_idx = torch.where(T.row_kind[None, :] == 0, none_idx, act_idx)
+        out = (probs * alive).contiguous()
+        planning.bd_posterior(out, alive.to(torch.uint8).contiguous(),
+                              T.hyp_pair[None].expand(N, T.H, T.E).contiguous(),
+                              T.pair_w[None].expand(N, T.P).contiguous(), qdiff,
+                              n_valid.to(torch.uint8).contiguous(), act_idx.to(torch.uint8).contiguous(), self.beta)
+        self.posterior_updates += N
+        return out
+
+    def _select_action(self, i, ci, doable, offered):
+        T, S, N, dev = self.tables[i], self.S, self.N, self.device
+        inc, cur = self.incomplete[:, i], self.cur_sub[:, i]
+        alive_new = self._entries_ok(T, doable, inc) & T.static_ok
+        alive_cur, has = self.alive[i], self.has_probs[:, i]
+        # update_subtasks :176-203
+        stale = (cur < S) & (((inc >> cur.clamp(max=S - 1)) & 1) == 0)
+        reset = stale | ~has | (alive_new.sum(1) != alive_cur.sum(1))  # should_reset_priors bd:54-79
+        do_prior = reset | (cur >= S)
+        if T.fallback.any():  # dc: an empty distribution becomes {None: me} (bd:1019-1024)
+            alive_new = alive_new | (T.fallback[None, :] & ~alive_new.any(1, keepdim=True))
+        prior = self._priors(T, alive_new, ci)
+        if self.prev is not None and not bool(do_prior.all()):
+            alive_upd = alive_cur & self._entries_ok(T, self.prev["doable"], None)
+            if T.fallback.any():
+                alive_upd = alive_upd | (T.fallback[None, :] & ~alive_upd.any(1, keepdim=True))
+            if T.model == "fb":
+                upd = self.probs[i] * alive_upd
+            else:
+                upd = self._bayes_update(T, self.probs[i], alive_upd)
+            probs = torch.where(do_prior[:, None], prior, upd)
+            alive = torch.where(do_prior[:, None], alive_new, alive_upd)
+        else:
+            probs, alive = prior, alive_new
+        self.probs[i], self.alive[i] = probs, alive
+        self.has_probs[:, i] = True
+        # select_subtask bd:1009-1017 (get_max: uniform among exact ties, dutils:37-42)
+        masked = torch.where(alive, probs, -1.0)
+        best_p = masked.max(1, keepdim=True).values
+        tol = 1e-12 if self.deterministic else 0.0
+        best = self._pick(alive & (masked >= best_p - tol), T.rank)
+        nothing = ~alive.any(1)
+        new_sub = torch.where(nothing, S, T.sel_sub[best])
+        new_joint = T.sel_joint[best] & ~nothing
+        # plan :218-281
+        subc = new_sub.clamp(max=S - 1)
+        pid = torch.where(new_joint, T.plan_joint[subc], T.plan_single[subc])
+        q = self.cache.q[ci, pid]  # [N][25]
+        q = torch.where(new_joint[:, None] | (torch.arange(25, device=dev)[None, :] < 5), q, float("nan"))
+        valid = ~torch.isnan(q)
+        qv = torch.where(valid, q.clamp(max=1e30), float("inf"))
+        a = self._pick(valid & (qv == qv.min(1, keepdim=True).values))  # argmin, random ties (e2e:27-30)
+        own = torch.where(new_joint, (a // 5) if i == 0 else (a % 5), a)
+        own = torch.where(valid.any(1), own, 4)
+        # doing nothing: stay with none_action_prob, else a uniformly random offered move (:235-243)
+        off = offered[:, i]
+        if self.deterministic:
+            a_none = torch.full((N,), 4, dtype=torch.int64, device=dev)
+        else:
+            u = torch.rand(N, device=dev, generator=self.gen)
+            a_none = torch.where((u < self.none_action_prob) | ~off.any(1), 4, self._pick(off))
+        self.cur_sub[:, i], self.cur_joint[:, i] = new_sub, new_joint
+        return torch.where(new_sub >= S, a_none, own).to(torch.uint8)
+
+    # -- the loop -----------------------------------------------------------------------------
+    def step(self):
+        """One pass of main_loop's body for every env; returns the reward/done bytes."""
+        kb = self.kb
+        state = kb.state
+        ci = self.cache.lookup(state)
+        doable = planning.lower_bound(kb, self.lpairs) < self.perimeter  # bd:156
+        offered = self.single_actions(state)
+        actions = torch.stack([self._select_action(i, ci, doable, offered) for i in range(self.NA)], dim=1)
+        self.prev = dict(state=state.clone(), ci=ci, doable=doable, offered=offered)
+        self.last_actions = actions.contiguous()
+        kb.step(self.last_actions, executed_out=self.executed)
+        for i in range(self.NA):  # refresh_subtasks :151-171
+            sub = self.cur_sub[:, i]
+            subc = sub.clamp(max=self.S - 1)
+            complete = (sub < self.S) & (self.goal_count(kb.state, subc) > self.goal_count(self.prev["state"], subc))
+            self.incomplete[:, i] &= ~(complete.long() << subc)
+        self.t += 1
+        return kb.reward_done
+
+    def run(self, max_steps=None):
+        """Steps until every env is done (env.done(), main.py:99); returns the number of steps."""
+        limit = max_steps if max_steps is not None else self.kb.max_num_timesteps + 1
+        steps = 0
+        while steps < limit:
+            rd = self.step()
+            steps += 1
+            if bool((rd & 1).all()):
+                break
+        return steps

@@ -60,7 +60,7 @@ extern "C" {
 #define GC_MAX_SUBTASKS 32
 #define GC_MAX_PAIRS 128
 #define GC_MAX_JOINT_ACTIONS 25
-#define GC_MAX_HYPOTHESES 96
+#define GC_MAX_HYPOTHESES 128
 #define GC_MAX_LEVELS 16
 
 /* error codes */

@@ -1,0 +1,78 @@
+"""The device-resident Bayesian-Delegation loop (batched_agents.BatchedDelegation) against the host
+facade loop (main.main_loop over RealAgent / BayesianDelegator / E2E_BRTDP): with every random
+tie-break made deterministic in BOTH, each env of a batch must pick the facade's actions step by
+step; with random tie-breaks the batch must finish like the reference's episodes do."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+import gym_cooking_b200 as gcb
+from gym_cooking_b200 import batched_agents, delegation_planner, main as gmain, navigation_planner
+
+pytestmark = pytest.mark.gpu
+
+
+def _arglist(level, models, max_t=100):
+    models = list(models) + [None] * (4 - len(models))
+    return argparse.Namespace(level=level, num_agents=sum(m is not None for m in models), max_num_timesteps=max_t,
+                              max_num_subtasks=14, seed=1, beta=1.3, alpha=0.01, tau=2, cap=75, main_cap=100,
+                              play=False, record=False, with_image_obs=False, model1=models[0], model2=models[1],
+                              model3=models[2], model4=models[3])
+
+
+@pytest.fixture
+def deterministic_facade(monkeypatch):
+    """first-minimum argmin, canonical-key arg-max, 'do nothing' = stay"""
+    subtasks = {}
+
+    def get_max(self):
+        if not self.probs:
+            return None
+        best = max(self.probs.values())
+        cands = [a for a, p in self.probs.items() if p >= best - 1e-12]
+        return min(cands, key=lambda a: batched_agents.alloc_key(a, subtasks["list"]))
+
+    monkeypatch.setattr(delegation_planner.SubtaskAllocDistribution, "get_max", get_max)
+    monkeypatch.setattr(navigation_planner, "argmin", lambda v: int(np.argmin(np.asarray(v, dtype=np.float64))))
+    monkeypatch.setattr(np.random, "choice", lambda n, p=None: n - 1)
+    return subtasks
+
+
+@pytest.mark.parametrize("level,models", [("open-divider_tomato", ("bd", "bd")),
+                                          ("partial-divider_tomato", ("bd", "up")),
+                                          ("open-divider_tl", ("bd", "bd")),
+                                          ("partial-divider_tl", ("greedy", "bd")),
+                                          ("open-divider_tomato", ("dc", "fb"))])
+def test_batched_loop_equals_facade_loop(level, models, deterministic_facade):
+    loop = batched_agents.BatchedDelegation(level, 8, models, deterministic=True)
+    deterministic_facade["list"] = loop.subtasks
+    env, agents, history = gmain.main_loop(_arglist(level, models), max_steps=40)
+    for step, action_dict in enumerate(history):
+        loop.step()
+        want = [gcb.ACTION_INDEX[tuple(action_dict["agent-%d" % (i + 1)])] for i in range(len(models))]
+        got = loop.last_actions.cpu().numpy()
+        assert (got == np.array(want, dtype=np.uint8)[None, :]).all(), "step %d: facade %s, batched %s" % (
+            step, want, got[0].tolist())
+    words = np.array([int(w) & 0xFFFFFFFF for w in env.state[0].tolist()], dtype=np.uint32)
+    assert (loop.kb.state.cpu().numpy().view(np.uint32) == words[None, :]).all()
+    assert bool(loop.kb.done.all()) == bool(env.done())
+
+
+@pytest.mark.parametrize("level,models,limit", [("open-divider_tomato", ("bd", "bd"), 40),
+                                                ("partial-divider_tl", ("bd", "bd"), 100)])
+def test_random_tie_breaks_finish(level, models, limit):
+    n = 512
+    loop = batched_agents.BatchedDelegation(level, n, models, seed=3)
+    steps = loop.run()
+    stats = loop.kb.stats().cpu().numpy()
+    done = loop.kb.done
+    assert bool(done.all())
+    success = int(stats[1])
+    t = ((loop.kb.state[:, 0].to(torch.int64) >> 24) & 127).float()
+    print("%s %s: %d/%d delivered, mean %.1f steps (%d loop steps), %d planning states solved for %d lookups" % (
+        level, models, success, n, float(t.mean()), steps, loop.cache.solved_states, loop.cache.lookups))
+    assert success >= 0.9 * n
+    assert float(t[loop.kb.reward.bool()].mean()) <= limit
+    assert loop.cache.solved_states < loop.cache.lookups / 4  # the memo is doing its job
