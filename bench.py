@@ -250,11 +250,7 @@ def run_ours(args):
 
     secondary = secondary_metrics(gcb, torch, dev) if (rank == 0 and not args.no_secondary) else None
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        peak, peak_src = hbm_peak_gbs()
         launch_s = ms * 1e-3 / args.steps  # average gc_env_step launch, launch gaps included
         achieved = BYTES_PER_ENV_STEP * N_ENVS / launch_s / 1e9
         traffic = None
@@ -285,6 +281,14 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def hbm_peak_gbs():
+    """(GB/s, source): the driver-measured copy bandwidth, else the profiling recipe's fallback"""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def secondary_metrics(gcb, torch, dev):
@@ -318,8 +322,27 @@ def secondary_metrics(gcb, torch, dev):
     bytes_per = 8 * H + 4 * P * A + 3 * P + H * E
     out.append({"metric": "bd_posterior_updates_per_sec", "value": n / t, "unit": "updates/s", "dtype": "f32",
                 "config": "cfg-4 shape: H=8 hypotheses, P=8 likelihood rows, A=5 actions, 2^21 rows resident (520 MB)",
-                "bytes_per_update": bytes_per, "achieved_gbs": n * bytes_per / t / 1e9})
+                "bytes_per_update": bytes_per, "achieved_gbs": n * bytes_per / t / 1e9,
+                "roofline_frac": n * bytes_per / t / 1e9 / hbm_peak_gbs()[0]})
     del probs, hyp, w, qd, nv, ai
+    # cfg-3 as a whole: the device-resident Bayesian-Delegation loop (lower bounds + exact Q through the
+    # planning-state memo + posterior + action selection + env step), wall clock with a sync on both sides
+    from gym_cooking_b200 import batched_agents
+    n_loop, loop_steps = 1 << 14, 30
+    loop = batched_agents.BatchedDelegation("open-divider_salad", n_loop, ("bd", "bd"), seed=1, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(loop_steps):
+        loop.step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    st = loop.kb.stats().cpu().tolist()
+    out.append({"metric": "bd_loop_agent_steps_per_sec", "value": n_loop * 2 * loop_steps / dt, "unit": "agent-steps/s",
+                "config": "cfg-3: 2-agent open-divider_salad, bd/bd, 2^14 envs x %d steps from reset, cold planner memo"
+                          % loop_steps,
+                "posterior_updates_per_sec": loop.posterior_updates / dt, "seconds": dt,
+                "delivered_by_step_%d" % loop_steps: st[1], "planning_states_solved": loop.cache.solved_states})
+    del loop
     # path B: cfg-3 (3 agents, full-divider_salad), envs diversified by k = env % 41 random steps
     n = 1 << 12  # bounded sample: the joint solver runs up to 25 searches per (env, pair)
     kb = gcb.KitchenBatch("full-divider_salad", 3, n, HORIZON, device=dev)
