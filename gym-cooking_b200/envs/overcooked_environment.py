@@ -191,6 +191,12 @@ class OvercookedEnvironment:
         self.agent_actions = {}
         self._sync_view()
         self.obs_tm1 = copy.copy(self._view) if self.num_envs == 1 else None
+        self.game = None
+        if self._atlas is not None and self.num_envs == 1:  # env:240-248
+            from ..misc.game.gameimage import GameImage
+            self.game = GameImage(self.filename, self.get_image_obs, record=bool(getattr(a, "record", False)))
+            if self.game.record:
+                self.game.save_image_obs(self.t)
         return self._obs()
 
     def close(self):
@@ -233,6 +239,8 @@ class OvercookedEnvironment:
         for i, nm in enumerate(names):
             self.agent_actions[nm] = engine.ACTIONS[executed[i]]
             self._view.sim_agents[i].action = engine.ACTIONS[executed[i]]
+        if self.game is not None and self.game.record:  # env:285-286
+            self.game.save_image_obs(self.t)
         done = bool(int(rd[0]) & 1)
         self.successful = bool(int(rd[0]) & 2)
         self._set_termination(done)

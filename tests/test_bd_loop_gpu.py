@@ -64,3 +64,22 @@ def test_delegator_and_planner_surface():
     assert abs(sum(d.probs.probs.values()) - 1) < 1e-12 and d.probs.probs != before
     st, names = d.select_subtask("agent-1")
     assert "agent-1" in names
+
+
+def test_bag_and_record(tmp_path, monkeypatch):
+    """main_loop writes the reference's Bag pickle and, with --record, one PNG per step (+ t=000)"""
+    import pickle
+    from gym_cooking_b200.misc.game.gameimage import decode_png
+    monkeypatch.chdir(tmp_path)
+    gmain.fix_seed(1)
+    args = _arglist("open-divider_tomato", 2, ("bd", "bd"))
+    args.record = True
+    env, agents, history = gmain.main_loop(args, bag_directory=str(tmp_path / "pickles"))
+    data = pickle.load(open(env.bag_path, "rb"))
+    assert data["was_successful"] and data["num_completed_subtasks_end"] == 3 and data["num_total_subtasks"] == 3
+    assert len(data["actions"]["agent-1"]) == len(history) == env.t
+    assert data["actions"]["agent-2"][0] == history[0]["agent-2"]
+    frames = sorted((tmp_path / "misc" / "game" / "record" / env.filename).iterdir())
+    assert [f.name for f in frames] == ["t=%03d.png" % t for t in range(env.t + 1)]
+    first, last = decode_png(frames[0].read_bytes()), decode_png(frames[-1].read_bytes())
+    assert first.shape == (560, 560, 3) and (first != last).any()
