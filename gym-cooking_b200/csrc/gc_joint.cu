@@ -15,6 +15,17 @@
 // arena keyed by an injective 64-bit packing of the planning state.  Q(start, a) = cost(a) +
 // V*(T(start, a)); V*(start) = min_a Q.  Searches are budgeted (kSlots states); a search that
 // exceeds its budget is reported (status 3), never guessed.
+//
+// Two kernels share those rules.  joint_tree_kernel (first) runs ONE search per (env, pair): a
+// forward Dial pass from the start state that records every generated edge in per-state
+// predecessor lists, out to cost V* + kSlack (or until the reachable space is exhausted), then a
+// backward Dial pass from the goal states over the recorded edges, which yields the exact
+// cost-to-go of every state whose optimal plan stays inside the explored ball - in particular of
+// the start's successors, i.e. Q(start, a) for (almost) all 25 joint actions at once.  An action
+// whose Q is not proven by that pass (Q above the explored radius, e.g. after an irreversible
+// move) is handed to joint_q_kernel, the per-action search described above.
+#include <stdlib.h>
+
 #include "gc_device.cuh"
 #include "gc_host.h"
 #include "gc_nav.cuh"
@@ -32,6 +43,27 @@ constexpr uint32_t kInfCost = 0xFFFFFFFFu;
 
 enum { ST_OK = 0, ST_UNREACHABLE = 2, ST_BUDGET = 3, ST_UNSUPPORTED = 4 };
 
+// tree search (one per problem)
+constexpr uint32_t kSlots2 = 1u << 17;
+constexpr uint32_t kMaxStates2 = 96 * 1024;
+constexpr int kRing = 64;                    // A* keys may jump by an edge (<= 12) plus a heuristic change (< 52)
+constexpr uint32_t kRingCap = 16 * 1024;     // entries per key bucket
+constexpr uint32_t kPool = 1u << 20;         // predecessor-list nodes
+constexpr uint32_t kGoalCap = 4096;
+constexpr uint32_t kNil = 0xFFFFFFFFu;
+constexpr int kSlack = 24;                   // explore to V* + 2.4: covers "step away and come back"
+
+struct Arena2 {
+  unsigned long long keys[kSlots2];
+  uint4 states[kSlots2];
+  uint32_t gcost[kSlots2];  // forward: 2*cost (+1 once settled)
+  uint32_t val[kSlots2];    // backward: cost-to-go in tenths
+  uint32_t head[kSlots2];   // predecessor list
+  uint32_t bucket[kRing][kRingCap];  // forward: slot | g << 17 by key f; backward: slots by cost-to-go
+  uint2 pool[kPool];        // .x = predecessor slot | (edge cost - 10) << 30, .y = next node
+  uint32_t goals[kGoalCap];
+};
+
 // per-CTA scratch layout
 struct Arena {
   unsigned long long keys[kSlots];
@@ -43,7 +75,7 @@ struct Arena {
 struct World {
   unsigned long long floorp, nonfloor, cut, deliv;
   unsigned long long blocked;  // level-1 only: squares of the other agents (cannot be faced or entered)
-  uint32_t goal_mask, goal_kind;
+  uint32_t goal_mask, goal_kind, a_mask, b_mask;
 };
 
 // planning state: two agents, object slots with holder 1 / 2 (the two subtask agents)
@@ -223,6 +255,49 @@ __device__ bool maybe_reachable(const World& w, const PState& p, uint32_t a_mask
   return ok;
 }
 
+// Planning world + start state of problem (env, pair pi).  Returns 0 = not a joint pair / bad
+// subtask (nothing to do), 1 = outside the supported envelope, 2 = search, 3 = offered actions only
+// (a goal object exists already, or square adjacency rules the goal out).
+__device__ int setup_problem(const GcNavLevels& levels, const GcPairs& pairs, const uint8_t* level_id,
+                             const uint4* state, int64_t env, int pi, int n_agents, World& w, PState& p,
+                             gc_subtask& st) {
+  const GcNavLevel& L = levels.lv[level_id ? level_id[env] : 0];
+  const int sub = pairs.p[pi][0], ai = pairs.p[pi][1], aj = pairs.p[pi][2];
+  const bool level1 = pairs.p[pi][3] != 0;
+  if (aj == 0xFF || (uint32_t)sub >= L.n_subtasks) return 0;
+  const uint4 s = state[env];
+  st = L.st[sub];
+  unsigned long long frozen = 0;
+  for (int i = 0; i < n_agents; i++)
+    if (i != ai && i != aj) frozen |= 1ull << ((s.x >> (6 * i)) & 63u);
+  w.floorp = L.floor_mask & ~frozen;
+  w.blocked = level1 ? frozen : 0ull;
+  w.nonfloor = ~w.floorp;
+  w.cut = L.cut_mask;
+  w.deliv = L.deliv_mask;
+  w.goal_mask = st.goal;
+  w.goal_kind = st.kind;
+  w.a_mask = st.a;
+  w.b_mask = st.b;
+  p.cell[0] = (s.x >> (6 * ai)) & 63u;
+  p.cell[1] = (s.x >> (6 * aj)) & 63u;
+  bool supported = gcnav::slot_of(s, 4) == GC_SLOT_DEAD && gcnav::slot_of(s, 5) == GC_SLOT_DEAD;
+  for (int k = 0; k < 4; k++) {
+    uint32_t sl = gcnav::slot_of(s, k);
+    const uint32_t holder = sl >> 13;
+    if (holder >= 1u && holder <= 4u)
+      sl = (int)holder == ai + 1 ? ((sl & 0x7fu) | (1u << 13))
+           : (int)holder == aj + 1 ? ((sl & 0x7fu) | (2u << 13))
+           : level1 ? ((sl & 0x7fu) | (3u << 13)) : GC_SLOT_DEAD;  // level 1: kept but out of reach
+    p.slot[k] = sl;
+  }
+  supported = supported && __popcll(w.nonfloor) <= 60;  // ranks 60..63 are reserved by compact_key
+  if (!supported) return 1;
+  // a goal object is already there: the count can never rise (one food of each kind); or the
+  // squares the two agents can touch rule the goal out
+  return (is_goal(w, p) || !maybe_reachable(w, p, st.a, st.b)) ? 3 : 2;
+}
+
 // insert / relax `p` with cost c (tenths); pushes it into its bucket when it improved
 __device__ __forceinline__ void relax(const World& w, Arena* A, uint32_t* bcount, uint32_t* n_states, int* over,
                                       const PState& p, uint32_t c) {
@@ -248,10 +323,349 @@ __device__ __forceinline__ void relax(const World& w, Arena* A, uint32_t* bcount
   atomicExch(over, 1);
 }
 
+// ---------------------------------------------------------------------------------------
+// tree search: one forward A* pass + one backward Dial pass per (env, pair)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash_key2(unsigned long long k) {
+  k ^= k >> 31;
+  k *= 0x9E3779B97F4A7C15ull;
+  k ^= k >> 29;
+  return (uint32_t)k & (kSlots2 - 1u);
+}
+
+__device__ __forceinline__ uint32_t find2(const World& w, const Arena2* A, const PState& p) {
+  const unsigned long long k = compact_key(w, p);
+  uint32_t h = hash_key2(k);
+  for (uint32_t probe = 0; probe < kSlots2; probe++, h = (h + 1u) & (kSlots2 - 1u)) {
+    const unsigned long long cur = A->keys[h];
+    if (cur == k) return h;
+    if (cur == kEmpty) return kNil;
+  }
+  return kNil;
+}
+
+// Distance tables of one planning world (shared memory, bytes, gcnav::kFar = no path):
+//   walk[x][y]  steps an agent needs between floor squares (the partner ignored),
+//   carry[x][y] steps an OBJECT needs between any two squares: it moves one square per step, either
+//               carried over floor or put on / picked from a counter next to the carrier, so edges
+//               join 4-neighbours of which at least one is floor (hand-overs across a divider included),
+//   reach[c]    carry distance from square c to where the subtask's last action happens: a floor
+//               square next to a cutboard (Chop), or a delivery square itself (Deliver).
+struct Tables {
+  uint8_t walk[64 * 64];
+  uint8_t carry[64 * 64];
+  uint8_t reach[64];
+};
+
+__device__ void fill_tables(const World& w, Tables* T) {
+  gcnav::fill_floor_distances(w.floorp, T->walk);
+  for (int s = threadIdx.x; s < 64; s += blockDim.x) {
+    uint8_t* row = T->carry + s * 64;
+    for (int c = 0; c < 64; c += 4) *reinterpret_cast<uint32_t*>(row + c) = 0xFFFFFFFFu;
+    unsigned long long visited = 1ull << s, frontier = visited;
+    row[s] = 0;
+    for (uint32_t d = 1; frontier; d++) {
+      frontier = (gcnav::neighbours(frontier & w.floorp) | (gcnav::neighbours(frontier & ~w.floorp) & w.floorp)) & ~visited;
+      visited |= frontier;
+      for (unsigned long long f = frontier; f; f &= f - 1) row[__ffsll((long long)f) - 1] = (uint8_t)d;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 64; c += blockDim.x) {
+    unsigned long long tgt = w.goal_kind == GC_ST_DELIVER ? w.deliv
+                             : w.goal_kind == GC_ST_CHOP  ? (gcnav::neighbours(w.cut) & w.floorp) : 0ull;
+    uint32_t best = gcnav::kFar;
+    for (; tgt; tgt &= tgt - 1) best = min(best, (uint32_t)T->carry[c * 64 + (__ffsll((long long)tgt) - 1)]);
+    T->reach[c] = (uint8_t)best;
+  }
+  __syncthreads();
+}
+
+// Admissible estimate (tenths) of the cost still to pay from planning state p; kInfCost = dead end.
+// Every step costs at least 11 (one mover), so it is 11 x a lower bound T on the number of steps:
+//   nobody holds the object(s) yet -> the nearest agent first walks next to one of them (approach),
+//   Chop:    the object then travels `reach` squares and is chopped in one more step,
+//   Deliver: it travels `reach` squares (the last one is the put-down),
+//   Merge:   the two parts close their carry distance D by at most 2 per step until they are
+//            neighbours, and merge in one more step.
+__device__ uint32_t heuristic(const World& w, const Tables* T, const PState& p) {
+  uint32_t best = kInfCost;
+  auto pos_of = [&](uint32_t sl) { return (sl >> 13) == 0u ? ((sl >> 7) & 63u) : p.cell[(sl >> 13) - 1u]; };
+  auto approach = [&](uint32_t sl) -> uint32_t {  // steps until some agent stands next to a lying object
+    if ((sl >> 13) != 0u) return 0u;
+    const uint32_t q = (sl >> 7) & 63u;
+    uint32_t ap = gcnav::kFar;
+    unsigned long long adj = gcnav::neighbours(1ull << q) & w.floorp;
+    for (; adj; adj &= adj - 1) {
+      const uint32_t f = (uint32_t)__ffsll((long long)adj) - 1u;
+      ap = min(ap, min((uint32_t)T->walk[p.cell[0] * 64 + f], (uint32_t)T->walk[p.cell[1] * 64 + f]));
+    }
+    return ap;
+  };
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint32_t sa = p.slot[i];
+    if ((sa >> 13) >= 3u || (sa & 0x7fu) != w.a_mask) continue;
+    if (w.goal_kind != GC_ST_MERGE) {
+      const uint32_t ap = approach(sa), r = T->reach[pos_of(sa)];
+      if (ap == gcnav::kFar || r == gcnav::kFar) continue;
+      best = min(best, ap + r + (w.goal_kind == GC_ST_CHOP ? 1u : 0u));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t sb = p.slot[j];
+        if (j == i || (sb >> 13) >= 3u || (sb & 0x7fu) != w.b_mask) continue;
+        const uint32_t D = T->carry[pos_of(sa) * 64 + pos_of(sb)];
+        if (D == gcnav::kFar) continue;
+        uint32_t ap = 0u;
+        if ((sa >> 13) == 0u && (sb >> 13) == 0u) {
+          ap = min(approach(sa), approach(sb));
+          if (ap == gcnav::kFar) continue;
+        }
+        best = min(best, ap + (D > 1u ? D / 2u : 0u) + 1u);  // ceil((D - 1) / 2) + 1
+      }
+    }
+  }
+  return best == kInfCost ? kInfCost : 11u * best;
+}
+
+// insert / relax successor `p` of state slot `pred` (kNil for the start) reached with total cost g
+// over an edge of cost 10 + code; records the edge in p's predecessor list.  fmin = the parent's
+// f, so that keys never decrease along a path (pathmax).  Bucket entries carry (slot, g).
+__device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* A, uint32_t* bcount, uint32_t* n_states,
+                                       uint32_t* n_pool, int* over, const PState& p, uint32_t g, uint32_t fmin,
+                                       uint32_t pred, uint32_t code) {
+  const unsigned long long k = compact_key(w, p);
+  uint32_t h = hash_key2(k);
+  for (uint32_t probe = 0; probe < kSlots2; probe++, h = (h + 1u) & (kSlots2 - 1u)) {
+    const unsigned long long old = atomicCAS(&A->keys[h], kEmpty, k);
+    if (old == kEmpty) {
+      A->states[h] = pack_state(p);
+      if (atomicAdd(n_states, 1u) >= kMaxStates2) atomicExch(over, 1);
+    } else if (old != k) {
+      continue;
+    }
+    if (pred != kNil) {
+      const uint32_t node = atomicAdd(n_pool, 1u);
+      if (node < kPool) {
+        A->pool[node].x = pred | (code << 30);
+        A->pool[node].y = atomicExch(&A->head[h], node);
+      } else {
+        atomicExch(over, 1);
+      }
+    }
+    const uint32_t prev = atomicMin(&A->gcost[h], 2u * g);
+    if (prev > 2u * g) {
+      const uint32_t est = is_goal(w, p) ? 0u : heuristic(w, T, p);
+      if (est == kInfCost) return;  // dead end: recorded (it has a slot and its edge) but never expanded
+      const uint32_t f = max(fmin, g + est);
+      if (pred == kNil) *n_pool = f;  // the start: its key is where the sweep begins (n_pool is reset by the caller)
+      else if (f >= fmin + (uint32_t)kRing || g >= (1u << 15)) {
+        atomicExch(over, 1);
+        return;
+      }
+      const uint32_t b = f & (kRing - 1);
+      const uint32_t pos = atomicAdd(&bcount[b], 1u);
+      if (pos < kRingCap) A->bucket[b][pos] = h | (g << 17);
+      else atomicExch(over, 1);
+    }
+    return;
+  }
+  atomicExch(over, 1);
+}
+
+__global__ void __launch_bounds__(kThreads)
+joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant__ GcPairs pairs,
+                  const uint8_t* __restrict__ level_id, const uint4* __restrict__ state, Arena2* __restrict__ arenas,
+                  float* __restrict__ q_out, int* __restrict__ flags, uint32_t* __restrict__ todo, int64_t n,
+                  int n_agents) {
+  __shared__ uint32_t bcount[kRing];
+  __shared__ uint32_t n_states, n_pool, n_goals, s_todo, s_v1, s_v2, s_f0, s_cnt;
+  __shared__ int over, result, s_kind;
+  __shared__ PState start;
+  __shared__ World w;
+  __shared__ __align__(16) Tables T;
+  Arena2* A = arenas + blockIdx.x;
+  const int64_t n_prob = n * pairs.n;
+  for (int64_t prob = blockIdx.x; prob < n_prob; prob += gridDim.x) {
+    const int64_t env = prob / pairs.n;
+    const int pi = (int)(prob - env * pairs.n);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      PState p;
+      gc_subtask st;
+      s_kind = setup_problem(levels, pairs, level_id, state, env, pi, n_agents, w, p, st);
+      start = p;
+      if (s_kind >= 2) {
+        s_v1 = single_actions(w, p, 0);
+        s_v2 = single_actions(w, p, 1);
+      }
+      n_states = n_pool = n_goals = s_todo = 0;
+      over = 0;
+      result = 0x7fffffff;
+    }
+    if (threadIdx.x < kRing) bcount[threadIdx.x] = 0;
+    __syncthreads();
+    if (s_kind == 0) continue;  // a single-agent pair: not ours
+    if (s_kind == 1) {
+      if (threadIdx.x == 0) {
+        atomicOr(&flags[prob], 4);
+        todo[prob] = 0;
+      }
+      continue;
+    }
+    const uint32_t a1 = threadIdx.x / 5u, a2 = threadIdx.x % 5u;
+    const bool offered = threadIdx.x < 25 && ((s_v1 >> a1) & 1u) && ((s_v2 >> a2) & 1u) && joint_ok(w, start, a1, a2);
+    if (offered) q_out[prob * 25 + threadIdx.x] = INFINITY;  // e2e_brtdp.get_actions :151-206
+    if (s_kind == 3) {  // nothing to search: a goal object exists, or adjacency rules the goal out
+      if (threadIdx.x == 0) todo[prob] = 0;
+      continue;
+    }
+    fill_tables(w, &T);
+    for (uint32_t k = threadIdx.x; k < kSlots2; k += kThreads) {
+      A->keys[k] = kEmpty;
+      A->gcost[k] = kInfCost;
+      A->val[k] = kInfCost;
+      A->head[k] = kNil;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      relax2(w, &T, A, bcount, &n_states, &n_pool, &over, start, 0u, 0u, kNil, 0u);
+      s_f0 = n_pool;
+      n_pool = 0;
+    }
+    __syncthreads();
+    // ---- forward A*: every state with key f <= V* + kSlack is expanded, every generated edge recorded ----
+    int empty_run = 0, limit = kMaxCost, cur = (int)s_f0;
+    bool complete = false;
+    for (; cur <= limit; cur++) {
+      const uint32_t b = (uint32_t)cur & (kRing - 1);
+      if (bcount[b] == 0) {  // uniform: bcount only changes between barriers
+        if (++empty_run >= kRing) {
+          complete = true;  // nothing left to expand: the whole space that can still reach the goal was covered
+          break;
+        }
+        continue;
+      }
+      empty_run = 0;
+      // children on the same plateau (pathmax) land in this very bucket: sweep it until it stops growing
+      for (uint32_t done = 0;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_cnt = min(bcount[b], kRingCap);
+        __syncthreads();
+        const uint32_t cnt = s_cnt;
+        if (cnt == done) break;
+        for (uint32_t e = done + threadIdx.x; e < cnt; e += kThreads) {
+        const uint32_t entry = A->bucket[b][e], h = entry & (kSlots2 - 1u), g = entry >> 17;
+        if (atomicCAS(&A->gcost[h], 2u * g, 2u * g + 1u) != 2u * g) continue;  // stale, or expanded already
+        const PState p = unpack_state(A->states[h]);
+        if (is_goal(w, p)) {  // absorbing
+          atomicMin(&result, (int)g);
+          A->val[h] = 0u;
+          const uint32_t gi = atomicAdd(&n_goals, 1u);
+          if (gi < kGoalCap) A->goals[gi] = h;
+          else atomicExch(&over, 1);
+          continue;
+        }
+        const uint32_t v1 = single_actions(w, p, 0), v2 = single_actions(w, p, 1);
+        for (uint32_t b1 = 0; b1 < 5; b1++) {
+          if (!((v1 >> b1) & 1u)) continue;
+          for (uint32_t b2 = 0; b2 < 5; b2++) {
+            if (!((v2 >> b2) & 1u) || (b1 == 4u && b2 == 4u) || !joint_ok(w, p, b1, b2)) continue;
+            PState nx = p;
+            interact(w, nx, 0, b1);
+            interact(w, nx, 1, b2);
+            const uint32_t code = (b1 != 4u) + (b2 != 4u);
+            relax2(w, &T, A, bcount, &n_states, &n_pool, &over, nx, g + 10u + code, (uint32_t)cur, h, code);
+          }
+        }
+        }
+        done = cnt;
+        if (cnt == kRingCap) break;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (bcount[b] > kRingCap) over = 1;
+        bcount[b] = 0;
+      }
+      __syncthreads();
+      if (over) break;
+      if (result != 0x7fffffff) limit = min(limit, result + kSlack);
+    }
+    // every state with key <= radius has been expanded
+    const int radius = complete ? 0x3fffffff : (over ? cur - 1 : (cur > limit ? limit : cur - 1));
+    __syncthreads();
+    if (threadIdx.x < kRing) bcount[threadIdx.x] = 0;
+    __syncthreads();
+    if (result == 0x7fffffff) {  // no goal inside the explored region
+      if (threadIdx.x == 0) {
+        if (!complete) atomicOr(&flags[prob], 1);  // budget: unknown.  complete: every offered Q is +inf, exactly
+        todo[prob] = 0;
+      }
+      continue;
+    }
+    // ---- backward: exact cost-to-go inside the region, from the goal states over the recorded edges ----
+    for (uint32_t i = threadIdx.x; i < min(n_goals, kGoalCap); i += kThreads) {
+      const uint32_t pos = atomicAdd(&bcount[0], 1u);
+      if (pos < kRingCap) A->bucket[0][pos] = A->goals[i];
+      else atomicExch(&over, 2);
+    }
+    __syncthreads();
+    const int bmax = complete ? kMaxCost : radius;
+    empty_run = 0;
+    for (cur = 0; cur <= bmax; cur++) {
+      const uint32_t b = (uint32_t)cur & (kBuckets - 1);
+      const uint32_t cnt = min(bcount[b], kRingCap);
+      if (cnt == 0) {
+        if (++empty_run >= kBuckets) break;
+        continue;
+      }
+      empty_run = 0;
+      for (uint32_t e = threadIdx.x; e < cnt; e += kThreads) {
+        const uint32_t h = A->bucket[b][e];
+        if (A->val[h] != (uint32_t)cur) continue;  // improved since it was pushed
+        for (uint32_t node = A->head[h]; node != kNil; node = A->pool[node].y) {
+          const uint32_t x = A->pool[node].x & 0x3FFFFFFFu;
+          const uint32_t nv = (uint32_t)cur + 10u + (A->pool[node].x >> 30);
+          if (atomicMin(&A->val[x], nv) > nv) {
+            const uint32_t pos = atomicAdd(&bcount[nv & (kBuckets - 1)], 1u);
+            if (pos < kRingCap) A->bucket[nv & (kBuckets - 1)][pos] = x;
+            else atomicExch(&over, 2);
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) bcount[b] = 0;
+      __syncthreads();
+    }
+    // ---- Q(start, a) = cost(a) + cost-to-go of T(start, a), proven when it fits inside the region ----
+    if (offered && threadIdx.x != 24) {
+      PState nx = start;
+      interact(w, nx, 0, a1);
+      interact(w, nx, 1, a2);
+      const uint32_t code = (a1 != 4u) + (a2 != 4u);
+      const float step_cost = 1.0f + 0.1f * (float)code;
+      if (is_goal(w, nx)) {
+        q_out[prob * 25 + threadIdx.x] = step_cost;
+      } else {
+        const uint32_t h = find2(w, A, nx);
+        const uint32_t v = h == kNil ? kInfCost : A->val[h];
+        const bool proven = over != 2 && v != kInfCost && (complete || (int)(v + 10u + code) <= radius);
+        const bool dead = heuristic(w, &T, nx) == kInfCost;  // no way back: +inf is exact
+        if (proven) q_out[prob * 25 + threadIdx.x] = step_cost + 0.1f * (float)v;
+        else if (!dead && !(complete && over != 2)) atomicOr(&s_todo, 1u << threadIdx.x);  // complete: +inf is exact
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) todo[prob] = s_todo;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 joint_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant__ GcPairs pairs,
                const uint8_t* __restrict__ level_id, const uint4* __restrict__ state, Arena* __restrict__ arenas,
-               float* __restrict__ q_out, int* __restrict__ flags, int64_t n, int n_agents) {
+               float* __restrict__ q_out, int* __restrict__ flags, const uint32_t* __restrict__ todo, int64_t n,
+               int n_agents) {
   __shared__ uint32_t bcount[kBuckets];
   __shared__ uint32_t n_states;
   __shared__ int over, result;
@@ -268,54 +682,26 @@ joint_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant
     const uint32_t a1 = (uint32_t)(act / 5), a2 = (uint32_t)(act % 5);
     __syncthreads();
     if (threadIdx.x == 0) {
-      const GcNavLevel& L = levels.lv[level_id ? level_id[env] : 0];
-      const int sub = pairs.p[pi][0], ai = pairs.p[pi][1], aj = pairs.p[pi][2];
-      const bool level1 = pairs.p[pi][3] != 0;
-      const uint4 s = state[env];
       root_state = 1;
-      if (aj != 0xFF && (uint32_t)sub < L.n_subtasks) {
-        const gc_subtask st = L.st[sub];
-        unsigned long long frozen = 0;
-        for (int i = 0; i < n_agents; i++)
-          if (i != ai && i != aj) frozen |= 1ull << ((s.x >> (6 * i)) & 63u);
-        w.floorp = L.floor_mask & ~frozen;
-        w.blocked = level1 ? frozen : 0ull;
-        w.nonfloor = ~w.floorp;
-        w.cut = L.cut_mask;
-        w.deliv = L.deliv_mask;
-        w.goal_mask = st.goal;
-        w.goal_kind = st.kind;
-        PState p;
-        p.cell[0] = (s.x >> (6 * ai)) & 63u;
-        p.cell[1] = (s.x >> (6 * aj)) & 63u;
-        bool supported = gcnav::slot_of(s, 4) == GC_SLOT_DEAD && gcnav::slot_of(s, 5) == GC_SLOT_DEAD;
-        bool goal_exists = false;
-        for (int k = 0; k < 4; k++) {
-          uint32_t sl = gcnav::slot_of(s, k);
-          const uint32_t holder = sl >> 13;
-          if (holder >= 1u && holder <= 4u)
-            sl = (int)holder == ai + 1 ? ((sl & 0x7fu) | (1u << 13))
-                 : (int)holder == aj + 1 ? ((sl & 0x7fu) | (2u << 13))
-                 : level1 ? ((sl & 0x7fu) | (3u << 13)) : GC_SLOT_DEAD;  // level 1: kept but out of reach
-          p.slot[k] = sl;
-        }
-        // a goal object is already there: the count can never rise (one food of each kind); or the
-        // squares the two agents can touch rule the goal out
-        goal_exists = is_goal(w, p) || !maybe_reachable(w, p, st.a, st.b);
-        supported = supported && __popcll(w.nonfloor) <= 60;  // ranks 60..63 are reserved by compact_key
-        if (!supported) {
-          atomicOr(&flags[prob], 4);
-        } else {
-          const uint32_t v1 = single_actions(w, p, 0), v2 = single_actions(w, p, 1);
-          if (((v1 >> a1) & 1u) && ((v2 >> a2) & 1u) && joint_ok(w, p, a1, a2)) {
-            q_out[prob * 25 + act] = INFINITY;  // offered (e2e_brtdp.get_actions :151-206)
-            // (stay, stay) leaves the state unchanged: Q = 1 + V*(start), filled in by the finalize kernel
-            if (!goal_exists && act != 24) {
-              interact(w, p, 0, a1);
-              interact(w, p, 1, a2);
-              root = p;
-              root_state = is_goal(w, p) ? 2 : 0;
-            }
+      PState p;
+      gc_subtask st;
+      const bool wanted = !todo || ((todo[prob] >> act) & 1u);
+      const int kind = wanted ? setup_problem(levels, pairs, level_id, state, env, pi, n_agents, w, p, st) : 0;
+      if (kind == 1) {
+        atomicOr(&flags[prob], 4);
+      } else if (kind >= 2 && wanted) {
+        const bool goal_exists = kind == 3;
+        const uint32_t v1 = single_actions(w, p, 0), v2 = single_actions(w, p, 1);
+        if (((v1 >> a1) & 1u) && ((v2 >> a2) & 1u) && joint_ok(w, p, a1, a2)) {
+          q_out[prob * 25 + act] = INFINITY;  // offered (e2e_brtdp.get_actions :151-206)
+          // (stay, stay) leaves the state unchanged: Q = 1 + V*(start), filled in by the finalize kernel
+          if (!goal_exists && act != 24) {
+            interact(w, p, 0, a1);
+            interact(w, p, 1, a2);
+            root = p;
+            root_state = is_goal(w, p) ? 2 : 0;
+            // an irreversible move can put the goal out of reach: same adjacency test as at the start
+            if (root_state == 0 && !maybe_reachable(w, p, st.a, st.b)) root_state = 1;
           }
         }
       }
@@ -403,10 +789,11 @@ __global__ void joint_finalize_kernel(const __grid_constant__ GcPairs pairs, flo
 }
 
 __global__ void joint_init_kernel(const __grid_constant__ GcPairs pairs, float* __restrict__ q_out,
-                                  int* __restrict__ flags, int64_t n) {
+                                  int* __restrict__ flags, uint32_t* __restrict__ todo, int64_t n) {
   const int64_t prob = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (prob >= n * pairs.n) return;
   flags[prob] = 0;
+  todo[prob] = 0;
   if (pairs.p[prob % pairs.n][2] == 0xFF) return;
   for (int a = 0; a < 25; a++) q_out[prob * 25 + a] = NAN;  // NaN = not offered; +inf = offered, goal out of reach
 }
@@ -415,15 +802,26 @@ __global__ void joint_init_kernel(const __grid_constant__ GcPairs pairs, float* 
 
 extern "C" {
 
-int64_t gc_joint_q_scratch_bytes(int64_t n, int n_pairs, int* n_ctas_out) {
+// scratch layout: [arenas: max(per-action arenas, tree arenas)] [flags: int per problem] [todo: u32 per problem]
+static void joint_ctas(int64_t n, int n_pairs, int* tree_ctas, int* act_ctas) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
-  int64_t ctas = (int64_t)sms * 4;
-  const int64_t searches = n * n_pairs * 25;
-  if (searches < ctas) ctas = searches > 0 ? searches : 1;
-  if (n_ctas_out) *n_ctas_out = (int)ctas;
-  return ctas * (int64_t)sizeof(Arena) + n * n_pairs * (int64_t)sizeof(int);
+  const int64_t cap = (int64_t)sms * 4, problems = n * n_pairs;
+  *tree_ctas = (int)(problems < cap ? (problems > 0 ? problems : 1) : cap);
+  *act_ctas = (int)(problems * 25 < cap ? (problems > 0 ? problems * 25 : 1) : cap);
+}
+
+static int64_t joint_arena_bytes(int tree_ctas, int act_ctas) {
+  const int64_t a = (int64_t)tree_ctas * (int64_t)sizeof(Arena2), b = (int64_t)act_ctas * (int64_t)sizeof(Arena);
+  return ((a > b ? a : b) + 255) & ~(int64_t)255;
+}
+
+int64_t gc_joint_q_scratch_bytes(int64_t n, int n_pairs, int* n_ctas_out) {
+  int tree_ctas = 0, act_ctas = 0;
+  joint_ctas(n, n_pairs, &tree_ctas, &act_ctas);
+  if (n_ctas_out) *n_ctas_out = tree_ctas;
+  return joint_arena_bytes(tree_ctas, act_ctas) + n * n_pairs * (int64_t)(sizeof(int) + sizeof(uint32_t));
 }
 
 int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, const uint32_t* state,
@@ -438,18 +836,30 @@ int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, co
   if (n_levels > 1 && !level_id) return gc_fail(GC_E_ARG, "gc_joint_q: n_levels > 1 needs level_id");
   if (n == 0) return GC_OK;
   if (int rc = gc_require_device()) return rc;
-  int n_ctas = 0;
-  const int64_t need = gc_joint_q_scratch_bytes(n, n_pairs, &n_ctas);
+  int tree_ctas = 0, act_ctas = 0;
+  joint_ctas(n, n_pairs, &tree_ctas, &act_ctas);
+  const int64_t need = gc_joint_q_scratch_bytes(n, n_pairs, nullptr);
   if (!scratch || scratch_bytes < need)
     return gc_fail(GC_E_ARG, "gc_joint_q: scratch of %lld bytes needed, %lld given", (long long)need, (long long)scratch_bytes);
-  Arena* arenas = reinterpret_cast<Arena*>(scratch);
-  int* flags = reinterpret_cast<int*>(reinterpret_cast<char*>(scratch) + (int64_t)n_ctas * sizeof(Arena));
+  char* base = reinterpret_cast<char*>(scratch);
+  int* flags = reinterpret_cast<int*>(base + joint_arena_bytes(tree_ctas, act_ctas));
+  uint32_t* todo = reinterpret_cast<uint32_t*>(flags + n * n_pairs);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t probs = n * n_pairs;
   const unsigned pgrid = (unsigned)((probs + 255) / 256);
-  joint_init_kernel<<<pgrid, 256, 0, st>>>(pr, q, flags, n);
-  joint_q_kernel<<<(unsigned)n_ctas, kThreads, 0, st>>>(lv, pr, n_levels > 1 ? level_id : nullptr,
-                                                       reinterpret_cast<const uint4*>(state), arenas, q, flags, n, n_agents);
+  const uint4* s4 = reinterpret_cast<const uint4*>(state);
+  const uint8_t* lid = n_levels > 1 ? level_id : nullptr;
+  static const bool per_action_only = getenv("GC_JOINT_PER_ACTION") != nullptr;  // the first-generation path, for A/B runs
+  joint_init_kernel<<<pgrid, 256, 0, st>>>(pr, q, flags, todo, n);
+  if (per_action_only) {
+    joint_q_kernel<<<(unsigned)act_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, reinterpret_cast<Arena*>(base), q, flags,
+                                                            nullptr, n, n_agents);
+  } else {
+    joint_tree_kernel<<<(unsigned)tree_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, reinterpret_cast<Arena2*>(base), q,
+                                                                flags, todo, n, n_agents);
+    joint_q_kernel<<<(unsigned)act_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, reinterpret_cast<Arena*>(base), q, flags,
+                                                            todo, n, n_agents);
+  }
   joint_finalize_kernel<<<pgrid, 256, 0, st>>>(pr, v, q, status, flags, n);
   return gc_check_launch("gc_joint_q");
 }
