@@ -272,3 +272,36 @@ def test_level1_values_inside_reference_brtdp_bracket(golden_dir):
                 below += 1
             checked += 1
     assert checked >= 100 and budget <= 8 and below <= checked // 10, (checked, budget, below)
+
+
+def test_tree_search_equals_per_action_search(tmp_path):
+    """Two independent exact solvers for joint pairs: the one-search-per-problem A* + backward pass
+    (default) and the per-action uniform-cost searches (GC_JOINT_PER_ACTION=1) must agree bit for bit
+    on V and on all 25 Q values wherever both finish inside their budgets, and the tree search must
+    not lose problems the per-action search solves.  Separate processes: the switch is read once."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for tag, extra in (("tree", {}), ("act", {"GC_JOINT_PER_ACTION": "1"})):
+        path = str(tmp_path / ("joint_%s.npz" % tag))
+        env = dict(os.environ, **extra)
+        env.pop("GC_JOINT_PER_ACTION", None) if not extra else None
+        subprocess.run([sys.executable, os.path.join(root, "scripts", "dump_joint.py"), path, "512"], check=True,
+                       env=env, cwd=root, timeout=900)
+        outs.append(np.load(path))
+    a, b = outs
+    compared = 0
+    for k in a.files:
+        if not k.endswith("_v"):
+            continue
+        lv = k[:-2]
+        sa, sb = a[lv + "_s"], b[lv + "_s"]
+        both = (sa == 0) & (sb == 0)
+        assert ((sa == 2) == (sb == 2)).all(), lv            # unreachable verdicts agree
+        assert not ((sa != 0) & (sb == 0)).any(), lv          # nothing the old search solved is lost
+        assert (a[lv + "_v"][both] == b[lv + "_v"][both]).all(), lv
+        qa, qb = a[lv + "_q"][both], b[lv + "_q"][both]
+        assert (np.isnan(qa) == np.isnan(qb)).all() and (qa[~np.isnan(qa)] == qb[~np.isnan(qb)]).all(), lv
+        compared += int(both.sum())
+    assert compared >= 2000, compared
