@@ -51,7 +51,9 @@ constexpr uint32_t kRingCap = 16 * 1024;     // entries per key bucket
 constexpr uint32_t kPool = 1u << 20;         // predecessor-list nodes
 constexpr uint32_t kGoalCap = 4096;
 constexpr uint32_t kNil = 0xFFFFFFFFu;
-constexpr int kSlack = 24;                   // explore to V* + 2.4: covers "step away and come back"
+constexpr int kSlack = 12;                   // first pass explores keys up to V* + 1.2, then widens by
+constexpr int kSlackStep = 12;               // 1.2 per round while offered actions remain unproven,
+constexpr int kMaxSlack = 48;                // up to V* + 4.8; what is still open goes to the per-action search
 
 struct Arena2 {
   unsigned long long keys[kSlots2];
@@ -59,7 +61,8 @@ struct Arena2 {
   uint32_t gcost[kSlots2];  // forward: 2*cost (+1 once settled)
   uint32_t val[kSlots2];    // backward: cost-to-go in tenths
   uint32_t head[kSlots2];   // predecessor list
-  uint32_t bucket[kRing][kRingCap];  // forward: slot | g << 17 by key f; backward: slots by cost-to-go
+  uint32_t bucket[kRing][kRingCap];      // forward open list: slot | g << 17, by key f
+  uint32_t bbucket[kBuckets][kRingCap];  // backward pass: slots by cost-to-go
   uint2 pool[kPool];        // .x = predecessor slot | (edge cost - 10) << 30, .y = next node
   uint32_t goals[kGoalCap];
 };
@@ -391,6 +394,8 @@ __device__ void fill_tables(const World& w, Tables* T) {
 __device__ uint32_t heuristic(const World& w, const Tables* T, const PState& p) {
   uint32_t best = kInfCost;
   auto pos_of = [&](uint32_t sl) { return (sl >> 13) == 0u ? ((sl >> 7) & 63u) : p.cell[(sl >> 13) - 1u]; };
+  // an object on a delivery square is never picked up again, and facing it does not merge (interact.py:41-46, 73)
+  auto stuck = [&](uint32_t sl) { return (sl >> 13) == 0u && ((w.deliv >> ((sl >> 7) & 63u)) & 1ull); };
   auto approach = [&](uint32_t sl) -> uint32_t {  // steps until some agent stands next to a lying object
     if ((sl >> 13) != 0u) return 0u;
     const uint32_t q = (sl >> 7) & 63u;
@@ -405,7 +410,7 @@ __device__ uint32_t heuristic(const World& w, const Tables* T, const PState& p) 
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const uint32_t sa = p.slot[i];
-    if ((sa >> 13) >= 3u || (sa & 0x7fu) != w.a_mask) continue;
+    if ((sa >> 13) >= 3u || (sa & 0x7fu) != w.a_mask || stuck(sa)) continue;
     if (w.goal_kind != GC_ST_MERGE) {
       const uint32_t ap = approach(sa), r = T->reach[pos_of(sa)];
       if (ap == gcnav::kFar || r == gcnav::kFar) continue;
@@ -414,7 +419,7 @@ __device__ uint32_t heuristic(const World& w, const Tables* T, const PState& p) 
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const uint32_t sb = p.slot[j];
-        if (j == i || (sb >> 13) >= 3u || (sb & 0x7fu) != w.b_mask) continue;
+        if (j == i || (sb >> 13) >= 3u || (sb & 0x7fu) != w.b_mask || stuck(sb)) continue;
         const uint32_t D = T->carry[pos_of(sa) * 64 + pos_of(sb)];
         if (D == gcnav::kFar) continue;
         uint32_t ap = 0u;
@@ -479,7 +484,7 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
                   const uint8_t* __restrict__ level_id, const uint4* __restrict__ state, Arena2* __restrict__ arenas,
                   float* __restrict__ q_out, int* __restrict__ flags, uint32_t* __restrict__ todo, int64_t n,
                   int n_agents) {
-  __shared__ uint32_t bcount[kRing];
+  __shared__ uint32_t bcount[kRing], bbcount[kBuckets];
   __shared__ uint32_t n_states, n_pool, n_goals, s_todo, s_v1, s_v2, s_f0, s_cnt;
   __shared__ int over, result, s_kind;
   __shared__ PState start;
@@ -536,8 +541,9 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
     }
     __syncthreads();
     // ---- forward A*: every state with key f <= V* + kSlack is expanded, every generated edge recorded ----
-    int empty_run = 0, limit = kMaxCost, cur = (int)s_f0;
+    int empty_run = 0, limit = kMaxCost, cur = (int)s_f0, slack = kSlack;
     bool complete = false;
+    for (;;) {  // widen the explored region until every offered action is proven (or kMaxSlack / the budget is hit)
     for (; cur <= limit; cur++) {
       const uint32_t b = (uint32_t)cur & (kRing - 1);
       if (bcount[b] == 0) {  // uniform: bcount only changes between barriers
@@ -590,52 +596,54 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
       }
       __syncthreads();
       if (over) break;
-      if (result != 0x7fffffff) limit = min(limit, result + kSlack);
+      if (result != 0x7fffffff) limit = min(kMaxCost, result + slack);
     }
     // every state with key <= radius has been expanded
     const int radius = complete ? 0x3fffffff : (over ? cur - 1 : (cur > limit ? limit : cur - 1));
     __syncthreads();
-    if (threadIdx.x < kRing) bcount[threadIdx.x] = 0;
+    if (threadIdx.x < kBuckets) bbcount[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_todo = 0;
     __syncthreads();
     if (result == 0x7fffffff) {  // no goal inside the explored region
       if (threadIdx.x == 0) {
         if (!complete) atomicOr(&flags[prob], 1);  // budget: unknown.  complete: every offered Q is +inf, exactly
         todo[prob] = 0;
       }
-      continue;
+      break;
     }
-    // ---- backward: exact cost-to-go inside the region, from the goal states over the recorded edges ----
+    // ---- backward: exact cost-to-go inside the region, from the goal states over the recorded edges
+    // (its own buckets: the forward pass may resume from its open list) ----
     for (uint32_t i = threadIdx.x; i < min(n_goals, kGoalCap); i += kThreads) {
-      const uint32_t pos = atomicAdd(&bcount[0], 1u);
-      if (pos < kRingCap) A->bucket[0][pos] = A->goals[i];
+      const uint32_t pos = atomicAdd(&bbcount[0], 1u);
+      if (pos < kRingCap) A->bbucket[0][pos] = A->goals[i];
       else atomicExch(&over, 2);
     }
     __syncthreads();
     const int bmax = complete ? kMaxCost : radius;
-    empty_run = 0;
-    for (cur = 0; cur <= bmax; cur++) {
-      const uint32_t b = (uint32_t)cur & (kBuckets - 1);
-      const uint32_t cnt = min(bcount[b], kRingCap);
+    int brun = 0;
+    for (int bc = 0; bc <= bmax; bc++) {
+      const uint32_t b = (uint32_t)bc & (kBuckets - 1);
+      const uint32_t cnt = min(bbcount[b], kRingCap);
       if (cnt == 0) {
-        if (++empty_run >= kBuckets) break;
+        if (++brun >= kBuckets) break;
         continue;
       }
-      empty_run = 0;
+      brun = 0;
       for (uint32_t e = threadIdx.x; e < cnt; e += kThreads) {
-        const uint32_t h = A->bucket[b][e];
-        if (A->val[h] != (uint32_t)cur) continue;  // improved since it was pushed
+        const uint32_t h = A->bbucket[b][e];
+        if (A->val[h] != (uint32_t)bc) continue;  // improved since it was pushed
         for (uint32_t node = A->head[h]; node != kNil; node = A->pool[node].y) {
           const uint32_t x = A->pool[node].x & 0x3FFFFFFFu;
-          const uint32_t nv = (uint32_t)cur + 10u + (A->pool[node].x >> 30);
+          const uint32_t nv = (uint32_t)bc + 10u + (A->pool[node].x >> 30);
           if (atomicMin(&A->val[x], nv) > nv) {
-            const uint32_t pos = atomicAdd(&bcount[nv & (kBuckets - 1)], 1u);
-            if (pos < kRingCap) A->bucket[nv & (kBuckets - 1)][pos] = x;
+            const uint32_t pos = atomicAdd(&bbcount[nv & (kBuckets - 1)], 1u);
+            if (pos < kRingCap) A->bbucket[nv & (kBuckets - 1)][pos] = x;
             else atomicExch(&over, 2);
           }
         }
       }
       __syncthreads();
-      if (threadIdx.x == 0) bcount[b] = 0;
+      if (threadIdx.x == 0) bbcount[b] = 0;
       __syncthreads();
     }
     // ---- Q(start, a) = cost(a) + cost-to-go of T(start, a), proven when it fits inside the region ----
@@ -657,7 +665,19 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) todo[prob] = s_todo;
+    const uint32_t open_actions = s_todo;
+    if (open_actions == 0u || complete || over || slack >= kMaxSlack || limit >= kMaxCost) {
+      if (threadIdx.x == 0) todo[prob] = open_actions;
+      break;
+    }
+    // widen: the forward pass resumes where it stopped; cost-to-go values are rebuilt from the goals
+    slack += kSlackStep;
+    limit = min(kMaxCost, result + slack);
+    for (uint32_t k = threadIdx.x; k < kSlots2; k += kThreads) A->val[k] = kInfCost;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < min(n_goals, kGoalCap); i += kThreads) A->val[A->goals[i]] = 0u;
+    __syncthreads();
+    }  // widening loop
   }
 }
 
