@@ -310,7 +310,87 @@ step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ sta
     } else {
       gclut::Env<NOBJ> e;
       gclut::unpack<NA, NOBJ>(s, e);
-      const uint32_t ncoll = gclut::step<NA, NOBJ>(e, act, T, L, done, success);
+      const uint32_t ncoll = gclut::step<NA, NOBJ>(e, act, T.st, T.mv.v, L, done, success);
+      s = gclut::pack<NA, NOBJ>(e, done);
+      gc::st_stream(state + i, s);
+      if (collisions && ncoll) collisions[i] += ncoll;
+    }
+    if (reward_done) reward_done[i] = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
+    if (hash) hash[i] = gc::state_hash<NA>(s);
+    if (executed) store_actions<NA>(executed, i, act);
+  }
+}
+
+
+// Table-driven step for multi-level batches (per-env level_id).  Same pipeline as step_lut_kernel;
+// the level tables (64 B of bitboards / goals each) arrive as a kernel parameter, every CTA stages
+// them in shared memory and derives one 512 B move table per level in its prologue - nothing is
+// uploaded per launch.  Dynamic shared memory: n_levels x 512 B.
+struct MultiShared {
+  gclut::StaticTables st;
+  GcLevelDev lv[GC_MAX_LEVELS];
+};
+
+template <int NA, int NOBJ>
+__global__ void __launch_bounds__(kThreads, GC_LUT_MIN_CTAS)
+step_lut_multi_kernel(const __grid_constant__ GcLevelsDev P, int n_levels, const uint8_t* __restrict__ level_id,
+                      uint4* __restrict__ state, const uint8_t* __restrict__ actions,
+                      uint8_t* __restrict__ reward_done, unsigned long long* __restrict__ hash,
+                      uint32_t* __restrict__ collisions, uint8_t* __restrict__ executed, int64_t n) {
+  __shared__ __align__(16) MultiShared S;
+  __shared__ __align__(16) uint4 s_stage[kThreads];
+  extern __shared__ __align__(16) uint8_t s_mv[];  // [n_levels][kMoveBytes]
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const uint32_t slot = (uint32_t)__cvta_generic_to_shared(&s_stage[threadIdx.x]);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(&g_static_tables);
+    uint4* d4 = reinterpret_cast<uint4*>(&S.st);
+    for (int k = threadIdx.x; k < (int)(sizeof(gclut::StaticTables) / 16); k += blockDim.x) d4[k] = src[k];
+    const uint32_t* ls = reinterpret_cast<const uint32_t*>(&P);
+    uint32_t* ld = reinterpret_cast<uint32_t*>(S.lv);
+    for (int k = threadIdx.x; k < n_levels * (int)(sizeof(GcLevelDev) / 4); k += blockDim.x) ld[k] = ls[k];
+    __syncthreads();
+    for (int l = 0; l < n_levels; l++) gclut::fill_move_table_dev(S.lv[l], s_mv + l * gclut::kMoveBytes);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  uint32_t a_next[NA], l_next = 0;
+#pragma unroll
+  for (int k = 0; k < NA; k++) a_next[k] = 4u;
+  if (i < n) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + i) : "memory");
+    load_actions<NA>(actions, i, a_next);
+    l_next = level_id[i];
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  __syncthreads();
+  for (; i < n; i += stride) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    uint4 s = s_stage[threadIdx.x];
+    uint32_t act[NA];
+#pragma unroll
+    for (int k = 0; k < NA; k++) act[k] = a_next[k];
+    const uint32_t lvl = min(l_next, (uint32_t)(n_levels - 1));
+    const int64_t inext = i + stride;
+    if (inext < n) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + inext) : "memory");
+      load_actions<NA>(actions, inext, a_next);
+      l_next = level_id[inext];
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const GcLevelDev& L = S.lv[lvl];
+    bool done, success;
+    if (s.x >> 31) {
+      const uint32_t t = (s.x >> 24) & 127u;
+      done = true;
+      success = !(L.max_t != 0u && t >= L.max_t);
+#pragma unroll
+      for (int k = 0; k < NA; k++) act[k] = 4u;
+    } else {
+      gclut::Env<NOBJ> e;
+      gclut::unpack<NA, NOBJ>(s, e);
+      const uint32_t ncoll = gclut::step<NA, NOBJ>(e, act, S.st, s_mv + lvl * gclut::kMoveBytes, L, done, success);
       s = gclut::pack<NA, NOBJ>(e, done);
       gc::st_stream(state + i, s);
       if (collisions && ncoll) collisions[i] += ncoll;
@@ -360,7 +440,7 @@ inline bool use_generic_step() {
 }
 
 template <int NA, int NOBJ>
-int launch_step(bool multi, const GcLevelsDev& lv, const uint8_t* level_id, uint32_t* state,
+int launch_step(bool multi, int n_levels, const GcLevelsDev& lv, const uint8_t* level_id, uint32_t* state,
                 const uint8_t* actions, uint8_t* rd, uint64_t* hash, uint32_t* coll, uint8_t* executed,
                 int64_t n, cudaStream_t st) {
   auto* s4 = reinterpret_cast<uint4*>(state);
@@ -380,6 +460,23 @@ int launch_step(bool multi, const GcLevelsDev& lv, const uint8_t* level_id, uint
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     const cudaError_t err = cudaLaunchKernelEx(&cfg, step_lut_kernel<NA, NOBJ>, P, s4, actions, rd, h, coll, executed, n);
+    if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step: launch failed: %s", cudaGetErrorString(err));
+    return gc_check_launch("gc_env_step");
+  }
+  if (multi && !use_generic_step()) {
+    static const bool pdl = getenv("GC_STEP_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(lut_grid(n));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)n_levels * gclut::kMoveBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, step_lut_multi_kernel<NA, NOBJ>, lv, n_levels, level_id, s4, actions,
+                                               rd, h, coll, executed, n);
     if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step: launch failed: %s", cudaGetErrorString(err));
     return gc_check_launch("gc_env_step");
   }
@@ -448,7 +545,7 @@ int gc_env_step(const gc_level* levels, int n_levels, const uint8_t* level_id, u
   if (n == 0) return GC_OK;
   if (int rc = gc_require_device()) return rc;
   const bool multi = n_levels > 1;
-  GC_DISPATCH_NA_NOBJ(launch_step, multi, lv, level_id, state, actions, reward_done, hash, collisions, executed,
+  GC_DISPATCH_NA_NOBJ(launch_step, multi, n_levels, lv, level_id, state, actions, reward_done, hash, collisions, executed,
                       n, (cudaStream_t)stream);
   return gc_fail(GC_E_ARG, "gc_env_step: n_agents must be 1..4");
 }

@@ -122,16 +122,16 @@ __device__ __forceinline__ uint4 pack(const Env<NOBJ>& e, bool done) {
 
 // env.step (envs/overcooked_environment.py:255-306) - same contract as gc::step.
 template <int NA, int NOBJ>
-__device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], const Tables& T,
-                                         const GcLevelDev& L, bool& done, bool& success) {
+__device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], const StaticTables& S,
+                                         const uint8_t* mv, const GcLevelDev& L, bool& done, bool& success) {
   e.t = min(e.t + 1u, 127u);  // env:257
   uint32_t tgt[NA], nxt[NA], kind8[NA];  // kind8 = kind(target) << 8, 0 for floor
 #pragma unroll
   for (int i = 0; i < NA; i++) {
     act[i] = min(act[i], 4u);
-    const uint32_t mv = T.mv.v[e.cell[i] * 8u + act[i]];
-    tgt[i] = mv & 63u;
-    kind8[i] = (mv & 0xC0u) << 2;
+    const uint32_t m = mv[e.cell[i] * 8u + act[i]];
+    tgt[i] = m & 63u;
+    kind8[i] = (m & 0xC0u) << 2;
     nxt[i] = kind8[i] ? e.cell[i] : tgt[i];  // is_collision :692-700
   }
   // check_collisions :724-762.  "agent i faces a square and keeps its action" (:705-708) is
@@ -166,9 +166,9 @@ __device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], cons
         mH = (e.place[k] == hp) ? e.mask[k] : mH;
         mT = (e.place[k] == tg) ? e.mask[k] : mT;
       }
-      const uint32_t idx = T.st.hprops[mH] + T.st.tprops[mT] + kind8[i];
-      const uint32_t c = T.st.chop[idx], m = T.st.merge[idx], d = T.st.drop[idx], p = T.st.pick[idx];
-      delivered += T.st.delivered[idx];
+      const uint32_t idx = S.hprops[mH] + S.tprops[mT] + kind8[i];
+      const uint32_t c = S.chop[idx], m = S.merge[idx], d = S.drop[idx], p = S.pick[idx];
+      delivered += S.delivered[idx];
       // Every update is flag * delta + old, i.e. one IMAD on the (idle) FMA pipe, predicated on
       // the slot being the hand slot / the square slot.
       //   hand slot:   mask += chop bits | merged contents;   place: hand -> square when dropped
@@ -207,6 +207,17 @@ __device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], cons
   done = timeout || all_goals;
   success = all_goals && !timeout;
   return ncoll;
+}
+
+// move[cell*8 + action] = target | kind(target) << 6 from a level's bitboards, filled by the CTA
+// (multi-level batches: one table per level is built in the kernel prologue)
+__device__ __forceinline__ void fill_move_table_dev(const GcLevelDev& L, uint8_t* mv) {
+  for (int k = threadIdx.x; k < kMoveBytes; k += blockDim.x) {
+    const uint32_t c = (uint32_t)k >> 3, a = (uint32_t)k & 7u;
+    const uint32_t t = (c + (uint32_t)gc::action_delta(a < 5u ? a : 4u)) & 63u;
+    const uint32_t kind = ((L.floor_mask >> t) & 1ull) ? 0u : ((L.cut_mask >> t) & 1ull) ? 2u : ((L.deliv_mask >> t) & 1ull) ? 3u : 1u;
+    mv[k] = (uint8_t)(t | (kind << 6));
+  }
 }
 
 // cooperative load of the tables into shared memory (call from every thread, then __syncthreads)
