@@ -344,8 +344,7 @@ class BatchedDelegation:
         order = torch.sort((~valid).to(torch.uint8), dim=-1, stable=True).indices
         qdiff = qdiff.gather(2, order).contiguous()
         n_valid = valid.sum(-1)
-        pos = valid.cumsum(-1) - 1
-        act_idx = pos.gather(2, taken[:, :, None])[:, :, 0]
+        act_idx = (valid & (torch.arange(5, device=dev)[None, None, :] < taken[:, :, None])).sum(-1)  # rank among the valid
         none_idx = torch.where(taken == 4, 0, 1).clamp(max=(n_valid - 1).clamp(min=0))
         act_idx = torch.where(T.row_kind[None, :] == 0, none_idx, act_idx)
         out = (probs * alive).contiguous()
