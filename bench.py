@@ -328,7 +328,7 @@ def secondary_metrics(gcb, torch, dev):
     # cfg-3 as a whole: the device-resident Bayesian-Delegation loop (lower bounds + exact Q through the
     # planning-state memo + posterior + action selection + env step), wall clock with a sync on both sides
     from gym_cooking_b200 import batched_agents
-    n_loop, loop_steps = 1 << 14, 30
+    n_loop, loop_steps = 1 << 16, 40
     loop = batched_agents.BatchedDelegation("open-divider_salad", n_loop, ("bd", "bd"), seed=1, device=dev)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -338,7 +338,7 @@ def secondary_metrics(gcb, torch, dev):
     dt = time.perf_counter() - t0
     st = loop.kb.stats().cpu().tolist()
     out.append({"metric": "bd_loop_agent_steps_per_sec", "value": n_loop * 2 * loop_steps / dt, "unit": "agent-steps/s",
-                "config": "cfg-3: 2-agent open-divider_salad, bd/bd, 2^14 envs x %d steps from reset, cold planner memo"
+                "config": "cfg-3: 2-agent open-divider_salad, bd/bd, 2^16 envs x %d steps from reset, cold planner memo"
                           % loop_steps,
                 "posterior_updates_per_sec": loop.posterior_updates / dt, "seconds": dt,
                 "delivered_by_step_%d" % loop_steps: st[1], "planning_states_solved": loop.cache.solved_states})

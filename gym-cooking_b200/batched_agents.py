@@ -340,11 +340,14 @@ class BatchedDelegation:
         none_valid = torch.arange(5, device=dev)[None, :] <= k[:, None]
         valid = torch.where(is_none, none_valid[:, None, :], valid)
         qdiff = torch.where(is_none, none_row[:, None, :], qdiff)
-        # compact the valid actions to the front (the kernel reads the first n_valid entries)
-        order = torch.sort((~valid).to(torch.uint8), dim=-1, stable=True).indices
-        qdiff = qdiff.gather(2, order).contiguous()
+        # compact the valid actions to the front, in order (the kernel reads the first n_valid entries)
+        before = torch.ones((5, 5), dtype=torch.bool, device=dev).tril(-1)  # before[k][j] = j < k
         n_valid = valid.sum(-1)
-        act_idx = (valid & (torch.arange(5, device=dev)[None, None, :] < taken[:, :, None])).sum(-1)  # rank among the valid
+        rank_valid = (valid[:, :, None, :] & before).sum(-1)
+        rank_invalid = (~valid[:, :, None, :] & before).sum(-1)
+        dest = torch.where(valid, rank_valid, n_valid[:, :, None] + rank_invalid)
+        qdiff = torch.zeros_like(qdiff).scatter_(2, dest, qdiff)
+        act_idx = rank_valid.gather(2, taken[:, :, None])[:, :, 0]
         none_idx = torch.where(taken == 4, 0, 1).clamp(max=(n_valid - 1).clamp(min=0))
         act_idx = torch.where(T.row_kind[None, :] == 0, none_idx, act_idx)
         out = (probs * alive).contiguous()

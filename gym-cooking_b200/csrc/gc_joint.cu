@@ -706,12 +706,14 @@ joint_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant
     const int64_t env = prob / pairs.n;
     const int pi = (int)(prob - env * pairs.n);
     const uint32_t a1 = (uint32_t)(act / 5), a2 = (uint32_t)(act % 5);
+    // after the tree search nearly every action is settled: skip without a barrier (the read is uniform)
+    if (todo && !((todo[prob] >> act) & 1u)) continue;
     __syncthreads();
     if (threadIdx.x == 0) {
       root_state = 1;
       PState p;
       gc_subtask st;
-      const bool wanted = !todo || ((todo[prob] >> act) & 1u);
+      const bool wanted = true;
       const int kind = wanted ? setup_problem(levels, pairs, level_id, state, env, pi, n_agents, w, p, st) : 0;
       if (kind == 1) {
         atomicOr(&flags[prob], 4);

@@ -6,7 +6,7 @@ from torch.profiler import profile, ProfilerActivity
 from gym_cooking_b200 import batched_agents
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 loop = batched_agents.BatchedDelegation("open-divider_salad", n, ("bd", "bd"), seed=1)
-for _ in range(12): loop.step()
+for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 12): loop.step()
 torch.cuda.synchronize()
 t0 = time.time()
 for _ in range(3): loop.step()
