@@ -401,6 +401,41 @@ step_lut_multi_kernel(const __grid_constant__ GcLevelsDev P, int n_levels, const
   }
 }
 
+// Fused rollout, table-driven form (single-level batches): same philox stream and the same
+// transitions as rollout_kernel, with gclut::step instead of gc::step.
+template <int NA, int NOBJ>
+__global__ void __launch_bounds__(kThreads)
+rollout_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ state,
+                   uint8_t* __restrict__ reward_done, unsigned long long* __restrict__ hash_trace,
+                   uint32_t* __restrict__ collisions, int64_t n, int n_steps, uint32_t t0, int64_t env0,
+                   unsigned long long seed) {
+  __shared__ __align__(16) gclut::Tables T;
+  gclut::load_tables(&T, &g_static_tables, P.mv);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const GcLevelDev& L = P.lv;
+  uint4 s = gc::ld_stream(state + i);
+  gclut::Env<NOBJ> e;
+  gclut::unpack<NA, NOBJ>(s, e);
+  bool done = s.x >> 31;
+  bool success = done && !(L.max_t != 0u && e.t >= L.max_t);
+  uint32_t ncoll = 0;
+  for (int k = 0; k < n_steps; k++) {
+    if (!done) {
+      uint32_t r[4], act[NA];
+      gc::philox_actions(seed, t0 + (uint32_t)k, (unsigned long long)(env0 + i), r);
+#pragma unroll
+      for (int a = 0; a < NA; a++) act[a] = r[a];
+      ncoll += gclut::step<NA, NOBJ>(e, act, T.st, T.mv.v, L, done, success);
+    }
+    if (hash_trace) hash_trace[(int64_t)k * n + i] = gc::state_hash<NA>(gclut::pack<NA, NOBJ>(e, done));
+  }
+  gc::st_stream(state + i, gclut::pack<NA, NOBJ>(e, done));
+  if (reward_done) reward_done[i] = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
+  if (collisions && ncoll) collisions[i] += ncoll;
+}
+
 // host: move[cell*8 + action] = target | kind(target) << 6 from the level's bitboards
 void fill_move_table(const GcLevelDev& L, gclut::MoveTable* mv) {
   static const int delta[5] = {8, -8, -1, 1, 0};
@@ -493,6 +528,14 @@ int launch_rollout(bool multi, const GcLevelsDev& lv, const uint8_t* level_id, u
                    uint64_t seed, cudaStream_t st) {
   auto* s4 = reinterpret_cast<uint4*>(state);
   auto* h = reinterpret_cast<unsigned long long*>(hash_trace);
+  if (!multi && !use_generic_step()) {
+    StepLutParams P;
+    P.lv = lv.lv[0];
+    fill_move_table(P.lv, &P.mv);
+    rollout_lut_kernel<NA, NOBJ><<<grid_for(n), kThreads, 0, st>>>(P, s4, rd, h, coll, n, n_steps, (uint32_t)t0, env0,
+                                                                   seed);
+    return gc_check_launch("gc_env_rollout");
+  }
   if (multi)
     rollout_kernel<NA, NOBJ, true><<<grid_for(n), kThreads, 0, st>>>(lv, level_id, s4, rd, h, coll, n, n_steps,
                                                                      (uint32_t)t0, env0, seed);
