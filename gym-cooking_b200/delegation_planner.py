@@ -55,6 +55,29 @@ class SubtaskAllocDistribution:
         best = max(self.probs.values())
         return random.choice([a for a, p in self.probs.items() if p == best])
 
+    def get_max_bucketed(self):  # :50-158 - marginal over single allocations, best full allocation containing it
+        subtasks, probs = [], []
+        for alloc, p in self.probs.items():
+            for t in alloc:
+                if t in subtasks:
+                    probs[subtasks.index(t)] += p
+                else:
+                    subtasks.append(t)
+                    probs.append(p)
+        if not subtasks:
+            return None
+        best = subtasks[int(np.argmax(probs))]
+        cands = [(a, p) for a, p in self.probs.items() if best in a]
+        return max(cands, key=lambda ap: ap[1])[0]
+
+    def get_best_containing(self, subtask):  # :160-168 (returns the subtask itself, as the reference does)
+        valid, valid_p = [], []
+        for alloc, p in self.probs.items():
+            if subtask in alloc:
+                valid.append(subtask)
+                valid_p.append(p)
+        return valid[int(np.argmax(valid_p))]
+
     def set(self, subtask_alloc, value):
         self.probs[tuple(subtask_alloc)] = value
 
@@ -133,6 +156,18 @@ class BayesianDelegator:
     def get_subtask_alloc_probs(self):  # :81-90
         return SubtaskAllocDistribution(hypothesis_space(self.model_type, self.agent_name, self.all_agent_names,
                                                          self.incomplete_subtasks))
+
+    def add_subtasks(self):  # :792-886
+        return hypothesis_space("bd", self.agent_name, self.all_agent_names, self.incomplete_subtasks)
+
+    def add_greedy_subtasks(self):  # :892-923
+        return hypothesis_space("greedy", self.agent_name, self.all_agent_names, self.incomplete_subtasks)
+
+    def add_dc_subtasks(self):  # :928-1000
+        return hypothesis_space("dc", self.agent_name, self.all_agent_names, self.incomplete_subtasks)
+
+    def get_other_subtask_allocations(self, remaining_agents, remaining_subtasks, base_subtask_alloc):  # :697-784
+        return _others(list(remaining_agents), list(remaining_subtasks), list(base_subtask_alloc))
 
     def _doable_table(self, env, allocs):
         """{(subtask, agent names): doable} for every pair named by `allocs`, one gc_lower_bound call"""

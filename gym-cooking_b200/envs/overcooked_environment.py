@@ -31,7 +31,41 @@ TERMINATION_TIMEOUT = "Terminating because passed {} timesteps"
 TERMINATION_SUCCESS = "Terminating because all deliveries were completed"
 
 
-class EnvView:
+class _ReferenceSurface:
+    """Read-only helpers of the reference env that both the facade and its obs views offer
+    (env:66-98 __str__, :378-390 print_agents/display/update_display, :396-473 run_recipes,
+    :594-664 get_lower_bound_for_subtask_given_objs)."""
+
+    def update_display(self):
+        self.rep = self.world.update_display()
+        for agent in self.sim_agents:
+            x, y = agent.location
+            self.rep[y][x] = str(agent)
+
+    def __str__(self):
+        self.update_display()
+        return "\n".join("".join(c + " " for c in row) for row in self.rep)
+
+    def display(self):
+        print(str(self))
+
+    def print_agents(self):
+        for a in self.sim_agents:
+            a.print_status()
+
+    def run_recipes(self):
+        return list(self.all_subtasks)
+
+    def get_lower_bound_for_subtask_given_objs(self, subtask, subtask_agent_names, start_obj=None, goal_obj=None,
+                                               subtask_action_obj=None):
+        """env:594-664 through gc_lower_bound; the object arguments follow from the subtask
+        (nav_utils.get_subtask_obj / get_subtask_action_obj) and are accepted for signature parity."""
+        assert len(subtask_agent_names) <= 2, "passed in %d agents but can only do 1 or 2" % len(subtask_agent_names)
+        from .. import navigation_planner
+        return navigation_planner.lower_bound_pair(self, subtask, subtask_agent_names)
+
+
+class EnvView(_ReferenceSurface):
     """What the reference hands out as `obs` (a copy of the env): world + sim_agents + t."""
 
     def __init__(self, env, words, actions=None):
@@ -126,7 +160,7 @@ class BatchObs:
         return EnvView(self._env, self.state[i].tolist())
 
 
-class OvercookedEnvironment:
+class OvercookedEnvironment(_ReferenceSurface):
     """Environment object for Overcooked (batched)."""
 
     metadata = {}

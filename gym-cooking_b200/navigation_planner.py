@@ -81,6 +81,16 @@ def solve_pair(env, subtask, subtask_agent_names, level1=False):
     return v, table, status
 
 
+def lower_bound_pair(env, subtask, subtask_agent_names):
+    """env.get_lower_bound_for_subtask_given_objs (env:594-664) of one (subtask, agent set) at env's state"""
+    pb = _plan_batch(env)
+    words = np.array(packed_words(env), dtype=np.uint32).view(np.int32)
+    pb.state.copy_(torch.from_numpy(words).to(pb.device).view(1, 4))
+    pb.set_subtask_masks([recipe_planner.subtask_masks(subtask)])
+    idx = sorted(int(nm.split("-")[1]) - 1 for nm in subtask_agent_names)
+    return float(planning.lower_bound(pb, [(0, idx[0], idx[1] if len(idx) > 1 else None)])[0, 0])
+
+
 def goal_count(world, subtask, goal_obj, delivery_locs):
     """e2e_brtdp._define_goal_state :435-566: how many goal objects the world holds"""
     if isinstance(subtask, recipe_planner.Deliver):
@@ -155,6 +165,18 @@ class E2E_BRTDP:
     def Q(self, state, action, value_f=None):
         """cost(s, a) + V*(T(s, a)) at the planning start state (:740-779); +inf for an invalid action"""
         return self._q.get(tuple(action) if not self.is_joint else (tuple(action[0]), tuple(action[1])), _INF)
+
+    def V(self, state, _type):
+        """V(s) = min_a Q(s, a) at the planning start state (:784-809); lower == upper here"""
+        return min(self._q.values()) if self._q else 0.0
+
+    def value_init(self, env_state):  # :701-737 - the bounds are exact from the start
+        key = (env_state.get_repr(), self.subtask)
+        self.v_l.setdefault(key, self.v_l.get((self.start.get_repr(), self.subtask), 0.0))
+        self.v_u.setdefault(key, self.v_l[key])
+
+    def get_subtask_agents(self, env_state):  # :645-659
+        return [a for a in env_state.sim_agents if a.name in self.subtask_agent_names]
 
     def cost(self, state, action):  # :816-826
         acts = [action] if isinstance(action[0], int) else list(action)

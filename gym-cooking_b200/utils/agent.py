@@ -20,6 +20,12 @@ class SimAgent:
     def get_holding(self):
         return "None" if self.holding is None else self.holding.full_name
 
+    def __str__(self):  # agent.py:382-383 (without the terminal colour codes)
+        return self.name[-1]
+
+    def print_status(self):  # agent.py:401-406
+        print("{} currently at {}, action {}, holding {}".format(self.name, self.location, self.action, self.get_holding()))
+
     def __repr__(self):
         return "SimAgent(%s @%s holding %s)" % (self.name, self.location, self.get_holding())
 
@@ -56,14 +62,39 @@ class RealAgent:
         me = next(a for a in obs.sim_agents if a.name == self.name)
         self.location, self.holding, self.action = me.location, me.holding, me.action
         if obs.t == 0:
-            self.incomplete_subtasks = list(obs.all_subtasks)
-            self.delegator = delegation_planner.BayesianDelegator(
-                agent_name=self.name, all_agent_names=obs.get_agent_names(), model_type=self.model_type,
-                planner=self.planner, none_action_prob=self.none_action_prob)
+            self.setup_subtasks(env=obs)
         self.update_subtasks(obs)
         self.new_subtask, self.new_subtask_agent_names = self.delegator.select_subtask(agent_name=self.name)
         self.plan(obs)
         return self.action
+
+    def __str__(self):  # :60-61
+        return self.name[-1]
+
+    def get_subtasks(self, world):  # :110-121 - the level's subtask list from the host recipe planner
+        from .. import recipe_planner
+        kinds = [nm for nm in ("Tomato", "Lettuce", "Onion", "Plate") for o in world.get_object_list()
+                 if getattr(o, "mask", None) is not None and o.name == nm]
+        return recipe_planner.level_subtasks(self.recipes, kinds, int(getattr(self.arglist, "max_num_subtasks", 14)))
+
+    def setup_subtasks(self, env):  # :123-146
+        from .. import delegation_planner
+        self.incomplete_subtasks = (list(env.all_subtasks) if getattr(env, "all_subtasks", None) is not None
+                                    else self.get_subtasks(world=env.world))
+        self.delegator = delegation_planner.BayesianDelegator(
+            agent_name=self.name, all_agent_names=env.get_agent_names(), model_type=self.model_type,
+            planner=self.planner, none_action_prob=self.none_action_prob)
+
+    def def_subtask_completion(self, env):  # :286-368
+        from ..navigation_planner import goal_count
+        from ..recipe_planner import subtask_masks
+        from .core import Object
+        goal_obj = Object((None, None), subtask_masks(self.new_subtask)[3])
+        delivery = [gs.location for gs in env.world.objects.get("Delivery", [])]
+        subtask = self.new_subtask
+        base = goal_count(env.world, subtask, goal_obj, delivery)
+        self.start_obj, self.goal_obj, self.cur_obj_count = None, goal_obj, base
+        self.is_subtask_complete = lambda w: goal_count(w, subtask, goal_obj, delivery) > base
 
     def update_subtasks(self, env):  # :176-203
         if ((self.subtask is not None and self.subtask not in self.incomplete_subtasks)
@@ -90,15 +121,8 @@ class RealAgent:
     def plan(self, env):  # :218-281
         import numpy as np
         from ..delegation_planner import _single_actions
-        from ..navigation_planner import goal_count
-        from ..recipe_planner import subtask_masks
-        from .core import Object
-        if self.new_subtask is not None:  # def_subtask_completion :286-368
-            goal_obj = Object((None, None), subtask_masks(self.new_subtask)[3])
-            delivery = [gs.location for gs in env.world.objects.get("Delivery", [])]
-            subtask, base = self.new_subtask, None
-            base = goal_count(env.world, subtask, goal_obj, delivery)
-            self.is_subtask_complete = lambda w: goal_count(w, subtask, goal_obj, delivery) > base
+        if self.new_subtask is not None:
+            self.def_subtask_completion(env=env)
         if self.new_subtask is None or not self.new_subtask_agent_names:
             me = next(a for a in env.sim_agents if a.name == self.name)
             actions = _single_actions(env, me)

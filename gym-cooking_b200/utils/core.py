@@ -37,6 +37,9 @@ class GridSquare:
     def __repr__(self):
         return "%s%r" % (self.name, (self.location,))
 
+    def __str__(self):  # core.py:37-38, without the terminal colour codes
+        return self.rep
+
 
 class Floor(GridSquare):
     collidable = False
@@ -164,6 +167,10 @@ class Object:
         return self.full_name
 
     __repr__ = __str__
+
+    def rep_str(self):
+        """the reference's Object.__str__ (core.py:139-141): content letters joined by '-', sorted by name"""
+        return "-".join(nm[0].lower() for nm, bit in KINDS if self.mask & bit)
 
     def get_repr(self):
         return ObjectRepr(name=self.full_name, location=self.location, is_held=self.is_held)

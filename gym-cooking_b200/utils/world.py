@@ -46,6 +46,21 @@ class World:
     def get_repr(self):
         return self.get_dynamic_objects()
 
+    def update_display(self):  # world.py:42-53
+        self.rep = [[" " for _ in range(self.width)] for _ in range(self.height)]
+        show = lambda o: o.rep_str() if hasattr(o, "rep_str") else str(o)
+        for obj in self.get_object_list():
+            x, y = obj.location
+            self.rep[y][x] = show(obj)
+        for obj in self.objects.get("Tomato", []):
+            x, y = obj.location
+            self.rep[y][x] = show(obj)
+        return self.rep
+
+    def print_objects(self):  # world.py:55-58
+        for k, v in self.objects.items():
+            print(k, [o.location for o in v])
+
     def get_object_list(self):
         out = []
         for v in self.objects.values():

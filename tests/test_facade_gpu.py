@@ -95,3 +95,27 @@ def test_batched_facade_host_actions():
     assert view.t == 30 and [a.location for a in view.sim_agents] == \
         [(x, y) for (x, y, _) in gcb.decode_state(w, 2)["agents"]]
     assert len(env.all_subtasks) == 6 and str(env.all_subtasks[0]) == "Chop(Tomato)"
+
+
+def test_reference_named_helpers():
+    """display / lower-bound / recipe helpers the reference's callers use on env and obs (env:66-98, 378-473, 594-664)"""
+    import argparse
+    ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=100, max_num_subtasks=14, seed=1,
+                            model1="bd", model2="bd", model3=None, model4=None, record=False, with_image_obs=False)
+    env = gcb.make(arglist=ns)
+    obs = env.reset()
+    text = str(obs)
+    rows = text.split("\n")
+    assert len(rows) == 7 and all(len(r) >= 14 for r in rows)
+    assert "1" in text and "2" in text and "t" in text and "p" in text and "/" in text and "*" in text
+    assert str(env) == text
+    assert [str(s) for s in obs.run_recipes()] == [str(s) for s in env.all_subtasks]
+    chop = env.all_subtasks[0]
+    lb1 = obs.get_lower_bound_for_subtask_given_objs(chop, ("agent-1",), None, None, None)
+    lb2 = env.get_lower_bound_for_subtask_given_objs(chop, ("agent-1", "agent-2"), None, None, None)
+    assert 1.0 <= lb2 <= lb1 < obs.world.perimeter
+    from gym_cooking_b200.utils.agent import RealAgent
+    agent = RealAgent(ns, "agent-1", "blue", env.recipes)
+    assert [str(s) for s in agent.get_subtasks(obs.world)] == [str(s) for s in env.all_subtasks]
+    agent.setup_subtasks(env=obs)
+    assert agent.delegator.add_subtasks() and str(agent) == "1"
