@@ -159,6 +159,9 @@ class _ObserverTables:
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         self.ent_sub, self.ent_lid, self.ent_pid0 = t(sub), t(lid), t(pid0)
         self.ent_has = t((sub >= 0) & (sub < S))
+        has = (sub >= 0) & (sub < S)
+        self.ent_lidx = t(np.where(has, lid, len(owner.lpairs)))
+        self.ent_pidx = t(np.where(has, pid0, len(owner.cpairs)))
         self.ent_subc = t(np.clip(sub, 0, S - 1))
         self.hyp_pair = t(hyp_pair)
         self.static_ok, self.fallback, self.rank = t(static_ok), t(fallback), t(rank)
@@ -209,6 +212,7 @@ class BatchedDelegation:
                 for lvl in ((0, 1) if len(ag) == 1 and self.NA > 1 else (0,)):
                     self.pid[(s, ag, lvl)] = len(self.cpairs)
                     self.cpairs.append((s, ag[0], ag[1] if len(ag) > 1 else None, bool(lvl)))
+        self.lpair_sub = torch.tensor([p[0] for p in self.lpairs], dtype=torch.int64, device=self.device)
         self.cache = PlanCache(self.kb, self.cpairs)
         self.tables = [_ObserverTables(self, i, models[i]) for i in range(self.NA)]
         masks = [recipe_planner.subtask_masks(s) for s in self.subtasks]
@@ -287,10 +291,17 @@ class BatchedDelegation:
 
     # -- one observer --------------------------------------------------------------------------
     def _entries_ok(self, T, doable, inc):
-        ok = doable[:, T.ent_lid]  # [N][H][E]
+        """hypothesis h survives iff each of its entries is None / empty or names a doable (and, with
+        `inc`, still incomplete) subtask: evaluated per (subtask, agent set) pair first ([N][3S], small),
+        then gathered per hypothesis entry"""
+        ok = doable
         if inc is not None:
-            ok = ok & (((inc[:, None, None] >> T.ent_subc) & 1) != 0)
-        return (ok | ~T.ent_has).all(-1)
+            ok = ok & (((inc[:, None] >> self.lpair_sub[None, :]) & 1) != 0)
+        ok = torch.cat([ok, torch.ones((ok.shape[0], 1), dtype=torch.bool, device=ok.device)], dim=1)
+        out = ok[:, T.ent_lidx[:, 0]]
+        for e in range(1, T.E):
+            out = out & ok[:, T.ent_lidx[:, e]]
+        return out
 
     def _pick(self, cand, rank=None):
         """index of one True per row of `cand`: uniformly random, or lowest rank when deterministic"""
@@ -305,8 +316,11 @@ class BatchedDelegation:
         p = alive.double() / cnt
         if T.spatial:  # get_spatial_priors bd:296-369: 4 * sum_t 1 / v_l(t)
             inv_v = 1.0 / self.cache.v[ci].double().clamp(min=1e-9)
-            w = (inv_v[:, T.ent_pid0] * T.ent_has).sum(-1) * 4.0
-            p = p * w
+            inv_v = torch.cat([inv_v, torch.zeros((inv_v.shape[0], 1), dtype=torch.float64, device=inv_v.device)], dim=1)
+            w = inv_v[:, T.ent_pidx[:, 0]]
+            for e in range(1, T.E):
+                w = w + inv_v[:, T.ent_pidx[:, e]]
+            p = p * (w * 4.0)
         tot = p.sum(1, keepdim=True)
         return torch.where(tot == 0, alive.double() / cnt, p / tot.clamp(min=1e-300))
 
@@ -315,18 +329,17 @@ class BatchedDelegation:
         N, dev, me = self.N, self.device, T.me
         pv = self.prev
         ex = self.executed.long()
-        q = self.cache.q[pv["ci"][:, None], T.row_pid[None, :]]  # [N][P][25]
         taken = ex[:, T.row_agent]  # [N][P] action of the row's (first) agent
+        ai = torch.arange(5, device=dev)[None, None, :]
         if self.NA == 2:  # joint rows: only joint actions matching the partner's move (bd:677-679)
             partner = ex[:, 1 - me][:, None, None]
-            ai = torch.arange(5, device=dev)[None, None, :]
             jidx = (ai * 5 + partner) if me == 0 else (partner * 5 + ai)
-            qj = q.gather(2, jidx.expand(N, T.P, 5))
             is_joint = (T.row_kind == 2)[None, :, None]
-            q5 = torch.where(is_joint, qj, q[:, :, :5])
+            idx5 = torch.where(is_joint, jidx, ai)
             taken = torch.where(T.row_kind[None, :] == 2, ex[:, me][:, None].expand(N, T.P), taken)
         else:
-            q5 = q[:, :, :5]
+            idx5 = ai.expand(N, T.P, 5)
+        q5 = self.cache.q[pv["ci"][:, None, None], T.row_pid[None, :, None], idx5]  # [N][P][5]
         onehot = torch.arange(5, device=dev)[None, None, :] == taken[:, :, None]
         valid = ~torch.isnan(q5) | onehot
         qc = torch.nan_to_num(q5, nan=UNREACHABLE_Q, posinf=UNREACHABLE_Q).clamp(max=UNREACHABLE_Q).double()
@@ -351,9 +364,10 @@ class BatchedDelegation:
         none_idx = torch.where(taken == 4, 0, 1).clamp(max=(n_valid - 1).clamp(min=0))
         act_idx = torch.where(T.row_kind[None, :] == 0, none_idx, act_idx)
         out = (probs * alive).contiguous()
-        planning.bd_posterior(out, alive.to(torch.uint8).contiguous(),
-                              T.hyp_pair[None].expand(N, T.H, T.E).contiguous(),
-                              T.pair_w[None].expand(N, T.P).contiguous(), qdiff,
+        if getattr(T, "_hyp_pair_n", None) is None or T._hyp_pair_n.shape[0] != N:  # static: expand once
+            T._hyp_pair_n = T.hyp_pair[None].expand(N, T.H, T.E).contiguous()
+            T._pair_w_n = T.pair_w[None].expand(N, T.P).contiguous()
+        planning.bd_posterior(out, alive.to(torch.uint8).contiguous(), T._hyp_pair_n, T._pair_w_n, qdiff,
                               n_valid.to(torch.uint8).contiguous(), act_idx.to(torch.uint8).contiguous(), self.beta)
         self.posterior_updates += N
         return out
