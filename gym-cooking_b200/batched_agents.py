@@ -196,6 +196,7 @@ class BatchedDelegation:
                 raise ValueError("unknown model type %r" % (m,))
         self.models, self.beta, self.none_action_prob = tuple(models), float(beta), float(none_action_prob)
         self.deterministic = bool(deterministic)
+        self._level, self._max_t = level, max_num_timesteps
         self.kb = engine.KitchenBatch(level, self.NA, num_envs, max_num_timesteps, device=device, track_collisions=True)
         self.device, self.N = self.kb.device, self.kb.num_envs
         self.names = ["agent-%d" % (i + 1) for i in range(self.NA)]
@@ -232,6 +233,8 @@ class BatchedDelegation:
 
     # -- state -------------------------------------------------------------------------------
     def reset(self):
+        self.wkb, self.ids = self.kb, None  # working batch: the envs still running (== kb until run() compacts)
+        self.N = self.kb.num_envs
         N, NA, dev = self.N, self.NA, self.device
         self.kb.reset()
         self.t = 0
@@ -428,8 +431,8 @@ class BatchedDelegation:
 
     # -- the loop -----------------------------------------------------------------------------
     def step(self):
-        """One pass of main_loop's body for every env; returns the reward/done bytes."""
-        kb = self.kb
+        """One pass of main_loop's body for every env of the working batch; returns its reward/done bytes."""
+        kb = self.wkb
         state = kb.state
         ci = self.cache.lookup(state)
         doable = planning.lower_bound(kb, self.lpairs) < self.perimeter  # bd:156
@@ -446,13 +449,46 @@ class BatchedDelegation:
         self.t += 1
         return kb.reward_done
 
-    def run(self, max_steps=None):
-        """Steps until every env is done (env.done(), main.py:99); returns the number of steps."""
+    def _write_back(self):
+        """final states of the working batch into the full batch"""
+        if self.ids is not None:
+            self.kb.state[self.ids] = self.wkb.state
+            self.kb.reward_done[self.ids] = self.wkb.reward_done
+            self.kb.collisions[self.ids] = self.wkb.collisions
+
+    def _compact(self):
+        """Drop the finished envs from the working batch: a done env only repeats its last state, but
+        it would still pay for the delegation arithmetic of every later step."""
+        self._write_back()
+        keep = ~self.wkb.done
+        live = keep.nonzero()[:, 0]
+        ids = live if self.ids is None else self.ids[live]
+        nkb = engine.KitchenBatch(self._level, self.NA, int(live.numel()), self._max_t, device=self.device,
+                                  track_collisions=True)
+        nkb.state.copy_(self.wkb.state[live])
+        nkb.reward_done.copy_(self.wkb.reward_done[live])
+        nkb.collisions.copy_(self.wkb.collisions[live])
+        self.wkb, self.ids, self.N = nkb, ids, nkb.num_envs
+        for name in ("incomplete", "cur_sub", "cur_joint", "has_probs", "executed"):
+            setattr(self, name, getattr(self, name)[live].contiguous())
+        self.probs = [p[live].contiguous() for p in self.probs]
+        self.alive = [a[live].contiguous() for a in self.alive]
+        if self.prev is not None:
+            self.prev = {k: v[live].contiguous() for k, v in self.prev.items()}
+
+    def run(self, max_steps=None, compact=True):
+        """Steps until every env is done (env.done(), main.py:99); returns the number of steps.  With
+        `compact`, finished envs leave the working batch once they are the majority; `kb` holds
+        every env's final state when this returns."""
         limit = max_steps if max_steps is not None else self.kb.max_num_timesteps + 1
         steps = 0
         while steps < limit:
             rd = self.step()
             steps += 1
-            if bool((rd & 1).all()):
+            done = int((rd & 1).sum())
+            if done == self.N:
                 break
+            if compact and self.N >= 4096 and 2 * done >= self.N:
+                self._compact()
+        self._write_back()
         return steps

@@ -9,17 +9,10 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 max_steps = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 loop = batched_agents.BatchedDelegation(level, n, ("bd", "bd"), seed=1)
 torch.cuda.synchronize(); t0 = time.time()
-steps = 0
-while steps < max_steps:
-    ts = time.time()
-    rd = loop.step(); steps += 1
-    done = int((rd & 1).sum())
-    torch.cuda.synchronize()
-    if steps <= 5 or steps % 10 == 0:
-        print("step %d: %.3f s, done %d/%d, cache %d states" % (steps, time.time() - ts, done, n, loop.cache.keys.shape[0]), flush=True)
-    if done == n:
-        break
+steps = loop.run(max_steps=max_steps)
+n_work = loop.wkb.num_envs
 torch.cuda.synchronize(); dt = time.time() - t0
+print("working batch at the end: %d envs" % n_work)
 stats = loop.kb.stats().cpu().numpy()
 t = ((loop.kb.state[:, 0].to(torch.int64) >> 24) & 127).float()
 print("%s n=%d: %d loop steps in %.2f s; delivered %d (%.1f%%), mean t %.1f; %d posterior updates (%.3e/s), %.3e agent-steps/s, %d planning states solved for %d lookups" % (

@@ -60,10 +60,10 @@ def test_batched_loop_equals_facade_loop(level, models, deterministic_facade):
     assert bool(loop.kb.done.all()) == bool(env.done())
 
 
-@pytest.mark.parametrize("level,models,limit", [("open-divider_tomato", ("bd", "bd"), 40),
-                                                ("partial-divider_tl", ("bd", "bd"), 100)])
-def test_random_tie_breaks_finish(level, models, limit):
-    n = 512
+@pytest.mark.parametrize("level,models,limit,n", [("open-divider_tomato", ("bd", "bd"), 40, 512),
+                                                  ("partial-divider_tl", ("bd", "bd"), 100, 512),
+                                                  ("open-divider_tomato", ("bd", "bd"), 40, 8192)])  # compacts on the way
+def test_random_tie_breaks_finish(level, models, limit, n):
     loop = batched_agents.BatchedDelegation(level, n, models, seed=3)
     steps = loop.run()
     stats = loop.kb.stats().cpu().numpy()
@@ -76,3 +76,4 @@ def test_random_tie_breaks_finish(level, models, limit):
     assert success >= 0.9 * n
     assert float(t[loop.kb.reward.bool()].mean()) <= limit
     assert loop.cache.solved_states < loop.cache.lookups / 4  # the memo is doing its job
+    assert int(stats[0]) == n and loop.kb.num_envs == n and (n < 4096 or loop.wkb.num_envs < n)
