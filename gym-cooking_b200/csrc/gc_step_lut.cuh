@@ -8,7 +8,8 @@
 //   * object predicates      -> two look-ups  hprops[mask in hand], tprops[mask on the square]
 //   * interact() case split  -> five 1 KB look-ups of 0/1 flags (chop, merge, drop, pick, delivered)
 //                               indexed by hprops | tprops | kind<<8
-//   * applying the outcome   -> flag * delta + old  (IMAD, FMA pipe), predicated per slot
+//   * slot gather / scatter  -> 0/1 "is the hand slot" / "is the square slot" flags per slot, then
+//                               flag * value + acc  (IMAD, FMA pipe; inline PTX keeps it an IMAD)
 // Semantics are those of gc::step (gc_device.cuh), which stays the reference form in the
 // multi-level kernels and is compared bit for bit against this one in the GPU tests.
 #pragma once
@@ -120,6 +121,13 @@ __device__ __forceinline__ uint4 pack(const Env<NOBJ>& e, bool done) {
   return make_uint4(x, w[0], w[1], w[2]);
 }
 
+// a * b + c that stays an IMAD (inline PTX: the compiler otherwise rewrites flag * delta into SEL + IADD)
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
 // env.step (envs/overcooked_environment.py:255-306) - same contract as gc::step.
 template <int NA, int NOBJ>
 __device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], const StaticTables& S,
@@ -160,34 +168,28 @@ __device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], cons
     e.cell[i] = cancel[i] ? e.cell[i] : nxt[i];  // interact.py:29-30
     if (!cancel[i] && kind8[i] != 0u) {          // utils/interact.py:33-89
       const uint32_t hp = (uint32_t)(i + 1) << 6, tg = tgt[i];
-      uint32_t mH = 0, mT = 0;
+      // 0/1 flags per slot once, then every gather / scatter is an IMAD on the (idle) FMA pipe
+      uint32_t fH[NOBJ], fT[NOBJ], mH = 0, mT = 0;
 #pragma unroll
       for (int k = 0; k < NOBJ; k++) {
-        mH = (e.place[k] == hp) ? e.mask[k] : mH;
-        mT = (e.place[k] == tg) ? e.mask[k] : mT;
+        fH[k] = e.place[k] == hp ? 1u : 0u;
+        fT[k] = e.place[k] == tg ? 1u : 0u;
+        mH = imad(fH[k], e.mask[k], mH);
+        mT = imad(fT[k], e.mask[k], mT);
       }
       const uint32_t idx = S.hprops[mH] + S.tprops[mT] + kind8[i];
       const uint32_t c = S.chop[idx], m = S.merge[idx], d = S.drop[idx], p = S.pick[idx];
       delivered += S.delivered[idx];
-      // Every update is flag * delta + old, i.e. one IMAD on the (idle) FMA pipe, predicated on
-      // the slot being the hand slot / the square slot.
-      //   hand slot:   mask += chop bits | merged contents;   place: hand -> square when dropped
-      //   square slot: picked up (square -> hand) or merged away (mask 0, dead place)
-      const uint32_t chop_bits = mH * 16u, to_square = tg - hp, to_hand = hp - tg;
-      const uint32_t minus_mT = 0u - mT, to_dead = kDeadPlace - tg;
+      // hand slot:   mask += chop bits | merged contents;   place: hand -> square when dropped
+      // square slot: picked up (square -> hand) or merged away (mask 0, dead place)
+      const uint32_t dmaskH = imad(c, mH * 16u, m * mT), dplaceH = d * (tg - hp);
+      const uint32_t dmaskT = m * (0u - mT), dplaceT = imad(p, hp - tg, m * (kDeadPlace - tg));
 #pragma unroll
       for (int k = 0; k < NOBJ; k++) {
-        const bool isH = e.place[k] == hp, isT = e.place[k] == tg;
-        if (isH) {
-          e.mask[k] = c * chop_bits + e.mask[k];
-          e.mask[k] = m * mT + e.mask[k];
-          e.place[k] = d * to_square + e.place[k];
-        }
-        if (isT) {
-          e.mask[k] = m * minus_mT + e.mask[k];
-          e.place[k] = p * to_hand + e.place[k];
-          e.place[k] = m * to_dead + e.place[k];
-        }
+        e.mask[k] = imad(fH[k], dmaskH, e.mask[k]);
+        e.mask[k] = imad(fT[k], dmaskT, e.mask[k]);
+        e.place[k] = imad(fH[k], dplaceH, e.place[k]);
+        e.place[k] = imad(fT[k], dplaceT, e.place[k]);
       }
     }
   }
