@@ -177,6 +177,10 @@ __device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], cons
         mH = imad(fH[k], e.mask[k], mH);
         mT = imad(fT[k], e.mask[k], mT);
       }
+      // at most one object is in a hand or lies on a counter / cutboard; a Delivery square may hold
+      // several (interact.py:38), whose masks add up here - keep the table index in range (the
+      // outcome on a Delivery square does not depend on what lies there, and m = p = 0 below)
+      mT &= 0x7Fu;
       const uint32_t idx = S.hprops[mH] + S.tprops[mT] + kind8[i];
       const uint32_t c = S.chop[idx], m = S.merge[idx], d = S.drop[idx], p = S.pick[idx];
       delivered += S.delivered[idx];

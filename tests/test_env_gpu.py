@@ -188,3 +188,28 @@ def test_empty_and_ragged_sizes():
     lv = gcb._lib.parse_level(gcb.levels.level_text("full-divider_tl"), 100)
     import ctypes as C
     assert lib.gc_env_step(C.byref(lv), 1, None, C.c_void_p(16), C.c_void_p(16), None, None, None, None, 0, 2, None) == 0
+
+
+def test_delivery_square_holding_several_objects():
+    """Injected state: two dishes already lie on the Delivery square and agent-1 faces it with a third
+    one (more than the reference levels can produce, but the transition is defined): every joint
+    action must match the oracle."""
+    level, n_agents = "partial-divider_tl", 2
+    text = gcb.levels.level_text(level)
+    lv = O.parse_level(text, 100)
+    deliv, dish_l = 3 * 8 + 0, 2 | 8 | 32
+    full = 0x7F  # every content bit: two of them overflow a 7-bit sum (the table-driven kernel adds masks)
+    slots = [full | deliv << 7, full | deliv << 7, dish_l | 1 << 13, 8 | (6 * 8 + 5) << 7]  # goals stay open
+    w = np.array([(3 * 8 + 1) | (1 * 8 + 4) << 6 | 5 << 24, slots[0] | slots[1] << 16, slots[2] | slots[3] << 16,
+                  0xE000E000], dtype=np.uint32)
+    acts = np.array([[a, b] for a in range(5) for b in range(5)], dtype=np.uint8)
+    ost = np.tile(w, (25, 1))
+    kb = gcb.KitchenBatch(level, n_agents, 25, 100)
+    kb.state.copy_(torch.from_numpy(ost.view(np.int32)).to(kb.device))
+    for rep in range(3):
+        kb.step(torch.from_numpy(acts).to(kb.device))
+        rd, _ = O.step_batch(lv, ost, acts, n_agents)
+        assert (_u32(kb.state) == ost).all(), rep
+        assert (kb.reward_done.cpu().numpy() == rd).all(), rep
+    delivered = [(int(s[1]) & 0xFFFF, int(s[1]) >> 16, int(s[2]) & 0xFFFF) for s in ost]
+    assert any(all((x >> 7) & 63 == deliv and (x >> 13) == 0 for x in d) for d in delivered)  # the third dish got there
