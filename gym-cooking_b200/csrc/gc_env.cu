@@ -255,22 +255,26 @@ struct StepLutParams {
 #ifndef GC_LUT_MIN_CTAS
 #define GC_LUT_MIN_CTAS 4
 #endif
+#ifndef GC_LUT_THREADS
+#define GC_LUT_THREADS 256
+#endif
+constexpr int kLutThreads = GC_LUT_THREADS;  // block size of the single-level table-driven step kernel
 template <int NA, int NOBJ>
-__global__ void __launch_bounds__(kThreads, GC_LUT_MIN_CTAS)
+__global__ void __launch_bounds__(kLutThreads, GC_LUT_MIN_CTAS)
 step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ state,
                 const uint8_t* __restrict__ actions, uint8_t* __restrict__ reward_done,
                 unsigned long long* __restrict__ hash, uint32_t* __restrict__ collisions,
                 uint8_t* __restrict__ executed, int64_t n) {
   __shared__ __align__(16) gclut::Tables T;
-  __shared__ __align__(16) uint4 s_stage[kThreads];  // each thread's NEXT state, filled by cp.async
+  __shared__ __align__(16) uint4 s_stage[kLutThreads];  // each thread's NEXT state, filled by cp.async
   // Persistent CTAs: the 5.9 KB of tables are loaded once per CTA and reused for every env the CTA
   // walks (a one-env-per-thread grid spent ~20 % of its instructions refilling them).  DRAM latency
   // is hidden by software pipelining WITHOUT registers: while a thread computes env i, the 16-byte
   // state of its next env streams into its private shared-memory slot with cp.async (LDGSTS), and
   // the next action word waits in one register.  (A register-prefetch variant pushed the kernel
   // over 32 registers / 100 % occupancy and lost more than it won.)
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * kLutThreads;
+  int64_t i = (int64_t)blockIdx.x * kLutThreads + threadIdx.x;
   const uint32_t slot = (uint32_t)__cvta_generic_to_shared(&s_stage[threadIdx.x]);
   uint32_t a_next[NA];
 #pragma unroll
@@ -332,7 +336,7 @@ struct MultiShared {
 };
 
 template <int NA, int NOBJ>
-__global__ void __launch_bounds__(kThreads, GC_LUT_MIN_CTAS)
+__global__ void __launch_bounds__(kThreads, 4)
 step_lut_multi_kernel(const __grid_constant__ GcLevelsDev P, int n_levels, const uint8_t* __restrict__ level_id,
                       uint4* __restrict__ state, const uint8_t* __restrict__ actions,
                       uint8_t* __restrict__ reward_done, unsigned long long* __restrict__ hash,
@@ -450,7 +454,7 @@ void fill_move_table(const GcLevelDev& L, gclut::MoveTable* mv) {
 
 // persistent grid of the table-driven kernel: GC_LUT_CTAS_PER_SM (default 4 = what fits at 53
 // registers without spilling; measured faster than 6 or 8 CTAs of 40 / 32 registers with spills)
-inline unsigned lut_grid(int64_t n) {
+inline unsigned lut_grid(int64_t n, int threads = kThreads) {
   static int sms = 0, per_sm = 0;
   if (!sms) {
     int dev = 0;
@@ -461,8 +465,9 @@ inline unsigned lut_grid(int64_t n) {
     per_sm = e ? atoi(e) : 4;
     if (per_sm < 1 || per_sm > 8) per_sm = 4;
   }
-  const unsigned full = grid_for(n), cap = (unsigned)(sms * per_sm);
-  return full < cap ? full : cap;
+  const unsigned full = (unsigned)((n + threads - 1) / threads);
+  const unsigned cap = (unsigned)(sms * per_sm * kThreads / threads);  // per_sm counts 256-thread CTAs
+  return full < cap ? full : (cap ? cap : 1u);
 }
 
 inline bool use_generic_step() {
@@ -486,8 +491,8 @@ int launch_step(bool multi, int n_levels, const GcLevelsDev& lv, const uint8_t* 
     fill_move_table(P.lv, &P.mv);
     static const bool pdl = getenv("GC_STEP_NO_PDL") == nullptr;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(lut_grid(n));
-    cfg.blockDim = dim3(kThreads);
+    cfg.gridDim = dim3(lut_grid(n, kLutThreads));
+    cfg.blockDim = dim3(kLutThreads);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
