@@ -33,6 +33,25 @@ __device__ __forceinline__ void load_actions(const uint8_t* __restrict__ actions
   }
 }
 
+// the same in two halves: the global load (issued one iteration ahead by the persistent kernels, kept
+// as the raw word so that nothing waits on it early) and the byte extraction at the point of use
+template <int NA>
+__device__ __forceinline__ uint32_t load_actions_raw(const uint8_t* __restrict__ actions, int64_t i) {
+  if constexpr (NA == 1) {
+    return actions[i];
+  } else if constexpr (NA == 2) {
+    return reinterpret_cast<const uint16_t*>(actions)[i];
+  } else if constexpr (NA == 4) {
+    return reinterpret_cast<const uint32_t*>(actions)[i];
+  } else {
+    return (uint32_t)actions[i * 3] | ((uint32_t)actions[i * 3 + 1] << 8) | ((uint32_t)actions[i * 3 + 2] << 16);
+  }
+}
+template <int NA>
+__device__ __forceinline__ void unpack_actions(uint32_t v, uint32_t (&a)[NA]) {
+#pragma unroll
+  for (int k = 0; k < NA; k++) a[k] = (v >> (8 * k)) & 0xffu;
+}
 template <int NA>
 __device__ __forceinline__ void store_actions(uint8_t* __restrict__ out, int64_t i, const uint32_t (&a)[NA]) {
 #pragma unroll
@@ -276,9 +295,7 @@ step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ sta
   const int64_t stride = (int64_t)gridDim.x * kLutThreads;
   int64_t i = (int64_t)blockIdx.x * kLutThreads + threadIdx.x;
   const uint32_t slot = (uint32_t)__cvta_generic_to_shared(&s_stage[threadIdx.x]);
-  uint32_t a_next[NA];
-#pragma unroll
-  for (int k = 0; k < NA; k++) a_next[k] = 4u;
+  uint32_t a_next = 0x04040404u;  // raw action word of the next env (all "stay")
   // Programmatic dependent launch: the tables do not depend on earlier kernels, so this grid may
   // start (and fill them) while the previous kernel of the stream drains; everything that can
   // have been written by it (state, actions) is read only after griddepcontrol.wait.
@@ -287,7 +304,7 @@ step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ sta
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (i < n) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + i) : "memory");
-    load_actions<NA>(actions, i, a_next);
+    a_next = load_actions_raw<NA>(actions, i);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   __syncthreads();
@@ -296,12 +313,11 @@ step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ sta
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     uint4 s = s_stage[threadIdx.x];  // written by this thread's own cp.async: no CTA barrier needed
     uint32_t act[NA];
-#pragma unroll
-    for (int k = 0; k < NA; k++) act[k] = a_next[k];
+    unpack_actions<NA>(a_next, act);
     const int64_t inext = i + stride;
     if (inext < n) {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + inext) : "memory");
-      load_actions<NA>(actions, inext, a_next);
+      a_next = load_actions_raw<NA>(actions, inext);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     bool done, success;
@@ -359,12 +375,10 @@ step_lut_multi_kernel(const __grid_constant__ GcLevelsDev P, int n_levels, const
     for (int l = 0; l < n_levels; l++) gclut::fill_move_table_dev(S.lv[l], s_mv + l * gclut::kMoveBytes);
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  uint32_t a_next[NA], l_next = 0;
-#pragma unroll
-  for (int k = 0; k < NA; k++) a_next[k] = 4u;
+  uint32_t a_next = 0x04040404u, l_next = 0;
   if (i < n) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + i) : "memory");
-    load_actions<NA>(actions, i, a_next);
+    a_next = load_actions_raw<NA>(actions, i);
     l_next = level_id[i];
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -373,13 +387,12 @@ step_lut_multi_kernel(const __grid_constant__ GcLevelsDev P, int n_levels, const
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     uint4 s = s_stage[threadIdx.x];
     uint32_t act[NA];
-#pragma unroll
-    for (int k = 0; k < NA; k++) act[k] = a_next[k];
+    unpack_actions<NA>(a_next, act);
     const uint32_t lvl = min(l_next, (uint32_t)(n_levels - 1));
     const int64_t inext = i + stride;
     if (inext < n) {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + inext) : "memory");
-      load_actions<NA>(actions, inext, a_next);
+      a_next = load_actions_raw<NA>(actions, inext);
       l_next = level_id[inext];
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
