@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kLutThreads, GC_LUT_MIN_CTAS)
 step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ state,
                 const uint8_t* __restrict__ actions, uint8_t* __restrict__ reward_done,
                 unsigned long long* __restrict__ hash, uint32_t* __restrict__ collisions,
-                uint8_t* __restrict__ executed, int64_t n) {
+                uint8_t* __restrict__ executed, uint32_t n) {  // n < 2^31: the host splits larger batches
   __shared__ __align__(16) gclut::Tables T;
   __shared__ __align__(16) uint4 s_stage[kLutThreads];  // each thread's NEXT state, filled by cp.async
   // Persistent CTAs: the 5.9 KB of tables are loaded once per CTA and reused for every env the CTA
@@ -292,8 +292,8 @@ step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ sta
   // state of its next env streams into its private shared-memory slot with cp.async (LDGSTS), and
   // the next action word waits in one register.  (A register-prefetch variant pushed the kernel
   // over 32 registers / 100 % occupancy and lost more than it won.)
-  const int64_t stride = (int64_t)gridDim.x * kLutThreads;
-  int64_t i = (int64_t)blockIdx.x * kLutThreads + threadIdx.x;
+  const uint32_t stride = gridDim.x * kLutThreads;  // 32-bit indices: one IMAD.WIDE per address
+  uint32_t i = blockIdx.x * kLutThreads + threadIdx.x;
   const uint32_t slot = (uint32_t)__cvta_generic_to_shared(&s_stage[threadIdx.x]);
   uint32_t a_next = 0x04040404u;  // raw action word of the next env (all "stay")
   // Programmatic dependent launch: the tables do not depend on earlier kernels, so this grid may
@@ -314,7 +314,7 @@ step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ sta
     uint4 s = s_stage[threadIdx.x];  // written by this thread's own cp.async: no CTA barrier needed
     uint32_t act[NA];
     unpack_actions<NA>(a_next, act);
-    const int64_t inext = i + stride;
+    const uint32_t inext = i + stride;
     if (inext < n) {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + inext) : "memory");
       a_next = load_actions_raw<NA>(actions, inext);
@@ -356,12 +356,12 @@ __global__ void __launch_bounds__(kThreads, 4)
 step_lut_multi_kernel(const __grid_constant__ GcLevelsDev P, int n_levels, const uint8_t* __restrict__ level_id,
                       uint4* __restrict__ state, const uint8_t* __restrict__ actions,
                       uint8_t* __restrict__ reward_done, unsigned long long* __restrict__ hash,
-                      uint32_t* __restrict__ collisions, uint8_t* __restrict__ executed, int64_t n) {
+                      uint32_t* __restrict__ collisions, uint8_t* __restrict__ executed, uint32_t n) {
   __shared__ __align__(16) MultiShared S;
   __shared__ __align__(16) uint4 s_stage[kThreads];
   extern __shared__ __align__(16) uint8_t s_mv[];  // [n_levels][kMoveBytes]
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const uint32_t stride = gridDim.x * kThreads;
+  uint32_t i = blockIdx.x * kThreads + threadIdx.x;
   const uint32_t slot = (uint32_t)__cvta_generic_to_shared(&s_stage[threadIdx.x]);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   {
@@ -389,7 +389,7 @@ step_lut_multi_kernel(const __grid_constant__ GcLevelsDev P, int n_levels, const
     uint32_t act[NA];
     unpack_actions<NA>(a_next, act);
     const uint32_t lvl = min(l_next, (uint32_t)(n_levels - 1));
-    const int64_t inext = i + stride;
+    const uint32_t inext = i + stride;
     if (inext < n) {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + inext) : "memory");
       a_next = load_actions_raw<NA>(actions, inext);
@@ -512,8 +512,16 @@ int launch_step(bool multi, int n_levels, const GcLevelsDev& lv, const uint8_t* 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    const cudaError_t err = cudaLaunchKernelEx(&cfg, step_lut_kernel<NA, NOBJ>, P, s4, actions, rd, h, coll, executed, n);
-    if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step: launch failed: %s", cudaGetErrorString(err));
+    // the kernel indexes with 32 bits: batches beyond 2^30 envs go in slices
+    const int64_t slice = (int64_t)1 << 30;
+    for (int64_t lo = 0; lo < n; lo += slice) {
+      const int64_t m = n - lo < slice ? n - lo : slice;
+      cfg.gridDim = dim3(lut_grid(m, kLutThreads));
+      const cudaError_t err = cudaLaunchKernelEx(
+          &cfg, step_lut_kernel<NA, NOBJ>, P, s4 + lo, actions + lo * NA, rd ? rd + lo : nullptr, h ? h + lo : nullptr,
+          coll ? coll + lo : nullptr, executed ? executed + lo * NA : nullptr, (uint32_t)m);
+      if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step: launch failed: %s", cudaGetErrorString(err));
+    }
     return gc_check_launch("gc_env_step");
   }
   if (multi && !use_generic_step()) {
@@ -528,9 +536,16 @@ int launch_step(bool multi, int n_levels, const GcLevelsDev& lv, const uint8_t* 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    const cudaError_t err = cudaLaunchKernelEx(&cfg, step_lut_multi_kernel<NA, NOBJ>, lv, n_levels, level_id, s4, actions,
-                                               rd, h, coll, executed, n);
-    if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step: launch failed: %s", cudaGetErrorString(err));
+    const int64_t slice = (int64_t)1 << 30;
+    for (int64_t lo = 0; lo < n; lo += slice) {
+      const int64_t m = n - lo < slice ? n - lo : slice;
+      cfg.gridDim = dim3(lut_grid(m));
+      const cudaError_t err = cudaLaunchKernelEx(
+          &cfg, step_lut_multi_kernel<NA, NOBJ>, lv, n_levels, level_id + lo, s4 + lo, actions + lo * NA,
+          rd ? rd + lo : nullptr, h ? h + lo : nullptr, coll ? coll + lo : nullptr,
+          executed ? executed + lo * NA : nullptr, (uint32_t)m);
+      if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step: launch failed: %s", cudaGetErrorString(err));
+    }
     return gc_check_launch("gc_env_step");
   }
   if (multi)
