@@ -180,16 +180,20 @@ def run_ours(args):
     actions = [kb.random_actions(HORIZON, env0=env0 + r * N_ENVS, seed=SEED) for r, kb in enumerate(ring)]
     local_t = [0] * RING
     launches = 0
+    # per-step action views made once: at ~12 us per kernel the Python side of a step must stay well
+    # below that, or the loop measures the interpreter instead of the GPU
+    views = [[actions[r][t] for t in range(HORIZON)] for r in range(RING)]
 
     def do_step(k):
         nonlocal launches
         r = k % RING
-        if local_t[r] == HORIZON:  # every env of this batch has timed out: start new episodes
+        t = local_t[r]
+        if t == HORIZON:  # every env of this batch has timed out: start new episodes
             ring[r].reset()
-            local_t[r] = 0
+            t = 0
             launches += 1  # gc_env_reset (the reward/done memset is torch's, not counted)
-        ring[r].step(actions[r][local_t[r]])
-        local_t[r] += 1
+        ring[r].step(views[r][t])
+        local_t[r] = t + 1
         launches += 1
 
     k = 0

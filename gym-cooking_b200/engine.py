@@ -76,7 +76,11 @@ class KitchenBatch:
 
     # -- marshalling helpers ------------------------------------------------------------
     def _lv(self):
-        return C.cast(self._level_arr, C.POINTER(_lib.Level))
+        lv = self.__dict__.get("_lv_cast")
+        if lv is None or self.__dict__.get("_lv_cast_of") is not self._level_arr:
+            lv = self._lv_cast = C.cast(self._level_arr, C.POINTER(_lib.Level))
+            self._lv_cast_of = self._level_arr
+        return lv
 
     def _stream(self):
         return _lib.stream_ptr(self.device)
@@ -95,11 +99,26 @@ class KitchenBatch:
         """actions: uint8[N][num_agents] CUDA tensor, values 0..4.  In place on self.state."""
         if actions.shape != (self.num_envs, self.num_agents):
             raise ValueError("actions must be [%d, %d]" % (self.num_envs, self.num_agents))
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.gc_env_step(
-                self._lv(), self.n_levels, _lib.ptr(self.level_id), _lib.ptr(self.state),
-                _lib.ptr(actions, torch.uint8), _lib.ptr(self.reward_done), _lib.ptr(hash_out),
-                _lib.ptr(self.collisions), _lib.ptr(executed_out), self.num_envs, self.num_agents, self._stream()))
+        if actions.dtype is not torch.uint8 or not actions.is_cuda or not actions.is_contiguous():
+            raise _lib.GcError("actions must be a contiguous uint8 CUDA tensor: libgymcook has no CPU path")
+        # hot call: at 2^20 envs the kernel takes ~12 us, so the marshalling is kept to pointer reads
+        # (the device guard is entered only when this batch is not on the current device)
+        dev = self.device
+        guard = None
+        if torch.cuda.current_device() != dev.index:
+            guard = torch.cuda.device(dev)
+            guard.__enter__()
+        try:
+            rc = self.lib.gc_env_step(
+                self._lv(), self.n_levels, _lib.ptr(self.level_id), self.state.data_ptr(), actions.data_ptr(),
+                self.reward_done.data_ptr(), _lib.ptr(hash_out),
+                self.collisions.data_ptr() if self.collisions is not None else None, _lib.ptr(executed_out),
+                self.num_envs, self.num_agents, torch.cuda.current_stream(dev).cuda_stream)
+        finally:
+            if guard is not None:
+                guard.__exit__(None, None, None)
+        if rc != 0:
+            _lib.check(rc)
         return self.reward_done
 
     def step_range(self, lo, hi, actions, stream=None):
