@@ -28,6 +28,8 @@ int gc_check_launch(const char* what) {
 }
 
 int gc_require_device() {
+  static bool seen = false;  // a positive answer does not change; a negative one is asked again
+  if (seen) return GC_OK;
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n < 1) {
@@ -35,6 +37,7 @@ int gc_require_device() {
     return gc_fail(GC_E_CUDA, "no usable CUDA device (%s); libgymcook has no CPU fallback",
                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
   }
+  seen = true;
   return GC_OK;
 }
 
