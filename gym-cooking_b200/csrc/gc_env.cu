@@ -626,6 +626,26 @@ int gc_env_step(const gc_level* levels, int n_levels, const uint8_t* level_id, u
   return gc_fail(GC_E_ARG, "gc_env_step: n_agents must be 1..4");
 }
 
+int gc_env_step_host(const gc_level* levels, int n_levels, const uint8_t* level_id, uint32_t* state,
+                     const uint8_t* actions_host, uint8_t* actions_dev, uint8_t* reward_done_dev,
+                     uint8_t* reward_done_host, uint32_t* collisions, int64_t n, int n_agents, void* stream) {
+  if (!actions_host || !actions_dev || !reward_done_dev || !reward_done_host)
+    return gc_fail(GC_E_ARG, "gc_env_step_host: null host/device action or reward_done buffer");
+  if (n < 0 || n_agents < 1 || n_agents > GC_MAX_AGENTS) return gc_fail(GC_E_ARG, "gc_env_step_host: bad n / n_agents");
+  if (n == 0) return GC_OK;
+  if (int rc = gc_require_device()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyAsync(actions_dev, actions_host, (size_t)n * n_agents, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step_host: copy in failed: %s", cudaGetErrorString(e));
+  if (int rc = gc_env_step(levels, n_levels, level_id, state, actions_dev, reward_done_dev, nullptr, collisions, nullptr,
+                           n, n_agents, stream))
+    return rc;
+  e = cudaMemcpyAsync(reward_done_host, reward_done_dev, (size_t)n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step_host: copy out failed: %s", cudaGetErrorString(e));
+  return GC_OK;
+}
+
 int gc_env_rollout(const gc_level* levels, int n_levels, const uint8_t* level_id, uint32_t* state,
                    uint8_t* reward_done, uint64_t* hash_trace, uint32_t* collisions, int64_t n, int n_agents,
                    int n_steps, int t0, int64_t env0, uint64_t seed, void* stream) {

@@ -121,6 +121,30 @@ class KitchenBatch:
             _lib.check(rc)
         return self.reward_done
 
+    def step_host(self, actions_host, actions_dev, reward_done_host):
+        """gc_env_step_host: actions from a (pinned) host tensor, reward/done bytes into a pinned host
+        tensor, one library call that returns when both copies and the step are done."""
+        if actions_host.shape != (self.num_envs, self.num_agents) or actions_host.dtype is not torch.uint8 \
+                or actions_host.is_cuda or not actions_host.is_contiguous():
+            raise ValueError("actions_host must be a contiguous uint8 host tensor [%d, %d]" % (self.num_envs, self.num_agents))
+        dev = self.device
+        guard = None
+        if torch.cuda.current_device() != dev.index:
+            guard = torch.cuda.device(dev)
+            guard.__enter__()
+        try:
+            rc = self.lib.gc_env_step_host(
+                self._lv(), self.n_levels, _lib.ptr(self.level_id), self.state.data_ptr(), actions_host.data_ptr(),
+                actions_dev.data_ptr(), self.reward_done.data_ptr(), reward_done_host.data_ptr(),
+                self.collisions.data_ptr() if self.collisions is not None else None, self.num_envs, self.num_agents,
+                torch.cuda.current_stream(dev).cuda_stream)
+        finally:
+            if guard is not None:
+                guard.__exit__(None, None, None)
+        if rc != 0:
+            _lib.check(rc)
+        return reward_done_host
+
     def step_range(self, lo, hi, actions, stream=None):
         """Step only envs [lo, hi) with actions uint8[hi-lo][num_agents], on `stream` (a
         torch.cuda.Stream; default: current).  Lets a caller pipeline host copies of one chunk

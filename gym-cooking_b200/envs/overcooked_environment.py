@@ -290,7 +290,6 @@ class OvercookedEnvironment(_ReferenceSurface):
     # 202 us vs 99 us per 2^20-env step - scripts/e2e_probe.py - so the default is one stream)
     PIPELINE_CHUNKS = 1
     PIPELINE_MIN_ENVS = 1 << 16
-    H2D_PIECE_BYTES = 1 << 30  # one copy; splitting into 128 KB-2 MB pieces measured no faster in the full step
 
     def _step_batched(self, acts):
         kb = self._kb
@@ -301,14 +300,15 @@ class OvercookedEnvironment(_ReferenceSurface):
             rd.copy_(kb.reward_done, non_blocking=True)
             torch.cuda.current_stream(kb.device).synchronize()
         elif self.PIPELINE_CHUNKS <= 1 or n < self.PIPELINE_MIN_ENVS or kb.n_levels > 1:
-            # H2D (async when `acts` is pinned), optionally in pieces (scripts/e2e_probe2.py)
-            flat_src, flat_dst = acts.view(-1), self._dev_actions.view(-1)
-            total, piece = flat_src.numel(), self.H2D_PIECE_BYTES
-            for lo in range(0, total, piece):
-                flat_dst[lo:lo + piece].copy_(flat_src[lo:lo + piece], non_blocking=True)
-            kb.step(self._dev_actions)
-            rd.copy_(kb.reward_done, non_blocking=True)        # D2H of the step's result
-            torch.cuda.current_stream(kb.device).synchronize()
+            # host actions in, reward/done bytes out: one library call (gc_env_step_host) that copies
+            # in (async when `acts` is pinned), steps, copies out and waits for the stream
+            if acts.dtype is torch.uint8 and acts.is_contiguous() and acts.shape == (n, self.num_agents):
+                kb.step_host(acts, self._dev_actions, rd)
+            else:
+                self._dev_actions.copy_(acts, non_blocking=True)
+                kb.step(self._dev_actions)
+                rd.copy_(kb.reward_done, non_blocking=True)
+                torch.cuda.current_stream(kb.device).synchronize()
         else:
             if self._streams is None:
                 self._streams = [torch.cuda.Stream(device=kb.device) for _ in range(self.PIPELINE_CHUNKS)]

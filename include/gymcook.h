@@ -161,6 +161,18 @@ int gc_env_step(const gc_level* levels, int n_levels, const uint8_t* level_id /*
                 uint8_t* reward_done, uint64_t* hash, uint32_t* collisions, uint8_t* executed,
                 int64_t n, int n_agents, void* stream);
 
+/* step() for a caller whose actions and results live in HOST memory (the gym-style call:
+ * `obs, reward, done, info = env.step(actions)`, env:255-306): copies `actions_host`
+ * (uint8[n][n_agents], pinned for an asynchronous copy) into `actions_dev`, runs gc_env_step,
+ * copies the reward/done bytes back into `reward_done_host` and waits for the stream - one call
+ * instead of three stream operations plus a synchronisation on the caller's side.  The state
+ * stays on the device.  `actions_dev` / `reward_done_dev` are caller-owned device buffers of
+ * n * n_agents / n bytes. */
+int gc_env_step_host(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
+                     uint32_t* state /*device*/, const uint8_t* actions_host, uint8_t* actions_dev,
+                     uint8_t* reward_done_dev, uint8_t* reward_done_host, uint32_t* collisions /*device*/,
+                     int64_t n, int n_agents, void* stream);
+
 /* rollout(): `n_steps` fused transitions with uniform-random actions generated in-kernel:
  * action[t][env][agent] = philox4x32-10(key=(seed_lo,seed_hi), ctr=(t0+t, env0+env, agent, 0)).x % 5
  * (SURVEY.md section 8d cfg-2).  State stays in registers between steps.
