@@ -55,6 +55,7 @@ constexpr int kRing = 64;                    // A* keys may jump by an edge (<= 
 constexpr uint32_t kRingCap = 16 * 1024;     // entries per key bucket
 constexpr uint32_t kPool = 1u << 20;         // predecessor-list nodes
 constexpr uint32_t kGoalCap = 4096;
+constexpr uint32_t kTouchedCap = kMaxStates2 + 8192;
 constexpr uint32_t kNil = 0xFFFFFFFFu;
 constexpr int kSlack = 12;                   // first pass explores keys up to V* + 1.2, then widens by
 constexpr int kSlackStep = 12;               // 1.2 per round while offered actions remain unproven,
@@ -70,6 +71,7 @@ struct Arena2 {
   uint32_t bbucket[kBuckets][kRingCap];  // backward pass: slots by cost-to-go
   uint2 pool[kPool];        // .x = predecessor slot | (edge cost - 10) << 30, .y = next node
   uint32_t goals[kGoalCap];
+  uint32_t touched[kTouchedCap];  // slots inserted by the current search: cleaning them beats clearing 2^17 slots
 };
 
 // per-CTA scratch layout
@@ -451,7 +453,9 @@ __device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* 
     const unsigned long long old = atomicCAS(&A->keys[h], kEmpty, k);
     if (old == kEmpty) {
       A->states[h] = pack_state(p);
-      if (atomicAdd(n_states, 1u) >= max_states) atomicExch(over, 1);
+      const uint32_t idx = atomicAdd(n_states, 1u);
+      if (idx < kTouchedCap) A->touched[idx] = h;
+      if (idx >= max_states) atomicExch(over, 1);
     } else if (old != k) {
       continue;
     }
@@ -498,6 +502,15 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
   __shared__ __align__(16) Tables T;
   Arena2* A = arenas + blockIdx.x;
   const int64_t n_prob = n * pairs.n;
+  auto clear_all = [&]() {
+    for (uint32_t k = threadIdx.x; k < kSlots2; k += kTreeThreads) {
+      A->keys[k] = kEmpty;
+      A->gcost[k] = kInfCost;
+      A->val[k] = kInfCost;
+      A->head[k] = kNil;
+    }
+  };
+  clear_all();  // once per CTA; every search cleans up the slots it inserted
   for (int64_t prob = blockIdx.x; prob < n_prob; prob += gridDim.x) {
     const int64_t env = prob / pairs.n;
     const int pi = (int)(prob - env * pairs.n);
@@ -532,14 +545,7 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
       if (threadIdx.x == 0) todo[prob] = 0;
       continue;
     }
-    fill_tables(w, &T);
-    for (uint32_t k = threadIdx.x; k < kSlots2; k += kTreeThreads) {
-      A->keys[k] = kEmpty;
-      A->gcost[k] = kInfCost;
-      A->val[k] = kInfCost;
-      A->head[k] = kNil;
-    }
-    __syncthreads();
+    fill_tables(w, &T);  // (ends with a barrier; the table is clean: see the end of the search)
     if (threadIdx.x == 0) {
       relax2(w, &T, A, bcount, &n_states, &n_pool, &over, start, 0u, 0u, kNil, 0u, max_states);
       s_f0 = n_pool;
@@ -684,6 +690,18 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
     for (uint32_t i = threadIdx.x; i < min(n_goals, kGoalCap); i += kTreeThreads) A->val[A->goals[i]] = 0u;
     __syncthreads();
     }  // widening loop
+    __syncthreads();
+    if (n_states <= kTouchedCap) {
+      for (uint32_t i = threadIdx.x; i < n_states; i += kTreeThreads) {
+        const uint32_t h = A->touched[i];
+        A->keys[h] = kEmpty;
+        A->gcost[h] = kInfCost;
+        A->val[h] = kInfCost;
+        A->head[h] = kNil;
+      }
+    } else {
+      clear_all();
+    }
   }
 }
 
