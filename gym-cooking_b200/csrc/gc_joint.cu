@@ -45,7 +45,13 @@ enum { ST_OK = 0, ST_UNREACHABLE = 2, ST_BUDGET = 3, ST_UNSUPPORTED = 4 };
 
 // tree search (one per problem)
 constexpr uint32_t kSlots2 = 1u << 17;
-constexpr uint32_t kMaxStates2 = 96 * 1024;
+#ifndef GC_JOINT_MAX_STATES
+#define GC_JOINT_MAX_STATES (96 * 1024)
+#endif
+#ifndef GC_JOINT_MAX_SLACK
+#define GC_JOINT_MAX_SLACK 48
+#endif
+constexpr uint32_t kMaxStates2 = GC_JOINT_MAX_STATES;
 constexpr int64_t kWideProblems = 32 * 1024;
 // one search per CTA: large batches run 4 CTAs of 128 threads per SM (throughput); small ones
 // (the delegation loop solving the few states it has not seen yet) run 2 CTAs of 512 threads so
@@ -59,7 +65,7 @@ constexpr uint32_t kTouchedCap = kMaxStates2 + 8192;
 constexpr uint32_t kNil = 0xFFFFFFFFu;
 constexpr int kSlack = 12;                   // first pass explores keys up to V* + 1.2, then widens by
 constexpr int kSlackStep = 12;               // 1.2 per round while offered actions remain unproven,
-constexpr int kMaxSlack = 48;                // up to V* + 4.8; what is still open goes to the per-action search
+constexpr int kMaxSlack = GC_JOINT_MAX_SLACK;                // up to V* + 4.8; what is still open goes to the per-action search
 
 struct Arena2 {
   unsigned long long keys[kSlots2];
@@ -679,7 +685,12 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
     __syncthreads();
     const uint32_t open_actions = s_todo;
     if (open_actions == 0u || complete || over || slack >= kMaxSlack || limit >= kMaxCost) {
-      if (threadIdx.x == 0) todo[prob] = open_actions;
+      if (threadIdx.x == 0) {
+        // a search that outgrew the budget keeps what it proved and reports the rest as unknown: the
+        // per-action searches explore the same region with half the budget and would burn it 24 times
+        if (over && open_actions) atomicOr(&flags[prob], 1);
+        todo[prob] = over ? 0u : open_actions;
+      }
       break;
     }
     // widen: the forward pass resumes where it stopped; cost-to-go values are rebuilt from the goals
