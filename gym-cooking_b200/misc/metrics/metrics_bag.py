@@ -11,56 +11,57 @@ import os
 import pickle
 
 
+# per-agent series: key -> how one RealAgent contributes to it at a step (metrics_bag.py:44-51)
+AGENT_SERIES = (
+    ("states", lambda a: copy.copy(a.location)),
+    ("holding", lambda a: a.get_holding()),
+    ("actions", lambda a: a.action),
+    ("subtasks", lambda a: a.subtask),
+    ("subtask_agents", lambda a: a.subtask_agent_names),
+    ("incomplete_subtasks", lambda a: a.incomplete_subtasks),
+)
+
+
 class Bag:
     def __init__(self, arglist, filename, directory="misc/metrics/pickles/"):
+        self.arglist, self.filename, self.directory = arglist, filename, directory
         self.data = {}
-        self.arglist = arglist
-        self.directory = directory
-        self.filename = filename
         self.set_general()
 
     def set_general(self):  # :13-33
-        n = self.arglist.num_agents
-        self.data["level"] = self.arglist.level
-        self.data["num_agents"] = n
-        self.data["profiling"] = {info: [] for info in ["Delegation", "Navigation", "Total"]}
-        self.data["num_completed_subtasks"] = []
-        for i in range(1, 5):
+        names = ["agent-%d" % (i + 1) for i in range(self.arglist.num_agents)]
+        self.data.update(level=self.arglist.level, num_agents=self.arglist.num_agents, num_completed_subtasks=[],
+                         profiling={k: [] for k in ("Delegation", "Navigation", "Total")})
+        for i in range(1, 5):  # model types of the ablation runs
             model = getattr(self.arglist, "model%d" % i, None)
             if model is not None:
                 self.data["agent-%d" % i] = model
-        for info in ["states", "actions", "subtasks", "subtask_agents", "bayes", "holding", "incomplete_subtasks"]:
-            self.data[info] = {"agent-%d" % (i + 1): ({} if info == "bayes" else []) for i in range(n)}
+        for key, _ in AGENT_SERIES:
+            self.data[key] = {nm: [] for nm in names}
+        self.data["bayes"] = {nm: {} for nm in names}
 
     def set_recipe(self, recipe_subtasks):  # :36-38
-        self.data["all_subtasks"] = recipe_subtasks
-        self.data["num_total_subtasks"] = len(recipe_subtasks)
+        self.data.update(all_subtasks=recipe_subtasks, num_total_subtasks=len(recipe_subtasks))
 
     def set_collisions(self, collisions):  # :40-41
         self.data["collisions"] = collisions
 
     def add_status(self, cur_time, real_agents):  # :44-61
-        for a in real_agents:
-            self.data["states"][a.name].append(copy.copy(a.location))
-            self.data["holding"][a.name].append(a.get_holding())
-            self.data["actions"][a.name].append(a.action)
-            self.data["subtasks"][a.name].append(a.subtask)
-            self.data["subtask_agents"][a.name].append(a.subtask_agent_names)
-            self.data["incomplete_subtasks"][a.name].append(a.incomplete_subtasks)
-            for task_combo, p in a.delegator.probs.get_list():
-                self.data["bayes"][a.name].setdefault(cur_time, []).append((task_combo, p))
-        incomplete = set(self.data["all_subtasks"])
-        for a in real_agents:
-            incomplete &= set(a.incomplete_subtasks)
-        self.data["num_completed_subtasks"].append(self.data["num_total_subtasks"] - len(incomplete))
+        still_open = set(self.data["all_subtasks"])
+        for agent in real_agents:
+            for key, value_of in AGENT_SERIES:
+                self.data[key][agent.name].append(value_of(agent))
+            beliefs = self.data["bayes"][agent.name].setdefault(cur_time, []) if agent.delegator.probs.get_list() else None
+            for alloc, prob in agent.delegator.probs.get_list():
+                beliefs.append((alloc, prob))
+            still_open &= set(agent.incomplete_subtasks)  # open = what EVERY agent still believes open
+        self.data["num_completed_subtasks"].append(self.data["num_total_subtasks"] - len(still_open))
 
     def set_termination(self, termination_info, successful, save=True):  # :63-72
-        self.data["termination"] = termination_info
-        self.data["was_successful"] = successful
-        done = self.data["num_completed_subtasks"]
-        self.data["num_completed_subtasks_end"] = done[-1] if done else 0
-        if save:
-            return self.save()
+        series = self.data["num_completed_subtasks"]
+        self.data.update(termination=termination_info, was_successful=successful,
+                         num_completed_subtasks_end=series[-1] if series else 0)
+        return self.save() if save else None
 
     def save(self):
         os.makedirs(self.directory, exist_ok=True)
