@@ -175,6 +175,8 @@ class _ObserverTables:
                        dtype=np.int64)
         w = np.array([1 if model == "greedy" else len(ag) for s, ag in rows], dtype=np.uint8)
         self.row_kind, self.row_agent, self.row_pid, self.pair_w = t(kind), t(agent), t(pid), t(w)
+        self.row_kind_host, self.row_agent_host, self.row_pid_host = kind, agent, pid
+        self.row_agent2_host = np.array([ag[1] if len(ag) > 1 else ag[0] for s, ag in rows], dtype=np.int64)
         plan_lvl = 0 if model == "greedy" else lvl1  # RealAgent.plan :252-257
         self.plan_single = t(np.array([owner.pid[(s, (me,), plan_lvl)] for s in range(S)], dtype=np.int64))
         if owner.NA > 1:
@@ -327,8 +329,8 @@ class BatchedDelegation:
         tot = p.sum(1, keepdim=True)
         return torch.where(tot == 0, alive.double() / cnt, p / tot.clamp(min=1e-300))
 
-    def _bayes_update(self, T, probs, alive):
-        """bayes_update bd:1045-1072 on obs_tm1 = self.prev, actions_tm1 = self.executed"""
+    def _likelihood_rows_torch(self, T):
+        """torch restatement of gc_bd_likelihood_rows (kept as the kernel's cross-check in the tests)"""
         N, dev, me = self.N, self.device, T.me
         pv = self.prev
         ex = self.executed.long()
@@ -366,12 +368,26 @@ class BatchedDelegation:
         act_idx = rank_valid.gather(2, taken[:, :, None])[:, :, 0]
         none_idx = torch.where(taken == 4, 0, 1).clamp(max=(n_valid - 1).clamp(min=0))
         act_idx = torch.where(T.row_kind[None, :] == 0, none_idx, act_idx)
+        return qdiff.contiguous(), n_valid.to(torch.uint8).contiguous(), act_idx.to(torch.uint8).contiguous()
+
+    def _likelihood_rows(self, T):
+        """gc_bd_likelihood_rows on obs_tm1 = self.prev, actions_tm1 = self.executed"""
+        pv = self.prev
+        n_moves = pv["offered"][:, T.me].sum(-1).to(torch.uint8)
+        return planning.bd_likelihood_rows(self.cache.q, pv["ci"].contiguous(), T.row_pid_host, T.row_kind_host,
+                                           T.row_agent_host, T.row_agent2_host, self.executed, n_moves, T.me,
+                                           self.none_action_prob, UNREACHABLE_Q)
+
+    def _bayes_update(self, T, probs, alive):
+        """bayes_update bd:1045-1072 on obs_tm1 = self.prev, actions_tm1 = self.executed"""
+        N = self.N
+        qdiff, n_valid, act_idx = self._likelihood_rows(T)
         out = (probs * alive).contiguous()
         if getattr(T, "_hyp_pair_n", None) is None or T._hyp_pair_n.shape[0] != N:  # static: expand once
             T._hyp_pair_n = T.hyp_pair[None].expand(N, T.H, T.E).contiguous()
             T._pair_w_n = T.pair_w[None].expand(N, T.P).contiguous()
         planning.bd_posterior(out, alive.to(torch.uint8).contiguous(), T._hyp_pair_n, T._pair_w_n, qdiff,
-                              n_valid.to(torch.uint8).contiguous(), act_idx.to(torch.uint8).contiguous(), self.beta)
+                              n_valid, act_idx, self.beta)
         self.posterior_updates += N
         return out
 

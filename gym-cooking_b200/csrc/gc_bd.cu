@@ -13,6 +13,7 @@
 // the L values of its hypothesis with warp shuffles and the group reduces the normaliser with
 // xor-shuffles - no shared memory, no atomics.
 #include <stdlib.h>
+#include <string.h>
 
 #include "gc_device.cuh"
 #include "gc_host.h"
@@ -478,6 +479,109 @@ int launch(T* probs, const uint8_t* alive, const uint8_t* hyp_pair, const uint8_
   return gc_check_launch("gc_bd_posterior");
 }
 
+
+// ---- likelihood rows (prob_nav_actions :461-689): softmax inputs from the planner's Q rows ------
+struct RowTable {
+  int32_t pair[128];
+  uint8_t kind[128], agent[128], agent2[128];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bd_rows_kernel(const float* __restrict__ q_table, const int64_t* __restrict__ q_row, int n_pairs,
+               const __grid_constant__ RowTable rows, const uint8_t* __restrict__ executed,
+               const uint8_t* __restrict__ n_moves, int observer, T none_p, T q_cap, T* __restrict__ qdiff,
+               uint8_t* __restrict__ n_valid, uint8_t* __restrict__ act_idx, int64_t n, int P, int n_agents) {
+  const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= n * P) return;
+  const int64_t env = idx / P;
+  const int p = (int)(idx - env * P);
+  const int kind = rows.kind[p], ag = rows.agent[p];
+  T out[5] = {T(0), T(0), T(0), T(0), T(0)};
+  int nv = 0, taken_rank = 0;
+  if (kind == 0) {  // doing nothing (bd:618-641)
+    const int k = min((int)n_moves[env], 4);
+    nv = k + 1;
+    out[0] = none_p;
+    for (int a = 1; a <= k; a++) out[a] = (T(1) - none_p) / T(k);
+    taken_rank = executed[env * n_agents + ag] == 4 ? 0 : min(1, nv - 1);
+  } else {
+    const float* base = q_table + (q_row[env] * n_pairs + rows.pair[p]) * 25;
+    int taken = executed[env * n_agents + ag];
+    int stride = 1, offset = 0;  // entry a of the row is base[offset + a * stride]
+    if (kind == 2) {             // only joint actions matching the partner's executed move (bd:677-679)
+      const int ag2 = rows.agent2[p];
+      if (observer == ag) {
+        stride = 5;
+        offset = executed[env * n_agents + ag2];
+      } else {
+        offset = 5 * taken;
+        taken = executed[env * n_agents + ag2];
+      }
+    }
+    taken = min(taken, 4);
+    T qc[5];
+    bool valid[5];
+#pragma unroll
+    for (int a = 0; a < 5; a++) {
+      const float q = base[offset + a * stride];
+      valid[a] = !isnan(q) || a == taken;
+      qc[a] = (isnan(q) || isinf(q)) ? q_cap : min((T)q, q_cap);
+    }
+    T old = qc[0];
+#pragma unroll
+    for (int a = 1; a < 5; a++) old = a == taken ? qc[a] : old;
+#pragma unroll
+    for (int a = 0; a < 5; a++) {
+      if (valid[a]) {
+        if (a == taken) taken_rank = nv;
+#pragma unroll
+        for (int o = 0; o < 5; o++)
+          if (o == nv) out[o] = old - qc[a];
+        nv++;
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 5; a++) qdiff[idx * 5 + a] = out[a];
+  n_valid[idx] = (uint8_t)nv;
+  act_idx[idx] = (uint8_t)taken_rank;
+}
+
+template <typename T>
+int launch_rows(const float* q_table, const int64_t* q_row, int n_pairs, const int32_t* row_pair,
+                const uint8_t* row_kind, const uint8_t* row_agent, const uint8_t* row_agent2, const uint8_t* executed,
+                const uint8_t* n_moves, int observer, T none_p, T q_cap, T* qdiff, uint8_t* n_valid, uint8_t* act_idx,
+                int64_t n, int P, int n_agents, void* stream) {
+  if (!q_table || !q_row || !row_pair || !row_kind || !row_agent || !row_agent2 || !executed || !n_moves || !qdiff ||
+      !n_valid || !act_idx)
+    return gc_fail(GC_E_ARG, "gc_bd_likelihood_rows: null array");
+  if (n < 0 || P < 1 || P > 128 || n_pairs < 1 || n_agents < 1 || n_agents > GC_MAX_AGENTS || observer < 0 ||
+      observer >= n_agents)
+    return gc_fail(GC_E_ARG, "gc_bd_likelihood_rows: bad sizes (n=%lld P=%d pairs=%d agents=%d observer=%d)",
+                   (long long)n, P, n_pairs, n_agents, observer);
+  RowTable rt;
+  memset(&rt, 0, sizeof(rt));
+  for (int p = 0; p < P; p++) {
+    const int kind = row_kind[p];
+    if (kind > 2 || row_agent[p] >= n_agents || (kind == 2 && row_agent2[p] >= n_agents) ||
+        (kind != 0 && (row_pair[p] < 0 || row_pair[p] >= n_pairs)))
+      return gc_fail(GC_E_ARG, "gc_bd_likelihood_rows: row %d is malformed", p);
+    if (kind == 2 && observer != row_agent[p] && observer != row_agent2[p])
+      return gc_fail(GC_E_LIMIT, "gc_bd_likelihood_rows: joint row %d does not contain the observer", p);
+    rt.pair[p] = row_pair[p];
+    rt.kind[p] = (uint8_t)kind;
+    rt.agent[p] = row_agent[p];
+    rt.agent2[p] = row_agent2[p];
+  }
+  if (n == 0) return GC_OK;
+  if (int rc = gc_require_device()) return rc;
+  const int64_t total = n * P;
+  bd_rows_kernel<T><<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      q_table, q_row, n_pairs, rt, executed, n_moves, observer, none_p, q_cap, qdiff, n_valid, act_idx, n, P, n_agents);
+  return gc_check_launch("gc_bd_likelihood_rows");
+}
+
 }  // namespace
 
 extern "C" {
@@ -492,6 +596,24 @@ int gc_bd_posterior_f64(double* probs, const uint8_t* alive, const uint8_t* hyp_
                         const double* qdiff, const uint8_t* n_valid, const uint8_t* act_idx, double beta, int64_t n,
                         int H, int P, int A, int n_entries, void* stream) {
   return launch<double>(probs, alive, hyp_pair, pair_w, qdiff, n_valid, act_idx, beta, n, H, P, A, n_entries, stream);
+}
+
+int gc_bd_likelihood_rows_f32(const float* q_table, const int64_t* q_row, int n_pairs, const int32_t* row_pair,
+                              const uint8_t* row_kind, const uint8_t* row_agent, const uint8_t* row_agent2,
+                              const uint8_t* executed, const uint8_t* n_moves, int observer, float none_action_prob,
+                              float q_cap, float* qdiff, uint8_t* n_valid, uint8_t* act_idx, int64_t n, int P,
+                              int n_agents, void* stream) {
+  return launch_rows<float>(q_table, q_row, n_pairs, row_pair, row_kind, row_agent, row_agent2, executed, n_moves,
+                            observer, none_action_prob, q_cap, qdiff, n_valid, act_idx, n, P, n_agents, stream);
+}
+
+int gc_bd_likelihood_rows_f64(const float* q_table, const int64_t* q_row, int n_pairs, const int32_t* row_pair,
+                              const uint8_t* row_kind, const uint8_t* row_agent, const uint8_t* row_agent2,
+                              const uint8_t* executed, const uint8_t* n_moves, int observer, double none_action_prob,
+                              double q_cap, double* qdiff, uint8_t* n_valid, uint8_t* act_idx, int64_t n, int P,
+                              int n_agents, void* stream) {
+  return launch_rows<double>(q_table, q_row, n_pairs, row_pair, row_kind, row_agent, row_agent2, executed, n_moves,
+                             observer, none_action_prob, q_cap, qdiff, n_valid, act_idx, n, P, n_agents, stream);
 }
 
 }  // extern "C"

@@ -77,3 +77,24 @@ def test_random_tie_breaks_finish(level, models, limit, n):
     assert float(t[loop.kb.reward.bool()].mean()) <= limit
     assert loop.cache.solved_states < loop.cache.lookups / 4  # the memo is doing its job
     assert int(stats[0]) == n and loop.kb.num_envs == n and (n < 4096 or loop.wkb.num_envs < n)
+
+
+@pytest.mark.parametrize("level,models", [("open-divider_salad", ("bd", "bd")), ("partial-divider_tl", ("greedy", "dc"))])
+def test_likelihood_row_kernel_equals_the_torch_restatement(level, models):
+    """gc_bd_likelihood_rows (prob_nav_actions' softmax inputs, bd:461-689) against the tensor-op
+    restatement, on the states / executed actions of a running delegation loop"""
+    loop = batched_agents.BatchedDelegation(level, 2048, models, seed=5)
+    compared = 0
+    for step in range(14):
+        loop.step()
+        if step % 3 != 1:
+            continue
+        for T in loop.tables:
+            qd, nv, ai = loop._likelihood_rows(T)
+            qd_t, nv_t, ai_t = loop._likelihood_rows_torch(T)
+            assert torch.equal(nv, nv_t) and torch.equal(ai, ai_t)
+            live = torch.arange(5, device=qd.device)[None, None, :] < nv[:, :, None]
+            assert torch.equal(torch.where(live, qd, 0.0), torch.where(live, qd_t, 0.0))
+            assert bool((nv >= 1).all()) and bool((ai < nv).all())
+            compared += int(nv.numel())
+    assert compared > 100000
