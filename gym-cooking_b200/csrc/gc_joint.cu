@@ -728,15 +728,20 @@ joint_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant
   __shared__ World w;
   __shared__ int root_state;  // 0 search, 1 invalid action, 2 goal right away
   Arena* A = arenas + blockIdx.x;
-  const int64_t n_search = n * pairs.n * 25;
-  for (int64_t sid = blockIdx.x; sid < n_search; sid += gridDim.x) {
-    const int64_t prob = sid / 25;
-    const int act = (int)(sid - prob * 25);
+  // work units: with a todo mask (after the tree search) one problem, whose open actions are walked
+  // here - nearly all masks are 0, and one uniform read per PROBLEM skips them; without it (the
+  // first-generation path) one (problem, action)
+  const int64_t n_prob = n * pairs.n;
+  const int64_t n_units = todo ? n_prob : n_prob * 25;
+  for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+   const int64_t prob = todo ? unit : unit / 25;
+   uint32_t open = todo ? todo[prob] : (1u << (int)(unit - prob * 25));
+   while (open) {
+    const int act = __ffs((int)open) - 1;
+    open &= open - 1u;
     const int64_t env = prob / pairs.n;
     const int pi = (int)(prob - env * pairs.n);
     const uint32_t a1 = (uint32_t)(act / 5), a2 = (uint32_t)(act % 5);
-    // after the tree search nearly every action is settled: skip without a barrier (the read is uniform)
-    if (todo && !((todo[prob] >> act) & 1u)) continue;
     __syncthreads();
     if (threadIdx.x == 0) {
       root_state = 1;
@@ -822,6 +827,7 @@ joint_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant
       if (result != 0x7fffffff) q_out[prob * 25 + act] = step_cost + 0.1f * (float)result;
       else if (over) atomicOr(&flags[prob], 1);  // budget exceeded: this Q stays +inf and is flagged
     }
+   }  // open actions
   }
 }
 
