@@ -269,20 +269,24 @@ int gc_lower_bound(const gc_level* levels, int n_levels, const uint8_t* level_id
  * goal = "count of goal objects increased" (:435-566), other agents frozen (:360-406).
  *   v      device float[n][n_pairs]       V*(start); +inf when the goal is unreachable
  *   q      device float[n][n_pairs][25]   nullable; Q(start, a) = cost + V*(T(start,a)) for the
- *          joint action a = 5*a_i + a_j (single agent: a in 0..4); +inf for invalid actions
+ *          joint action a = 5*a_i + a_j (single agent: a in 0..4); NaN for actions that are not
+ *          offered, +inf for offered actions from which the goal is out of reach
  *   status device uint8[n][n_pairs]       nullable; 0 ok, 1 goal already satisfied at start,
  *          2 unreachable, 3 search budget exceeded */
 int gc_subtask_q(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
                  const uint32_t* state /*device*/, const uint8_t* pairs /*host*/, int n_pairs,
                  float* v, float* q, uint8_t* status, int64_t n, int n_agents, void* stream);
 
-/* Joint (two-agent) pairs of the same MDP: budgeted exact uniform-cost search over full planning
- * states, one CTA per (env, pair, root joint action), visited set in a caller-provided scratch
- * arena of gc_joint_q_scratch_bytes(n, n_pairs, NULL) bytes.  Only pairs with agent j != 0xFF are
- * written: v[n][n_pairs], q[n][n_pairs][25] (joint action 5*a_i + a_j), status (0 ok,
- * 2 unreachable, 3 a search exceeded its 48K-state budget - its Q stays +inf, 4 unsupported:
- * more than four objects).  Single-agent entries of v/q/status are left untouched, so both
- * solvers can fill the same arrays. */
+/* Joint (two-agent) pairs of the same MDP: budgeted exact search over full planning states.  One
+ * CTA per (env, pair) runs a forward A* pass that records every generated edge and a backward
+ * pass over those edges, which proves Q(start, a) for all offered joint actions whose value fits
+ * inside the explored region (widened up to V* + 4.8); what stays open is searched per action.
+ * The visited sets live in a caller-provided scratch arena of gc_joint_q_scratch_bytes(n, n_pairs,
+ * NULL) bytes.  Only pairs with agent j != 0xFF are written: v[n][n_pairs], q[n][n_pairs][25]
+ * (joint action 5*a_i + a_j; NaN = not offered, +inf = offered but the goal is out of reach or the
+ * value unproven), status (0 ok, 2 unreachable, 3 a search outgrew its budget of 96K states - the
+ * proven Q values are kept, the others stay +inf, 4 unsupported: more than four objects).
+ * Single-agent entries of v/q/status are left untouched, so both solvers fill the same arrays. */
 int64_t gc_joint_q_scratch_bytes(int64_t n, int n_pairs, int* n_ctas_out);
 int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
                const uint32_t* state /*device*/, const uint8_t* pairs /*host*/, int n_pairs, float* v, float* q,
