@@ -452,11 +452,14 @@ int launch(T* probs, const uint8_t* alive, const uint8_t* hyp_pair, const uint8_
   if (int rc = gc_require_device()) return rc;
   const int need = H > P ? H : P;
   cudaStream_t st = (cudaStream_t)stream;
-  // smallest group that covers max(H, P) in one chunk; larger tables loop in chunks of 32
-  if (need <= 8) {
+  // staged kernels: the group is sized for the likelihood rows (the expensive phase: up to 25 exps
+  // per row); hypotheses loop in chunks of G.  GC_BD_GROUP_BY_MAX=1 restores "G covers max(H, P)".
+  static const bool by_max = getenv("GC_BD_GROUP_BY_MAX") != nullptr;
+  const int lanes = by_max ? need : P;
+  if (lanes <= 8) {
     if (launch_staged<T, 8>(probs, alive, hyp_pair, pair_w, qdiff, n_valid, act_idx, beta, n, H, P, A, n_entries, st))
       return gc_check_launch("gc_bd_posterior");
-  } else if (need <= 16) {
+  } else if (lanes <= 16) {
     if (launch_staged<T, 16>(probs, alive, hyp_pair, pair_w, qdiff, n_valid, act_idx, beta, n, H, P, A, n_entries, st))
       return gc_check_launch("gc_bd_posterior");
   } else {
