@@ -923,7 +923,8 @@ int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, co
     // many problems: 4 CTAs of 128 threads per SM (throughput).  Few (the delegation loop solving the
     // states it has not seen yet): 2 CTAs of 512 threads per SM, so that more hash / edge atomics are in
     // flight per search (a 96 K-state search is latency bound: 1.6x faster on the wide CTA)
-    if (probs > kWideProblems) {
+    static const int64_t wide_limit = getenv("GC_JOINT_WIDE_PROBLEMS") ? atoll(getenv("GC_JOINT_WIDE_PROBLEMS")) : kWideProblems;
+    if (probs > wide_limit) {
       joint_tree_kernel<kThreads><<<(unsigned)tree_ctas, kThreads, 0, st>>>(
           lv, pr, lid, s4, reinterpret_cast<Arena2*>(base), q, flags, todo, n, n_agents, kMaxStates2);
     } else {
