@@ -494,6 +494,36 @@ __device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* 
   atomicExch(over, 1);
 }
 
+// Forward pass, one open-list entry (slot | g << 17) popped at key `cur`: settle it (stale entries
+// and states expanded already fail the CAS), absorb goal states, relax every joint successor.
+__device__ __forceinline__ void expand_entry(const World& w, const Tables* T, Arena2* A, uint32_t* bcount,
+                                             uint32_t* n_states, uint32_t* n_pool, uint32_t* n_goals, int* over,
+                                             int* result, uint32_t entry, uint32_t cur, uint32_t max_states) {
+  const uint32_t h = entry & (kSlots2 - 1u), g = entry >> 17;
+  if (atomicCAS(&A->gcost[h], 2u * g, 2u * g + 1u) != 2u * g) return;
+  const PState p = unpack_state(A->states[h]);
+  if (is_goal(w, p)) {
+    atomicMin(result, (int)g);
+    A->val[h] = 0u;
+    const uint32_t gi = atomicAdd(n_goals, 1u);
+    if (gi < kGoalCap) A->goals[gi] = h;
+    else atomicExch(over, 1);
+    return;
+  }
+  const uint32_t v1 = single_actions(w, p, 0), v2 = single_actions(w, p, 1);
+  for (uint32_t b1 = 0; b1 < 5; b1++) {
+    if (!((v1 >> b1) & 1u)) continue;
+    for (uint32_t b2 = 0; b2 < 5; b2++) {
+      if (!((v2 >> b2) & 1u) || (b1 == 4u && b2 == 4u) || !joint_ok(w, p, b1, b2)) continue;
+      PState nx = p;
+      interact(w, nx, 0, b1);
+      interact(w, nx, 1, b2);
+      const uint32_t code = (b1 != 4u) + (b2 != 4u);
+      relax2(w, T, A, bcount, n_states, n_pool, over, nx, g + 10u + code, cur, h, code, max_states);
+    }
+  }
+}
+
 template <int kTreeThreads>
 __global__ void __launch_bounds__(kTreeThreads)
 joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant__ GcPairs pairs,
@@ -562,144 +592,122 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
     int empty_run = 0, limit = kMaxCost, cur = (int)s_f0, slack = kSlack;
     bool complete = false;
     for (;;) {  // widen the explored region until every offered action is proven (or kMaxSlack / the budget is hit)
-    for (; cur <= limit; cur++) {
-      const uint32_t b = (uint32_t)cur & (kRing - 1);
-      if (bcount[b] == 0) {  // uniform: bcount only changes between barriers
-        if (++empty_run >= kRing) {
-          complete = true;  // nothing left to expand: the whole space that can still reach the goal was covered
-          break;
-        }
-        continue;
-      }
-      empty_run = 0;
-      // children on the same plateau (pathmax) land in this very bucket: sweep it until it stops growing
-      for (uint32_t done = 0;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_cnt = min(bcount[b], kRingCap);
-        __syncthreads();
-        const uint32_t cnt = s_cnt;
-        if (cnt == done) break;
-        for (uint32_t e = done + threadIdx.x; e < cnt; e += kTreeThreads) {
-        const uint32_t entry = A->bucket[b][e], h = entry & (kSlots2 - 1u), g = entry >> 17;
-        if (atomicCAS(&A->gcost[h], 2u * g, 2u * g + 1u) != 2u * g) continue;  // stale, or expanded already
-        const PState p = unpack_state(A->states[h]);
-        if (is_goal(w, p)) {  // absorbing
-          atomicMin(&result, (int)g);
-          A->val[h] = 0u;
-          const uint32_t gi = atomicAdd(&n_goals, 1u);
-          if (gi < kGoalCap) A->goals[gi] = h;
-          else atomicExch(&over, 1);
+      for (; cur <= limit; cur++) {
+        const uint32_t b = (uint32_t)cur & (kRing - 1);
+        if (bcount[b] == 0) {  // uniform: bcount only changes between barriers
+          if (++empty_run >= kRing) {
+            complete = true;  // nothing left to expand: the whole space that can still reach the goal was covered
+            break;
+          }
           continue;
         }
-        const uint32_t v1 = single_actions(w, p, 0), v2 = single_actions(w, p, 1);
-        for (uint32_t b1 = 0; b1 < 5; b1++) {
-          if (!((v1 >> b1) & 1u)) continue;
-          for (uint32_t b2 = 0; b2 < 5; b2++) {
-            if (!((v2 >> b2) & 1u) || (b1 == 4u && b2 == 4u) || !joint_ok(w, p, b1, b2)) continue;
-            PState nx = p;
-            interact(w, nx, 0, b1);
-            interact(w, nx, 1, b2);
-            const uint32_t code = (b1 != 4u) + (b2 != 4u);
-            relax2(w, &T, A, bcount, &n_states, &n_pool, &over, nx, g + 10u + code, (uint32_t)cur, h, code, max_states);
+        empty_run = 0;
+        // children on the same plateau (pathmax) land in this very bucket: sweep it until it stops growing
+        for (uint32_t done = 0;;) {
+          __syncthreads();
+          if (threadIdx.x == 0) s_cnt = min(bcount[b], kRingCap);
+          __syncthreads();
+          const uint32_t cnt = s_cnt;
+          if (cnt == done) break;
+          for (uint32_t e = done + threadIdx.x; e < cnt; e += kTreeThreads)
+            expand_entry(w, &T, A, bcount, &n_states, &n_pool, &n_goals, &over, &result, A->bucket[b][e], (uint32_t)cur,
+                         max_states);
+          done = cnt;
+          if (cnt == kRingCap) break;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          if (bcount[b] > kRingCap) over = 1;
+          bcount[b] = 0;
+        }
+        __syncthreads();
+        if (over) break;
+        if (result != 0x7fffffff) limit = min(kMaxCost, result + slack);
+      }
+      // every state with key <= radius has been expanded
+      const int radius = complete ? 0x3fffffff : (over ? cur - 1 : (cur > limit ? limit : cur - 1));
+      __syncthreads();
+      if (threadIdx.x < kBuckets) bbcount[threadIdx.x] = 0;
+      if (threadIdx.x == 0) s_todo = 0;
+      __syncthreads();
+      if (result == 0x7fffffff) {  // no goal inside the explored region
+        if (threadIdx.x == 0) {
+          if (!complete) atomicOr(&flags[prob], 1);  // budget: unknown.  complete: every offered Q is +inf, exactly
+          todo[prob] = 0;
+        }
+        break;
+      }
+      // ---- backward: exact cost-to-go inside the region, from the goal states over the recorded edges
+      // (its own buckets: the forward pass may resume from its open list) ----
+      for (uint32_t i = threadIdx.x; i < min(n_goals, kGoalCap); i += kTreeThreads) {
+        const uint32_t pos = atomicAdd(&bbcount[0], 1u);
+        if (pos < kRingCap) A->bbucket[0][pos] = A->goals[i];
+        else atomicExch(&over, 2);
+      }
+      __syncthreads();
+      const int bmax = complete ? kMaxCost : radius;
+      int brun = 0;
+      for (int bc = 0; bc <= bmax; bc++) {
+        const uint32_t b = (uint32_t)bc & (kBuckets - 1);
+        const uint32_t cnt = min(bbcount[b], kRingCap);
+        if (cnt == 0) {
+          if (++brun >= kBuckets) break;
+          continue;
+        }
+        brun = 0;
+        for (uint32_t e = threadIdx.x; e < cnt; e += kTreeThreads) {
+          const uint32_t h = A->bbucket[b][e];
+          if (A->val[h] != (uint32_t)bc) continue;  // improved since it was pushed
+          for (uint32_t node = A->head[h]; node != kNil; node = A->pool[node].y) {
+            const uint32_t x = A->pool[node].x & 0x3FFFFFFFu;
+            const uint32_t nv = (uint32_t)bc + 10u + (A->pool[node].x >> 30);
+            if (atomicMin(&A->val[x], nv) > nv) {
+              const uint32_t pos = atomicAdd(&bbcount[nv & (kBuckets - 1)], 1u);
+              if (pos < kRingCap) A->bbucket[nv & (kBuckets - 1)][pos] = x;
+              else atomicExch(&over, 2);
+            }
           }
         }
-        }
-        done = cnt;
-        if (cnt == kRingCap) break;
+        __syncthreads();
+        if (threadIdx.x == 0) bbcount[b] = 0;
+        __syncthreads();
       }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        if (bcount[b] > kRingCap) over = 1;
-        bcount[b] = 0;
-      }
-      __syncthreads();
-      if (over) break;
-      if (result != 0x7fffffff) limit = min(kMaxCost, result + slack);
-    }
-    // every state with key <= radius has been expanded
-    const int radius = complete ? 0x3fffffff : (over ? cur - 1 : (cur > limit ? limit : cur - 1));
-    __syncthreads();
-    if (threadIdx.x < kBuckets) bbcount[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_todo = 0;
-    __syncthreads();
-    if (result == 0x7fffffff) {  // no goal inside the explored region
-      if (threadIdx.x == 0) {
-        if (!complete) atomicOr(&flags[prob], 1);  // budget: unknown.  complete: every offered Q is +inf, exactly
-        todo[prob] = 0;
-      }
-      break;
-    }
-    // ---- backward: exact cost-to-go inside the region, from the goal states over the recorded edges
-    // (its own buckets: the forward pass may resume from its open list) ----
-    for (uint32_t i = threadIdx.x; i < min(n_goals, kGoalCap); i += kTreeThreads) {
-      const uint32_t pos = atomicAdd(&bbcount[0], 1u);
-      if (pos < kRingCap) A->bbucket[0][pos] = A->goals[i];
-      else atomicExch(&over, 2);
-    }
-    __syncthreads();
-    const int bmax = complete ? kMaxCost : radius;
-    int brun = 0;
-    for (int bc = 0; bc <= bmax; bc++) {
-      const uint32_t b = (uint32_t)bc & (kBuckets - 1);
-      const uint32_t cnt = min(bbcount[b], kRingCap);
-      if (cnt == 0) {
-        if (++brun >= kBuckets) break;
-        continue;
-      }
-      brun = 0;
-      for (uint32_t e = threadIdx.x; e < cnt; e += kTreeThreads) {
-        const uint32_t h = A->bbucket[b][e];
-        if (A->val[h] != (uint32_t)bc) continue;  // improved since it was pushed
-        for (uint32_t node = A->head[h]; node != kNil; node = A->pool[node].y) {
-          const uint32_t x = A->pool[node].x & 0x3FFFFFFFu;
-          const uint32_t nv = (uint32_t)bc + 10u + (A->pool[node].x >> 30);
-          if (atomicMin(&A->val[x], nv) > nv) {
-            const uint32_t pos = atomicAdd(&bbcount[nv & (kBuckets - 1)], 1u);
-            if (pos < kRingCap) A->bbucket[nv & (kBuckets - 1)][pos] = x;
-            else atomicExch(&over, 2);
-          }
+      // ---- Q(start, a) = cost(a) + cost-to-go of T(start, a), proven when it fits inside the region ----
+      if (offered && threadIdx.x != 24) {
+        PState nx = start;
+        interact(w, nx, 0, a1);
+        interact(w, nx, 1, a2);
+        const uint32_t code = (a1 != 4u) + (a2 != 4u);
+        const float step_cost = 1.0f + 0.1f * (float)code;
+        if (is_goal(w, nx)) {
+          q_out[prob * 25 + threadIdx.x] = step_cost;
+        } else {
+          const uint32_t h = find2(w, A, nx);
+          const uint32_t v = h == kNil ? kInfCost : A->val[h];
+          const bool proven = over != 2 && v != kInfCost && (complete || (int)(v + 10u + code) <= radius);
+          const bool dead = heuristic(w, &T, nx) == kInfCost;  // no way back: +inf is exact
+          if (proven) q_out[prob * 25 + threadIdx.x] = step_cost + 0.1f * (float)v;
+          else if (!dead && !(complete && over != 2)) atomicOr(&s_todo, 1u << threadIdx.x);  // complete: +inf is exact
         }
       }
       __syncthreads();
-      if (threadIdx.x == 0) bbcount[b] = 0;
+      const uint32_t open_actions = s_todo;
+      if (open_actions == 0u || complete || over || slack >= kMaxSlack || limit >= kMaxCost) {
+        if (threadIdx.x == 0) {
+          // a search that outgrew the budget keeps what it proved and reports the rest as unknown: the
+          // per-action searches explore the same region with half the budget and would burn it 24 times
+          if (over && open_actions) atomicOr(&flags[prob], 1);
+          todo[prob] = over ? 0u : open_actions;
+        }
+        break;
+      }
+      // widen: the forward pass resumes where it stopped; cost-to-go values are rebuilt from the goals
+      slack += kSlackStep;
+      limit = min(kMaxCost, result + slack);
+      for (uint32_t k = threadIdx.x; k < kSlots2; k += kTreeThreads) A->val[k] = kInfCost;
       __syncthreads();
-    }
-    // ---- Q(start, a) = cost(a) + cost-to-go of T(start, a), proven when it fits inside the region ----
-    if (offered && threadIdx.x != 24) {
-      PState nx = start;
-      interact(w, nx, 0, a1);
-      interact(w, nx, 1, a2);
-      const uint32_t code = (a1 != 4u) + (a2 != 4u);
-      const float step_cost = 1.0f + 0.1f * (float)code;
-      if (is_goal(w, nx)) {
-        q_out[prob * 25 + threadIdx.x] = step_cost;
-      } else {
-        const uint32_t h = find2(w, A, nx);
-        const uint32_t v = h == kNil ? kInfCost : A->val[h];
-        const bool proven = over != 2 && v != kInfCost && (complete || (int)(v + 10u + code) <= radius);
-        const bool dead = heuristic(w, &T, nx) == kInfCost;  // no way back: +inf is exact
-        if (proven) q_out[prob * 25 + threadIdx.x] = step_cost + 0.1f * (float)v;
-        else if (!dead && !(complete && over != 2)) atomicOr(&s_todo, 1u << threadIdx.x);  // complete: +inf is exact
-      }
-    }
-    __syncthreads();
-    const uint32_t open_actions = s_todo;
-    if (open_actions == 0u || complete || over || slack >= kMaxSlack || limit >= kMaxCost) {
-      if (threadIdx.x == 0) {
-        // a search that outgrew the budget keeps what it proved and reports the rest as unknown: the
-        // per-action searches explore the same region with half the budget and would burn it 24 times
-        if (over && open_actions) atomicOr(&flags[prob], 1);
-        todo[prob] = over ? 0u : open_actions;
-      }
-      break;
-    }
-    // widen: the forward pass resumes where it stopped; cost-to-go values are rebuilt from the goals
-    slack += kSlackStep;
-    limit = min(kMaxCost, result + slack);
-    for (uint32_t k = threadIdx.x; k < kSlots2; k += kTreeThreads) A->val[k] = kInfCost;
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < min(n_goals, kGoalCap); i += kTreeThreads) A->val[A->goals[i]] = 0u;
-    __syncthreads();
+      for (uint32_t i = threadIdx.x; i < min(n_goals, kGoalCap); i += kTreeThreads) A->val[A->goals[i]] = 0u;
+      __syncthreads();
     }  // widening loop
     __syncthreads();
     if (n_states <= kTouchedCap) {
@@ -734,100 +742,100 @@ joint_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant
   const int64_t n_prob = n * pairs.n;
   const int64_t n_units = todo ? n_prob : n_prob * 25;
   for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-   const int64_t prob = todo ? unit : unit / 25;
-   uint32_t open = todo ? todo[prob] : (1u << (int)(unit - prob * 25));
-   while (open) {
-    const int act = __ffs((int)open) - 1;
-    open &= open - 1u;
-    const int64_t env = prob / pairs.n;
-    const int pi = (int)(prob - env * pairs.n);
-    const uint32_t a1 = (uint32_t)(act / 5), a2 = (uint32_t)(act % 5);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      root_state = 1;
-      PState p;
-      gc_subtask st;
-      const bool wanted = true;
-      const int kind = wanted ? setup_problem(levels, pairs, level_id, state, env, pi, n_agents, w, p, st) : 0;
-      if (kind == 1) {
-        atomicOr(&flags[prob], 4);
-      } else if (kind >= 2 && wanted) {
-        const bool goal_exists = kind == 3;
-        const uint32_t v1 = single_actions(w, p, 0), v2 = single_actions(w, p, 1);
-        if (((v1 >> a1) & 1u) && ((v2 >> a2) & 1u) && joint_ok(w, p, a1, a2)) {
-          q_out[prob * 25 + act] = INFINITY;  // offered (e2e_brtdp.get_actions :151-206)
-          // (stay, stay) leaves the state unchanged: Q = 1 + V*(start), filled in by the finalize kernel
-          if (!goal_exists && act != 24) {
-            interact(w, p, 0, a1);
-            interact(w, p, 1, a2);
-            root = p;
-            root_state = is_goal(w, p) ? 2 : 0;
-            // an irreversible move can put the goal out of reach: same adjacency test as at the start
-            if (root_state == 0 && !maybe_reachable(w, p, st.a, st.b)) root_state = 1;
+    const int64_t prob = todo ? unit : unit / 25;
+    uint32_t open = todo ? todo[prob] : (1u << (int)(unit - prob * 25));
+    while (open) {
+      const int act = __ffs((int)open) - 1;
+      open &= open - 1u;
+      const int64_t env = prob / pairs.n;
+      const int pi = (int)(prob - env * pairs.n);
+      const uint32_t a1 = (uint32_t)(act / 5), a2 = (uint32_t)(act % 5);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        root_state = 1;
+        PState p;
+        gc_subtask st;
+        const bool wanted = true;
+        const int kind = wanted ? setup_problem(levels, pairs, level_id, state, env, pi, n_agents, w, p, st) : 0;
+        if (kind == 1) {
+          atomicOr(&flags[prob], 4);
+        } else if (kind >= 2 && wanted) {
+          const bool goal_exists = kind == 3;
+          const uint32_t v1 = single_actions(w, p, 0), v2 = single_actions(w, p, 1);
+          if (((v1 >> a1) & 1u) && ((v2 >> a2) & 1u) && joint_ok(w, p, a1, a2)) {
+            q_out[prob * 25 + act] = INFINITY;  // offered (e2e_brtdp.get_actions :151-206)
+            // (stay, stay) leaves the state unchanged: Q = 1 + V*(start), filled in by the finalize kernel
+            if (!goal_exists && act != 24) {
+              interact(w, p, 0, a1);
+              interact(w, p, 1, a2);
+              root = p;
+              root_state = is_goal(w, p) ? 2 : 0;
+              // an irreversible move can put the goal out of reach: same adjacency test as at the start
+              if (root_state == 0 && !maybe_reachable(w, p, st.a, st.b)) root_state = 1;
+            }
           }
         }
+        n_states = 0;
+        over = 0;
+        result = 0x7fffffff;
       }
-      n_states = 0;
-      over = 0;
-      result = 0x7fffffff;
-    }
-    if (threadIdx.x < kBuckets) bcount[threadIdx.x] = 0;
-    __syncthreads();
-    const float step_cost = 1.0f + 0.1f * (float)((a1 != 4u) + (a2 != 4u));
-    if (root_state == 1) continue;
-    if (root_state == 2) {
-      if (threadIdx.x == 0) q_out[prob * 25 + act] = step_cost;
-      continue;
-    }
-    // ---- clear the table, seed the root ----
-    for (uint32_t k = threadIdx.x; k < kSlots; k += kThreads) {
-      A->keys[k] = kEmpty;
-      A->gcost[k] = kInfCost;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) relax(w, A, bcount, &n_states, &over, root, 0u);
-    __syncthreads();
-    // ---- Dial's algorithm ----
-    int empty_run = 0;
-    for (int cur = 0; cur <= kMaxCost && empty_run < kBuckets; cur++) {
-      const uint32_t b = (uint32_t)cur & (kBuckets - 1);
-      const uint32_t cnt = min(bcount[b], kBucketCap);
-      if (cnt == 0) {
-        empty_run++;
-        continue;  // uniform: bcount is shared and only changes between barriers
+      if (threadIdx.x < kBuckets) bcount[threadIdx.x] = 0;
+      __syncthreads();
+      const float step_cost = 1.0f + 0.1f * (float)((a1 != 4u) + (a2 != 4u));
+      if (root_state == 1) continue;
+      if (root_state == 2) {
+        if (threadIdx.x == 0) q_out[prob * 25 + act] = step_cost;
+        continue;
       }
-      empty_run = 0;
-      for (uint32_t e = threadIdx.x; e < cnt; e += kThreads) {
-        const uint32_t h = A->bucket[b][e];
-        // settle exactly once, and only if this entry still carries the best cost
-        if (atomicCAS(&A->gcost[h], 2u * (uint32_t)cur, 2u * (uint32_t)cur + 1u) != 2u * (uint32_t)cur) continue;
-        const PState p = unpack_state(A->states[h]);
-        if (is_goal(w, p)) {
-          atomicMin(&result, cur);
-          continue;
+      // ---- clear the table, seed the root ----
+      for (uint32_t k = threadIdx.x; k < kSlots; k += kThreads) {
+        A->keys[k] = kEmpty;
+        A->gcost[k] = kInfCost;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) relax(w, A, bcount, &n_states, &over, root, 0u);
+      __syncthreads();
+      // ---- Dial's algorithm ----
+      int empty_run = 0;
+      for (int cur = 0; cur <= kMaxCost && empty_run < kBuckets; cur++) {
+        const uint32_t b = (uint32_t)cur & (kBuckets - 1);
+        const uint32_t cnt = min(bcount[b], kBucketCap);
+        if (cnt == 0) {
+          empty_run++;
+          continue;  // uniform: bcount is shared and only changes between barriers
         }
-        const uint32_t v1 = single_actions(w, p, 0), v2 = single_actions(w, p, 1);
-        for (uint32_t b1 = 0; b1 < 5; b1++) {
-          if (!((v1 >> b1) & 1u)) continue;
-          for (uint32_t b2 = 0; b2 < 5; b2++) {
-            if (!((v2 >> b2) & 1u) || (b1 == 4u && b2 == 4u) || !joint_ok(w, p, b1, b2)) continue;
-            PState nx = p;
-            interact(w, nx, 0, b1);
-            interact(w, nx, 1, b2);
-            relax(w, A, bcount, &n_states, &over, nx, (uint32_t)cur + 10u + (b1 != 4u) + (b2 != 4u));
+        empty_run = 0;
+        for (uint32_t e = threadIdx.x; e < cnt; e += kThreads) {
+          const uint32_t h = A->bucket[b][e];
+          // settle exactly once, and only if this entry still carries the best cost
+          if (atomicCAS(&A->gcost[h], 2u * (uint32_t)cur, 2u * (uint32_t)cur + 1u) != 2u * (uint32_t)cur) continue;
+          const PState p = unpack_state(A->states[h]);
+          if (is_goal(w, p)) {
+            atomicMin(&result, cur);
+            continue;
+          }
+          const uint32_t v1 = single_actions(w, p, 0), v2 = single_actions(w, p, 1);
+          for (uint32_t b1 = 0; b1 < 5; b1++) {
+            if (!((v1 >> b1) & 1u)) continue;
+            for (uint32_t b2 = 0; b2 < 5; b2++) {
+              if (!((v2 >> b2) & 1u) || (b1 == 4u && b2 == 4u) || !joint_ok(w, p, b1, b2)) continue;
+              PState nx = p;
+              interact(w, nx, 0, b1);
+              interact(w, nx, 1, b2);
+              relax(w, A, bcount, &n_states, &over, nx, (uint32_t)cur + 10u + (b1 != 4u) + (b2 != 4u));
+            }
           }
         }
+        __syncthreads();
+        if (threadIdx.x == 0) bcount[b] = 0;
+        __syncthreads();
+        if (result != 0x7fffffff || over) break;
       }
-      __syncthreads();
-      if (threadIdx.x == 0) bcount[b] = 0;
-      __syncthreads();
-      if (result != 0x7fffffff || over) break;
-    }
-    if (threadIdx.x == 0) {
-      if (result != 0x7fffffff) q_out[prob * 25 + act] = step_cost + 0.1f * (float)result;
-      else if (over) atomicOr(&flags[prob], 1);  // budget exceeded: this Q stays +inf and is flagged
-    }
-   }  // open actions
+      if (threadIdx.x == 0) {
+        if (result != 0x7fffffff) q_out[prob * 25 + act] = step_cost + 0.1f * (float)result;
+        else if (over) atomicOr(&flags[prob], 1);  // budget exceeded: this Q stays +inf and is flagged
+      }
+    }  // open actions
   }
 }
 
