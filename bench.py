@@ -315,7 +315,9 @@ def run_ours(args):
                 "CUDA graphs of %d consecutive steps replayed, remainder launched one by one" % GRAPH_STEPS
                 if use_graphs else "one launch per step")), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_ENVS * N_AGENTS,
-                    "d2h_bytes_per_step": N_ENVS, "steps": e2e_steps,
+                    "d2h_bytes_per_step": (N_ENVS + 31) // 32 * 8 if env.PACKED_RESULTS else N_ENVS,
+                    "results": "done / reward bit planes (2 bits per env)" if env.PACKED_RESULTS else "reward_done bytes",
+                    "steps": e2e_steps,
                     "api": "OvercookedEnvironment(arglist, num_envs=2^20).step(pinned uint8[N][2])"},
             "gpu_launches": timed_launches,
             "roofline": {"bound": "hbm", "kernel": "step_lut_kernel<2,4> (gc_env_step)", "achieved": achieved,

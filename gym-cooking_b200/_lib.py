@@ -49,7 +49,7 @@ _SIGNATURES = {
     "gc_env_step": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP,
                               _VOIDP, C.c_int64, C.c_int, _VOIDP]),
     "gc_env_step_host": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP,
-                                   C.c_int64, C.c_int, _VOIDP]),
+                                   _VOIDP, _VOIDP, C.c_int64, C.c_int, _VOIDP]),
     "gc_env_rollout": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP,
                                  C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_uint64, _VOIDP]),
     "gc_fill_random_actions": (C.c_int, [_VOIDP, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64,

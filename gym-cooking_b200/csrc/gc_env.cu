@@ -238,6 +238,18 @@ stats_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restri
     if (s_hist[k]) atomicAdd(&stats[5 + k], (unsigned long long)s_hist[k]);
 }
 
+// reward/done bytes -> bit planes: bits[2*w] = done of envs 32w..32w+31, bits[2*w+1] = reward
+__global__ void __launch_bounds__(kThreads)
+pack_rd_kernel(const uint8_t* __restrict__ rd, uint32_t* __restrict__ bits, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const uint32_t v = i < n ? rd[i] : 0u;  // every lane votes: no early exit before the ballots
+  const uint32_t d = __ballot_sync(0xffffffffu, v & GC_RD_DONE), r = __ballot_sync(0xffffffffu, v & GC_RD_REWARD);
+  if ((threadIdx.x & 31) == 0 && i < n) {
+    bits[2 * (i >> 5)] = d;
+    bits[2 * (i >> 5) + 1] = r;
+  }
+}
+
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 // Grid of the step kernel.  Measured on B200 (profiles/r01_step_kernel.md): the kernel is bound
@@ -628,9 +640,12 @@ int gc_env_step(const gc_level* levels, int n_levels, const uint8_t* level_id, u
 
 int gc_env_step_host(const gc_level* levels, int n_levels, const uint8_t* level_id, uint32_t* state,
                      const uint8_t* actions_host, uint8_t* actions_dev, uint8_t* reward_done_dev,
-                     uint8_t* reward_done_host, uint32_t* collisions, int64_t n, int n_agents, void* stream) {
-  if (!actions_host || !actions_dev || !reward_done_dev || !reward_done_host)
+                     uint8_t* reward_done_host, uint32_t* rd_bits_dev, uint32_t* rd_bits_host, uint32_t* collisions,
+                     int64_t n, int n_agents, void* stream) {
+  if (!actions_host || !actions_dev || !reward_done_dev)
     return gc_fail(GC_E_ARG, "gc_env_step_host: null host/device action or reward_done buffer");
+  if (!reward_done_host && !(rd_bits_dev && rd_bits_host))
+    return gc_fail(GC_E_ARG, "gc_env_step_host: need reward_done_host or the rd_bits pair for the results");
   if (n < 0 || n_agents < 1 || n_agents > GC_MAX_AGENTS) return gc_fail(GC_E_ARG, "gc_env_step_host: bad n / n_agents");
   if (n == 0) return GC_OK;
   if (int rc = gc_require_device()) return rc;
@@ -640,7 +655,13 @@ int gc_env_step_host(const gc_level* levels, int n_levels, const uint8_t* level_
   if (int rc = gc_env_step(levels, n_levels, level_id, state, actions_dev, reward_done_dev, nullptr, collisions, nullptr,
                            n, n_agents, stream))
     return rc;
-  e = cudaMemcpyAsync(reward_done_host, reward_done_dev, (size_t)n, cudaMemcpyDeviceToHost, st);
+  if (rd_bits_dev && rd_bits_host) {  // two bit planes per 32 envs: a quarter of the bytes over PCIe
+    const int64_t words = (n + 31) / 32;
+    pack_rd_kernel<<<(unsigned)((words * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(reward_done_dev, rd_bits_dev, n);
+    e = cudaMemcpyAsync(rd_bits_host, rd_bits_dev, (size_t)words * 8, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess && reward_done_host)
+    e = cudaMemcpyAsync(reward_done_host, reward_done_dev, (size_t)n, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step_host: copy out failed: %s", cudaGetErrorString(e));
   return GC_OK;

@@ -121,9 +121,11 @@ class KitchenBatch:
             _lib.check(rc)
         return self.reward_done
 
-    def step_host(self, actions_host, actions_dev, reward_done_host):
-        """gc_env_step_host: actions from a (pinned) host tensor, reward/done bytes into a pinned host
-        tensor, one library call that returns when both copies and the step are done."""
+    def step_host(self, actions_host, actions_dev, reward_done_host=None, bits_dev=None, bits_host=None):
+        """gc_env_step_host: actions from a (pinned) host tensor, results into pinned host memory -
+        reward/done bytes (`reward_done_host`, uint8[N]) and/or bit planes (`bits_dev` / `bits_host`,
+        int32[(N+31)//32][2]: done bits, reward bits) - one library call that returns when the
+        copies and the step are done."""
         if actions_host.shape != (self.num_envs, self.num_agents) or actions_host.dtype is not torch.uint8 \
                 or actions_host.is_cuda or not actions_host.is_contiguous():
             raise ValueError("actions_host must be a contiguous uint8 host tensor [%d, %d]" % (self.num_envs, self.num_agents))
@@ -135,7 +137,10 @@ class KitchenBatch:
         try:
             rc = self.lib.gc_env_step_host(
                 self._lv(), self.n_levels, _lib.ptr(self.level_id), self.state.data_ptr(), actions_host.data_ptr(),
-                actions_dev.data_ptr(), self.reward_done.data_ptr(), reward_done_host.data_ptr(),
+                actions_dev.data_ptr(), self.reward_done.data_ptr(),
+                reward_done_host.data_ptr() if reward_done_host is not None else None,
+                bits_dev.data_ptr() if bits_dev is not None else None,
+                bits_host.data_ptr() if bits_host is not None else None,
                 self.collisions.data_ptr() if self.collisions is not None else None, self.num_envs, self.num_agents,
                 torch.cuda.current_stream(dev).cuda_stream)
         finally:
@@ -143,7 +148,7 @@ class KitchenBatch:
                 guard.__exit__(None, None, None)
         if rc != 0:
             _lib.check(rc)
-        return reward_done_host
+        return reward_done_host if reward_done_host is not None else bits_host
 
     def step_range(self, lo, hi, actions, stream=None):
         """Step only envs [lo, hi) with actions uint8[hi-lo][num_agents], on `stream` (a

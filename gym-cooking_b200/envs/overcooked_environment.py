@@ -146,6 +146,42 @@ class Flag:
         return a.astype(dtype) if dtype is not None else a
 
 
+class BitFlag(Flag):
+    """The same lazy view over the bit-plane results of gc_env_step_host: `bits` is the pinned
+    int32[(N+31)//32][2] buffer (plane 0 = done, plane 1 = reward), a quarter of the bytes of the
+    per-env byte array on the way back over PCIe."""
+
+    def __init__(self, bits, plane, n, as_bool):
+        self.bits, self.plane, self.n, self.as_bool = bits, plane, n, as_bool
+
+    def tensor(self):
+        w = self.bits[:, self.plane]
+        t = ((w[:, None] >> torch.arange(32, dtype=torch.int32)) & 1).reshape(-1)[:self.n]
+        return t.bool() if self.as_bool else t.to(torch.uint8)
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += self.n
+        v = (int(self.bits[i >> 5, self.plane]) >> (i & 31)) & 1
+        return bool(v) if self.as_bool else v
+
+    def __len__(self):
+        return self.n
+
+    def any(self):
+        return bool((self.bits[:, self.plane] != 0).any())  # the bits past N are written as 0
+
+    def sum(self):
+        return int(self.tensor().sum())
+
+    def all(self):
+        return self.sum() == self.n
+
+    @property
+    def shape(self):
+        return torch.Size([self.n])
+
+
 class BatchObs:
     """Handle over the packed uint32[N][4] state; `obs[i]` builds the view of env i on demand."""
 
@@ -181,6 +217,7 @@ class OvercookedEnvironment(_ReferenceSurface):
         self._pinned_rd = None
         self._dev_actions = None
         self._streams = None
+        self._pinned_bits = self._dev_bits = None
         # image_obs only when the reference would have a GameImage (env:240-246)
         self._atlas = None
         if getattr(arglist, "with_image_obs", False) or getattr(arglist, "record", False):
@@ -288,6 +325,9 @@ class OvercookedEnvironment(_ReferenceSurface):
     # full duplex and the copy engines run beside the SMs)
     # (opt-in: on the measured hosts the extra launches and syncs cost more than the overlap wins,
     # 202 us vs 99 us per 2^20-env step - scripts/e2e_probe.py - so the default is one stream)
+    # results of a host-actions step come back as two bit planes (done, reward) instead of one byte
+    # per env: 256 KB instead of 1 MB per 2^20-env step over PCIe; `done` / `reward` unpack lazily
+    PACKED_RESULTS = os.environ.get("GC_E2E_BYTE_RESULTS") is None
     PIPELINE_CHUNKS = 1
     PIPELINE_MIN_ENVS = 1 << 16
 
@@ -303,6 +343,17 @@ class OvercookedEnvironment(_ReferenceSurface):
             # host actions in, reward/done bytes out: one library call (gc_env_step_host) that copies
             # in (async when `acts` is pinned), steps, copies out and waits for the stream
             if acts.dtype is torch.uint8 and acts.is_contiguous() and acts.shape == (n, self.num_agents):
+                if self.PACKED_RESULTS:
+                    if self._pinned_bits is None:
+                        words = (n + 31) // 32
+                        self._pinned_bits = torch.zeros((words, 2), dtype=torch.int32).pin_memory()
+                        self._dev_bits = torch.zeros((words, 2), dtype=torch.int32, device=kb.device)
+                    kb.step_host(acts, self._dev_actions, None, self._dev_bits, self._pinned_bits)
+                    obs = self._obs()
+                    done = BitFlag(self._pinned_bits, 0, n, True)
+                    reward = BitFlag(self._pinned_bits, 1, n, False)
+                    return obs, reward, done, {"t": self.t, "obs": obs, "image_obs": None, "done": done,
+                                               "termination_info": ""}
                 kb.step_host(acts, self._dev_actions, rd)
             else:
                 self._dev_actions.copy_(acts, non_blocking=True)

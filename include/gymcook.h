@@ -167,11 +167,15 @@ int gc_env_step(const gc_level* levels, int n_levels, const uint8_t* level_id /*
  * copies the reward/done bytes back into `reward_done_host` and waits for the stream - one call
  * instead of three stream operations plus a synchronisation on the caller's side.  The state
  * stays on the device.  `actions_dev` / `reward_done_dev` are caller-owned device buffers of
- * n * n_agents / n bytes. */
+ * n * n_agents / n bytes.  Results come back as bytes (`reward_done_host`, n bytes, nullable) and/or
+ * as two bit planes per 32 envs (`rd_bits_dev` / `rd_bits_host`, uint32[(n+31)/32][2], nullable
+ * pair: word 0 = done bits, word 1 = reward bits of envs 32w .. 32w+31) - a quarter of the bytes
+ * over PCIe. */
 int gc_env_step_host(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
                      uint32_t* state /*device*/, const uint8_t* actions_host, uint8_t* actions_dev,
-                     uint8_t* reward_done_dev, uint8_t* reward_done_host, uint32_t* collisions /*device*/,
-                     int64_t n, int n_agents, void* stream);
+                     uint8_t* reward_done_dev, uint8_t* reward_done_host, uint32_t* rd_bits_dev,
+                     uint32_t* rd_bits_host, uint32_t* collisions /*device*/, int64_t n, int n_agents,
+                     void* stream);
 
 /* rollout(): `n_steps` fused transitions with uniform-random actions generated in-kernel:
  * action[t][env][agent] = philox4x32-10(key=(seed_lo,seed_hi), ctr=(t0+t, env0+env, agent, 0)).x % 5
