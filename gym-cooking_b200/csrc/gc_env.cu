@@ -286,12 +286,23 @@ struct StepLutParams {
 #ifndef GC_LUT_MIN_CTAS
 #define GC_LUT_MIN_CTAS 4
 #endif
+// The plain step (no optional outputs) fits 40 registers without spilling for <= 2 agents and <= 4
+// objects (6 CTAs of 256 threads per SM) and 48 registers otherwise (5 CTAs; <4,6> spills 12 bytes).
+#ifndef GC_LUT_MIN_CTAS_PLAIN
+#define GC_LUT_MIN_CTAS_PLAIN(NA, NOBJ) (((NA) <= 2 && (NOBJ) <= 4) ? 6 : 5)
+#endif
 #ifndef GC_LUT_THREADS
 #define GC_LUT_THREADS 256
 #endif
+#ifndef GC_LUT_L2_PREFETCH
+#define GC_LUT_L2_PREFETCH 1  // tiles per thread prefetched into L2 ahead of griddepcontrol.wait
+#endif
 constexpr int kLutThreads = GC_LUT_THREADS;  // block size of the single-level table-driven step kernel
-template <int NA, int NOBJ>
-__global__ void __launch_bounds__(kLutThreads, GC_LUT_MIN_CTAS)
+// EXTRAS = false is the plain gym step (state in place + reward/done byte): the optional outputs
+// (hash, collision counters, executed actions) and everything computed only for them drop out of
+// the loop at compile time instead of costing uniform branches and registers.
+template <int NA, int NOBJ, bool EXTRAS>
+__global__ void __launch_bounds__(kLutThreads, EXTRAS ? GC_LUT_MIN_CTAS : GC_LUT_MIN_CTAS_PLAIN(NA, NOBJ))
 step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ state,
                 const uint8_t* __restrict__ actions, uint8_t* __restrict__ reward_done,
                 unsigned long long* __restrict__ hash, uint32_t* __restrict__ collisions,
@@ -312,7 +323,20 @@ step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ sta
   // start (and fill them) while the previous kernel of the stream drains; everything that can
   // have been written by it (state, actions) is read only after griddepcontrol.wait.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  gclut::load_tables(&T, &g_static_tables, P.mv);
+  gclut::load_tables<kLutThreads>(&T, &g_static_tables, P.mv);
+#if GC_LUT_L2_PREFETCH > 0
+  // While the previous kernel drains, pull this CTA's first tiles from DRAM into L2.  L2 is the
+  // coherence point of the device, so a line prefetched there can never be stale: whatever the
+  // previous kernel still writes lands in the same L2 line.  Nothing is READ before the wait.
+#pragma unroll
+  for (int d = 0; d < GC_LUT_L2_PREFETCH; d++) {
+    const uint32_t ip = i + (uint32_t)d * stride;
+    if (ip < n && ip >= i) {
+      if ((threadIdx.x & 7u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(state + ip));
+      if ((threadIdx.x & 31u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(actions + (size_t)ip * NA));
+    }
+  }
+#endif
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (i < n) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + i) : "memory");
@@ -345,11 +369,18 @@ step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ sta
       const uint32_t ncoll = gclut::step<NA, NOBJ>(e, act, T.st, T.mv.v, L, done, success);
       s = gclut::pack<NA, NOBJ>(e, done);
       gc::st_stream(state + i, s);
-      if (collisions && ncoll) collisions[i] += ncoll;
+      if constexpr (EXTRAS) {
+        if (collisions && ncoll) collisions[i] += ncoll;
+      }
     }
-    if (reward_done) reward_done[i] = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
-    if (hash) hash[i] = gc::state_hash<NA>(s);
-    if (executed) store_actions<NA>(executed, i, act);
+    const uint8_t rd = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
+    if constexpr (EXTRAS) {
+      if (reward_done) reward_done[i] = rd;
+      if (hash) hash[i] = gc::state_hash<NA>(s);
+      if (executed) store_actions<NA>(executed, i, act);
+    } else {
+      reward_done[i] = rd;
+    }
   }
 }
 
@@ -377,14 +408,13 @@ step_lut_multi_kernel(const __grid_constant__ GcLevelsDev P, int n_levels, const
   const uint32_t slot = (uint32_t)__cvta_generic_to_shared(&s_stage[threadIdx.x]);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   {
-    const uint4* src = reinterpret_cast<const uint4*>(&g_static_tables);
-    uint4* d4 = reinterpret_cast<uint4*>(&S.st);
-    for (int k = threadIdx.x; k < (int)(sizeof(gclut::StaticTables) / 16); k += blockDim.x) d4[k] = src[k];
+    gclut::load_static_tables<kThreads>(&S.st, &g_static_tables);
     const uint32_t* ls = reinterpret_cast<const uint32_t*>(&P);
     uint32_t* ld = reinterpret_cast<uint32_t*>(S.lv);
-    for (int k = threadIdx.x; k < n_levels * (int)(sizeof(GcLevelDev) / 4); k += blockDim.x) ld[k] = ls[k];
+#pragma unroll 1
+    for (int k = threadIdx.x; k < n_levels * (int)(sizeof(GcLevelDev) / 4); k += kThreads) ld[k] = ls[k];
     __syncthreads();
-    for (int l = 0; l < n_levels; l++) gclut::fill_move_table_dev(S.lv[l], s_mv + l * gclut::kMoveBytes);
+    for (int l = 0; l < n_levels; l++) gclut::fill_move_table_dev<kThreads>(S.lv[l], s_mv + l * gclut::kMoveBytes);
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   uint32_t a_next = 0x04040404u, l_next = 0;
@@ -439,7 +469,7 @@ rollout_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ 
                    uint32_t* __restrict__ collisions, int64_t n, int n_steps, uint32_t t0, int64_t env0,
                    unsigned long long seed) {
   __shared__ __align__(16) gclut::Tables T;
-  gclut::load_tables(&T, &g_static_tables, P.mv);
+  gclut::load_tables<kThreads>(&T, &g_static_tables, P.mv);
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
@@ -495,6 +525,33 @@ inline unsigned lut_grid(int64_t n, int threads = kThreads) {
   return full < cap ? full : (cap ? cap : 1u);
 }
 
+// persistent grid of step_lut_kernel: as many CTAs as are resident at once (occupancy of the
+// instantiation: 5 per SM for the plain step at 48 registers, 4 with the optional outputs), unless
+// GC_LUT_CTAS_PER_SM overrides it
+template <int NA, int NOBJ, bool EXTRAS>
+unsigned lut_step_grid(int64_t n) {
+  static int resident = 0;  // CTAs per device
+  if (!resident) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    const char* e = getenv("GC_LUT_CTAS_PER_SM");
+    if (e) per_sm = atoi(e);
+    if (per_sm < 1 || per_sm > 8) {
+      per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_lut_kernel<NA, NOBJ, EXTRAS>, kLutThreads, 0) !=
+              cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 4;
+      }
+    }
+    resident = sms * per_sm;
+  }
+  const unsigned full = (unsigned)((n + kLutThreads - 1) / kLutThreads);
+  return full < (unsigned)resident ? full : (unsigned)resident;
+}
+
 inline bool use_generic_step() {
   static int v = -1;
   if (v < 0) {
@@ -516,7 +573,6 @@ int launch_step(bool multi, int n_levels, const GcLevelsDev& lv, const uint8_t* 
     fill_move_table(P.lv, &P.mv);
     static const bool pdl = getenv("GC_STEP_NO_PDL") == nullptr;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(lut_grid(n, kLutThreads));
     cfg.blockDim = dim3(kLutThreads);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -528,10 +584,12 @@ int launch_step(bool multi, int n_levels, const GcLevelsDev& lv, const uint8_t* 
     const int64_t slice = (int64_t)1 << 30;
     for (int64_t lo = 0; lo < n; lo += slice) {
       const int64_t m = n - lo < slice ? n - lo : slice;
-      cfg.gridDim = dim3(lut_grid(m, kLutThreads));
+      const bool extras = !rd || h || coll || executed;
+      cfg.gridDim = dim3(extras ? lut_step_grid<NA, NOBJ, true>(m) : lut_step_grid<NA, NOBJ, false>(m));
       const cudaError_t err = cudaLaunchKernelEx(
-          &cfg, step_lut_kernel<NA, NOBJ>, P, s4 + lo, actions + lo * NA, rd ? rd + lo : nullptr, h ? h + lo : nullptr,
-          coll ? coll + lo : nullptr, executed ? executed + lo * NA : nullptr, (uint32_t)m);
+          &cfg, extras ? step_lut_kernel<NA, NOBJ, true> : step_lut_kernel<NA, NOBJ, false>, P, s4 + lo,
+          actions + lo * NA, rd ? rd + lo : nullptr, h ? h + lo : nullptr, coll ? coll + lo : nullptr,
+          executed ? executed + lo * NA : nullptr, (uint32_t)m);
       if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step: launch failed: %s", cudaGetErrorString(err));
     }
     return gc_check_launch("gc_env_step");

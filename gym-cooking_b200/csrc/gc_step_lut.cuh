@@ -217,8 +217,14 @@ __device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], cons
 
 // move[cell*8 + action] = target | kind(target) << 6 from a level's bitboards, filled by the CTA
 // (multi-level batches: one table per level is built in the kernel prologue)
+// NT = threads of the CTA, a compile-time constant: with blockDim.x the loop bounds cost an integer
+// division per loop and ~150 prologue instructions per thread
+template <int NT>
 __device__ __forceinline__ void fill_move_table_dev(const GcLevelDev& L, uint8_t* mv) {
-  for (int k = threadIdx.x; k < kMoveBytes; k += blockDim.x) {
+#pragma unroll
+  for (int k0 = 0; k0 < kMoveBytes; k0 += NT) {
+    const int k = k0 + (int)threadIdx.x;
+    if (kMoveBytes % NT != 0 && k >= kMoveBytes) break;
     const uint32_t c = (uint32_t)k >> 3, a = (uint32_t)k & 7u;
     const uint32_t t = (c + (uint32_t)gc::action_delta(a < 5u ? a : 4u)) & 63u;
     const uint32_t kind = ((L.floor_mask >> t) & 1ull) ? 0u : ((L.cut_mask >> t) & 1ull) ? 2u : ((L.deliv_mask >> t) & 1ull) ? 3u : 1u;
@@ -227,14 +233,29 @@ __device__ __forceinline__ void fill_move_table_dev(const GcLevelDev& L, uint8_t
 }
 
 // cooperative load of the tables into shared memory (call from every thread, then __syncthreads)
-__device__ __forceinline__ void load_tables(Tables* dst, const StaticTables* g_static, const MoveTable& mv_param) {
+template <int NT>
+__device__ __forceinline__ void load_static_tables(StaticTables* dst, const StaticTables* g_static) {
   static_assert(sizeof(StaticTables) % 16 == 0, "vector copy");
+  constexpr int n4 = (int)(sizeof(StaticTables) / 16);
   const uint4* src = reinterpret_cast<const uint4*>(g_static);
-  uint4* d4 = reinterpret_cast<uint4*>(&dst->st);
-  for (int k = threadIdx.x; k < (int)(sizeof(StaticTables) / 16); k += blockDim.x) d4[k] = src[k];
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int k0 = 0; k0 < n4; k0 += NT) {
+    const int k = k0 + (int)threadIdx.x;
+    if (k < n4) d4[k] = src[k];
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void load_tables(Tables* dst, const StaticTables* g_static, const MoveTable& mv_param) {
+  load_static_tables<NT>(&dst->st, g_static);
   const uint32_t* ms = reinterpret_cast<const uint32_t*>(&mv_param);
   uint32_t* md = reinterpret_cast<uint32_t*>(&dst->mv);
-  for (int k = threadIdx.x; k < kMoveBytes / 4; k += blockDim.x) md[k] = ms[k];
+#pragma unroll
+  for (int k0 = 0; k0 < kMoveBytes / 4; k0 += NT) {
+    const int k = k0 + (int)threadIdx.x;
+    if (k < kMoveBytes / 4) md[k] = ms[k];
+  }
 }
 
 }  // namespace gclut
