@@ -252,6 +252,12 @@ pack_rd_kernel(const uint8_t* __restrict__ rd, uint32_t* __restrict__ bits, int6
 
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
+// bit planes from the reward/done bytes, for the step kernels that do not write them themselves
+inline void pack_rd(const uint8_t* rd, uint32_t* bits, int64_t n, cudaStream_t st) {
+  const int64_t words = (n + 31) / 32;
+  pack_rd_kernel<<<(unsigned)((words * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(rd, bits, n);
+}
+
 // Grid of the step kernel.  Measured on B200 (profiles/r01_step_kernel.md): the kernel is bound
 // by the integer ALU pipe, not by DRAM latency, so one env per thread (a full grid) beats a
 // persistent grid-stride loop with register prefetch by ~10 %.  GC_STEP_CTAS_PER_SM=k (1..8)
@@ -301,12 +307,17 @@ constexpr int kLutThreads = GC_LUT_THREADS;  // block size of the single-level t
 // EXTRAS = false is the plain gym step (state in place + reward/done byte): the optional outputs
 // (hash, collision counters, executed actions) and everything computed only for them drop out of
 // the loop at compile time instead of costing uniform branches and registers.
-template <int NA, int NOBJ, bool EXTRAS>
+// BITS (plain step only) also writes the results as two bit planes per 32 envs - rd_bits[2*w] = done,
+// rd_bits[2*w+1] = reward of envs 32w..32w+31, the format gc_env_step_host sends over PCIe - with two
+// ballots per warp; the warp then walks its tiles in lockstep (lanes past n idle but vote).
+template <int NA, int NOBJ, bool EXTRAS, bool BITS>
 __global__ void __launch_bounds__(kLutThreads, EXTRAS ? GC_LUT_MIN_CTAS : GC_LUT_MIN_CTAS_PLAIN(NA, NOBJ))
 step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ state,
                 const uint8_t* __restrict__ actions, uint8_t* __restrict__ reward_done,
                 unsigned long long* __restrict__ hash, uint32_t* __restrict__ collisions,
-                uint8_t* __restrict__ executed, uint32_t n) {  // n < 2^31: the host splits larger batches
+                uint8_t* __restrict__ executed, uint32_t* __restrict__ rd_bits,
+                uint32_t n) {  // n < 2^31: the host splits larger batches
+  static_assert(!(EXTRAS && BITS), "bit planes come with the plain step only");
   __shared__ __align__(16) gclut::Tables T;
   __shared__ __align__(16) uint4 s_stage[kLutThreads];  // each thread's NEXT state, filled by cp.async
   // Persistent CTAs: the 5.9 KB of tables are loaded once per CTA and reused for every env the CTA
@@ -345,9 +356,12 @@ step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ sta
   asm volatile("cp.async.commit_group;" ::: "memory");
   __syncthreads();
   const GcLevelDev& L = P.lv;
-  for (; i < n; i += stride) {
+  const uint32_t lane = threadIdx.x & 31u;
+  for (; BITS ? (i - lane < n) : (i < n); i += stride) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     uint4 s = s_stage[threadIdx.x];  // written by this thread's own cp.async: no CTA barrier needed
+    const bool valid = !BITS || i < n;
+    if (BITS && !valid) s.x = 0x80000000u;  // a lane past the end: nothing to compute, nothing stored
     uint32_t act[NA];
     unpack_actions<NA>(a_next, act);
     const uint32_t inext = i + stride;
@@ -379,7 +393,11 @@ step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ sta
       if (hash) hash[i] = gc::state_hash<NA>(s);
       if (executed) store_actions<NA>(executed, i, act);
     } else {
-      reward_done[i] = rd;
+      if (valid) reward_done[i] = rd;
+      if constexpr (BITS) {
+        const uint32_t d = __ballot_sync(0xffffffffu, done && valid), r = __ballot_sync(0xffffffffu, success && valid);
+        if (lane == 0u) *reinterpret_cast<uint2*>(rd_bits + 2u * (i >> 5)) = make_uint2(d, r);
+      }
     }
   }
 }
@@ -528,7 +546,7 @@ inline unsigned lut_grid(int64_t n, int threads = kThreads) {
 // persistent grid of step_lut_kernel: as many CTAs as are resident at once (occupancy of the
 // instantiation: 5 per SM for the plain step at 48 registers, 4 with the optional outputs), unless
 // GC_LUT_CTAS_PER_SM overrides it
-template <int NA, int NOBJ, bool EXTRAS>
+template <int NA, int NOBJ, bool EXTRAS, bool BITS>
 unsigned lut_step_grid(int64_t n) {
   static int resident = 0;  // CTAs per device
   if (!resident) {
@@ -540,7 +558,7 @@ unsigned lut_step_grid(int64_t n) {
     if (e) per_sm = atoi(e);
     if (per_sm < 1 || per_sm > 8) {
       per_sm = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_lut_kernel<NA, NOBJ, EXTRAS>, kLutThreads, 0) !=
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_lut_kernel<NA, NOBJ, EXTRAS, BITS>, kLutThreads, 0) !=
               cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         per_sm = 4;
@@ -564,7 +582,7 @@ inline bool use_generic_step() {
 template <int NA, int NOBJ>
 int launch_step(bool multi, int n_levels, const GcLevelsDev& lv, const uint8_t* level_id, uint32_t* state,
                 const uint8_t* actions, uint8_t* rd, uint64_t* hash, uint32_t* coll, uint8_t* executed,
-                int64_t n, cudaStream_t st) {
+                uint32_t* rd_bits, int64_t n, cudaStream_t st) {
   auto* s4 = reinterpret_cast<uint4*>(state);
   auto* h = reinterpret_cast<unsigned long long*>(hash);
   if (!multi && !use_generic_step()) {
@@ -585,12 +603,17 @@ int launch_step(bool multi, int n_levels, const GcLevelsDev& lv, const uint8_t* 
     for (int64_t lo = 0; lo < n; lo += slice) {
       const int64_t m = n - lo < slice ? n - lo : slice;
       const bool extras = !rd || h || coll || executed;
-      cfg.gridDim = dim3(extras ? lut_step_grid<NA, NOBJ, true>(m) : lut_step_grid<NA, NOBJ, false>(m));
+      const bool bits = rd_bits && !extras;
+      cfg.gridDim = dim3(extras ? lut_step_grid<NA, NOBJ, true, false>(m)
+                                : bits ? lut_step_grid<NA, NOBJ, false, true>(m) : lut_step_grid<NA, NOBJ, false, false>(m));
       const cudaError_t err = cudaLaunchKernelEx(
-          &cfg, extras ? step_lut_kernel<NA, NOBJ, true> : step_lut_kernel<NA, NOBJ, false>, P, s4 + lo,
-          actions + lo * NA, rd ? rd + lo : nullptr, h ? h + lo : nullptr, coll ? coll + lo : nullptr,
-          executed ? executed + lo * NA : nullptr, (uint32_t)m);
+          &cfg,
+          extras ? step_lut_kernel<NA, NOBJ, true, false>
+                 : bits ? step_lut_kernel<NA, NOBJ, false, true> : step_lut_kernel<NA, NOBJ, false, false>,
+          P, s4 + lo, actions + lo * NA, rd ? rd + lo : nullptr, h ? h + lo : nullptr, coll ? coll + lo : nullptr,
+          executed ? executed + lo * NA : nullptr, bits ? rd_bits + lo / 16 : nullptr, (uint32_t)m);
       if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step: launch failed: %s", cudaGetErrorString(err));
+      if (rd_bits && !bits) pack_rd(rd + lo, rd_bits + lo / 16, m, st);
     }
     return gc_check_launch("gc_env_step");
   }
@@ -616,12 +639,14 @@ int launch_step(bool multi, int n_levels, const GcLevelsDev& lv, const uint8_t* 
           executed ? executed + lo * NA : nullptr, (uint32_t)m);
       if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step: launch failed: %s", cudaGetErrorString(err));
     }
+    if (rd_bits) pack_rd(rd, rd_bits, n, st);
     return gc_check_launch("gc_env_step");
   }
   if (multi)
     step_kernel<NA, NOBJ, true><<<step_grid(n), kThreads, 0, st>>>(lv, level_id, s4, actions, rd, h, coll, executed, n);
   else
     step_kernel<NA, NOBJ, false><<<step_grid(n), kThreads, 0, st>>>(lv, level_id, s4, actions, rd, h, coll, executed, n);
+  if (rd_bits) pack_rd(rd, rd_bits, n, st);
   return gc_check_launch("gc_env_step");
 }
 
@@ -680,9 +705,10 @@ int gc_env_reset(const gc_level* levels, int n_levels, const uint8_t* level_id, 
   return gc_check_launch("gc_env_reset");
 }
 
-int gc_env_step(const gc_level* levels, int n_levels, const uint8_t* level_id, uint32_t* state,
-                const uint8_t* actions, uint8_t* reward_done, uint64_t* hash, uint32_t* collisions,
-                uint8_t* executed, int64_t n, int n_agents, void* stream) {
+// gc_env_step plus the optional bit planes of the results (internal: gc_env_step_host)
+static int env_step_impl(const gc_level* levels, int n_levels, const uint8_t* level_id, uint32_t* state,
+                         const uint8_t* actions, uint8_t* reward_done, uint64_t* hash, uint32_t* collisions,
+                         uint8_t* executed, uint32_t* rd_bits, int64_t n, int n_agents, void* stream) {
   GcLevelsDev lv;
   int max_objs = 0;
   if (int rc = gc_levels_to_dev(levels, n_levels, n_agents, &lv, &max_objs)) return rc;
@@ -691,9 +717,17 @@ int gc_env_step(const gc_level* levels, int n_levels, const uint8_t* level_id, u
   if (n == 0) return GC_OK;
   if (int rc = gc_require_device()) return rc;
   const bool multi = n_levels > 1;
+  if (rd_bits && !reward_done) return gc_fail(GC_E_ARG, "gc_env_step: bit planes need the reward_done buffer");
   GC_DISPATCH_NA_NOBJ(launch_step, multi, n_levels, lv, level_id, state, actions, reward_done, hash, collisions, executed,
-                      n, (cudaStream_t)stream);
+                      rd_bits, n, (cudaStream_t)stream);
   return gc_fail(GC_E_ARG, "gc_env_step: n_agents must be 1..4");
+}
+
+int gc_env_step(const gc_level* levels, int n_levels, const uint8_t* level_id, uint32_t* state,
+                const uint8_t* actions, uint8_t* reward_done, uint64_t* hash, uint32_t* collisions,
+                uint8_t* executed, int64_t n, int n_agents, void* stream) {
+  return env_step_impl(levels, n_levels, level_id, state, actions, reward_done, hash, collisions, executed, nullptr, n,
+                       n_agents, stream);
 }
 
 int gc_env_step_host(const gc_level* levels, int n_levels, const uint8_t* level_id, uint32_t* state,
@@ -710,12 +744,12 @@ int gc_env_step_host(const gc_level* levels, int n_levels, const uint8_t* level_
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemcpyAsync(actions_dev, actions_host, (size_t)n * n_agents, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step_host: copy in failed: %s", cudaGetErrorString(e));
-  if (int rc = gc_env_step(levels, n_levels, level_id, state, actions_dev, reward_done_dev, nullptr, collisions, nullptr,
-                           n, n_agents, stream))
+  const bool want_bits = rd_bits_dev && rd_bits_host;  // two bit planes per 32 envs: a quarter of the bytes over PCIe
+  if (int rc = env_step_impl(levels, n_levels, level_id, state, actions_dev, reward_done_dev, nullptr, collisions, nullptr,
+                             want_bits ? rd_bits_dev : nullptr, n, n_agents, stream))
     return rc;
-  if (rd_bits_dev && rd_bits_host) {  // two bit planes per 32 envs: a quarter of the bytes over PCIe
+  if (want_bits) {
     const int64_t words = (n + 31) / 32;
-    pack_rd_kernel<<<(unsigned)((words * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(reward_done_dev, rd_bits_dev, n);
     e = cudaMemcpyAsync(rd_bits_host, rd_bits_dev, (size_t)words * 8, cudaMemcpyDeviceToHost, st);
   }
   if (e == cudaSuccess && reward_done_host)

@@ -213,3 +213,45 @@ def test_delivery_square_holding_several_objects():
         assert (kb.reward_done.cpu().numpy() == rd).all(), rep
     delivered = [(int(s[1]) & 0xFFFF, int(s[1]) >> 16, int(s[2]) & 0xFFFF) for s in ost]
     assert any(all((x >> 7) & 63 == deliv and (x >> 13) == 0 for x in d) for d in delivered)  # the third dish got there
+
+
+def _planes(rd, n):
+    """done / reward bit planes of a reward_done byte vector, as gc_env_step_host defines them"""
+    words = (n + 31) // 32
+    b = np.zeros(words * 32, dtype=np.uint8)
+    b[:n] = rd
+    w = (1 << np.arange(32, dtype=np.uint64))
+    done = ((b & 1) != 0).reshape(words, 32).astype(np.uint64) @ w
+    rew = ((b & 2) != 0).reshape(words, 32).astype(np.uint64) @ w
+    return np.stack([done, rew], axis=1).astype(np.uint32)
+
+
+@pytest.mark.parametrize("n,kind", [(1000, "plain"), (65536 + 7, "plain"), (31, "plain"), (4099, "collisions"),
+                                    (3001, "multi")])
+def test_step_host_bit_planes(n, kind):
+    """gc_env_step_host's bit planes (written by the step kernel itself on the plain single-level path,
+    by pack_rd_kernel otherwise) equal the packed reward/done bytes, ragged tail included, and the
+    states equal those of the plain device step."""
+    max_t = 12  # short horizon: done bits show up within the run
+    if kind == "multi":
+        names = ["partial-divider_tl", "open-divider_salad"]
+        lid = (torch.arange(n) % 2).to(torch.uint8)
+        mk = lambda: gcb.KitchenBatch(names, 2, n, max_t, level_id=lid)
+    else:
+        mk = lambda: gcb.KitchenBatch("open-divider_tomato", 2, n, max_t, track_collisions=(kind == "collisions"))
+    kb, ref = mk(), mk()
+    acts = ref.random_actions(16, seed=21)
+    words = (n + 31) // 32
+    bits_dev = torch.full((words, 2), -1, dtype=torch.int32, device=kb.device)
+    bits_host = torch.zeros((words, 2), dtype=torch.int32).pin_memory()
+    adev = torch.empty((n, 2), dtype=torch.uint8, device=kb.device)
+    seen_done = 0
+    for s in range(16):
+        kb.step_host(acts[s].cpu().pin_memory(), adev, None, bits_dev, bits_host)
+        ref.step(acts[s])
+        torch.cuda.synchronize()
+        assert torch.equal(kb.state, ref.state) and torch.equal(kb.reward_done, ref.reward_done)
+        expect = _planes(ref.reward_done.cpu().numpy(), n)
+        assert np.array_equal(bits_host.numpy().view(np.uint32), expect), "step %d" % s
+        seen_done += int(expect[:, 0].any())
+    assert seen_done > 0
