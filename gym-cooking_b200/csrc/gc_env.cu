@@ -412,8 +412,8 @@ struct MultiShared {
   GcLevelDev lv[GC_MAX_LEVELS];
 };
 
-template <int NA, int NOBJ>
-__global__ void __launch_bounds__(kThreads, 4)
+template <int NA, int NOBJ, bool EXTRAS>
+__global__ void __launch_bounds__(kThreads, EXTRAS ? 4 : 5)
 step_lut_multi_kernel(const __grid_constant__ GcLevelsDev P, int n_levels, const uint8_t* __restrict__ level_id,
                       uint4* __restrict__ state, const uint8_t* __restrict__ actions,
                       uint8_t* __restrict__ reward_done, unsigned long long* __restrict__ hash,
@@ -470,11 +470,18 @@ step_lut_multi_kernel(const __grid_constant__ GcLevelsDev P, int n_levels, const
       const uint32_t ncoll = gclut::step<NA, NOBJ>(e, act, S.st, s_mv + lvl * gclut::kMoveBytes, L, done, success);
       s = gclut::pack<NA, NOBJ>(e, done);
       gc::st_stream(state + i, s);
-      if (collisions && ncoll) collisions[i] += ncoll;
+      if constexpr (EXTRAS) {
+        if (collisions && ncoll) collisions[i] += ncoll;
+      }
     }
-    if (reward_done) reward_done[i] = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
-    if (hash) hash[i] = gc::state_hash<NA>(s);
-    if (executed) store_actions<NA>(executed, i, act);
+    const uint8_t rd = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
+    if constexpr (EXTRAS) {
+      if (reward_done) reward_done[i] = rd;
+      if (hash) hash[i] = gc::state_hash<NA>(s);
+      if (executed) store_actions<NA>(executed, i, act);
+    } else {
+      reward_done[i] = rd;
+    }
   }
 }
 
@@ -525,24 +532,6 @@ void fill_move_table(const GcLevelDev& L, gclut::MoveTable* mv) {
     }
 }
 
-// persistent grid of the table-driven kernel: GC_LUT_CTAS_PER_SM (default 4 = what fits at 53
-// registers without spilling; measured faster than 6 or 8 CTAs of 40 / 32 registers with spills)
-inline unsigned lut_grid(int64_t n, int threads = kThreads) {
-  static int sms = 0, per_sm = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-    const char* e = getenv("GC_LUT_CTAS_PER_SM");
-    per_sm = e ? atoi(e) : 4;
-    if (per_sm < 1 || per_sm > 8) per_sm = 4;
-  }
-  const unsigned full = (unsigned)((n + threads - 1) / threads);
-  const unsigned cap = (unsigned)(sms * per_sm * kThreads / threads);  // per_sm counts 256-thread CTAs
-  return full < cap ? full : (cap ? cap : 1u);
-}
-
 // persistent grid of step_lut_kernel: as many CTAs as are resident at once (occupancy of the
 // instantiation: 5 per SM for the plain step at 48 registers, 4 with the optional outputs), unless
 // GC_LUT_CTAS_PER_SM overrides it
@@ -567,6 +556,32 @@ unsigned lut_step_grid(int64_t n) {
     resident = sms * per_sm;
   }
   const unsigned full = (unsigned)((n + kLutThreads - 1) / kLutThreads);
+  return full < (unsigned)resident ? full : (unsigned)resident;
+}
+
+template <int NA, int NOBJ, bool EXTRAS>
+unsigned lut_multi_grid(int64_t n, size_t dyn_smem) {
+  static int resident = 0;
+  static size_t resident_smem = 0;
+  if (!resident || resident_smem != dyn_smem) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    const char* e = getenv("GC_LUT_CTAS_PER_SM");
+    if (e) per_sm = atoi(e);
+    if (per_sm < 1 || per_sm > 8) {
+      per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_lut_multi_kernel<NA, NOBJ, EXTRAS>, kThreads,
+                                                        dyn_smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 4;
+      }
+    }
+    resident = sms * per_sm;
+    resident_smem = dyn_smem;
+  }
+  const unsigned full = (unsigned)((n + kThreads - 1) / kThreads);
   return full < (unsigned)resident ? full : (unsigned)resident;
 }
 
@@ -620,9 +635,9 @@ int launch_step(bool multi, int n_levels, const GcLevelsDev& lv, const uint8_t* 
   if (multi && !use_generic_step()) {
     static const bool pdl = getenv("GC_STEP_NO_PDL") == nullptr;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(lut_grid(n));
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = (size_t)n_levels * gclut::kMoveBytes;
+    const bool extras = !rd || h || coll || executed;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -632,9 +647,10 @@ int launch_step(bool multi, int n_levels, const GcLevelsDev& lv, const uint8_t* 
     const int64_t slice = (int64_t)1 << 30;
     for (int64_t lo = 0; lo < n; lo += slice) {
       const int64_t m = n - lo < slice ? n - lo : slice;
-      cfg.gridDim = dim3(lut_grid(m));
+      cfg.gridDim = dim3(extras ? lut_multi_grid<NA, NOBJ, true>(m, cfg.dynamicSmemBytes)
+                                : lut_multi_grid<NA, NOBJ, false>(m, cfg.dynamicSmemBytes));
       const cudaError_t err = cudaLaunchKernelEx(
-          &cfg, step_lut_multi_kernel<NA, NOBJ>, lv, n_levels, level_id + lo, s4 + lo, actions + lo * NA,
+          &cfg, extras ? step_lut_multi_kernel<NA, NOBJ, true> : step_lut_multi_kernel<NA, NOBJ, false>, lv, n_levels, level_id + lo, s4 + lo, actions + lo * NA,
           rd ? rd + lo : nullptr, h ? h + lo : nullptr, coll ? coll + lo : nullptr,
           executed ? executed + lo * NA : nullptr, (uint32_t)m);
       if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step: launch failed: %s", cudaGetErrorString(err));
