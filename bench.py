@@ -320,7 +320,7 @@ def run_ours(args):
                     "steps": e2e_steps,
                     "api": "OvercookedEnvironment(arglist, num_envs=2^20).step(pinned uint8[N][2])"},
             "gpu_launches": timed_launches,
-            "roofline": {"bound": "hbm", "kernel": "step_lut_kernel<2,4> (gc_env_step)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "step_lut_kernel<2,4,EXTRAS=0,BITS=0> (gc_env_step)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "bytes_per_launch": BYTES_PER_ENV_STEP * N_ENVS, "launch_us": launch_s * 1e6,
                          "traffic": traffic},
