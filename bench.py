@@ -272,7 +272,13 @@ def run_ours(args):
     env.reset()
     host_actions = [actions[0][s].cpu().pin_memory() for s in range(8)]
     e2e_steps = max(1, min(args.steps, 400))
-    for s in range(3):
+    # warm-up: one untimed block of the same length.  The first few hundred host-driven steps run up to
+    # 30-45 % slower than the steady state (PCIe link / copy-engine / host ramp; scripts/e2e_numa_probe.py:
+    # blocks of 400 steps measure 1.3-1.8e10, then 2.4e10 for every later block), so 3 steps are not enough
+    e2e_warmup = max(args.warmup, 3, e2e_steps)
+    for s in range(e2e_warmup):
+        if s and s % HORIZON == 0:
+            env.reset()
         env.step(host_actions[s % 8])
     env.reset()
     barrier()
@@ -317,7 +323,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_ENVS * N_AGENTS,
                     "d2h_bytes_per_step": (N_ENVS + 31) // 32 * 8 if env.PACKED_RESULTS else N_ENVS,
                     "results": "done / reward bit planes (2 bits per env)" if env.PACKED_RESULTS else "reward_done bytes",
-                    "steps": e2e_steps,
+                    "steps": e2e_steps, "warmup_steps": e2e_warmup,
                     "api": "OvercookedEnvironment(arglist, num_envs=2^20).step(pinned uint8[N][2])"},
             "gpu_launches": timed_launches,
             "roofline": {"bound": "hbm", "kernel": "step_lut_kernel<2,4,EXTRAS=0,BITS=0> (gc_env_step)", "achieved": achieved,
