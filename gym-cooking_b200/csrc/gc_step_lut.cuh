@@ -84,11 +84,13 @@ struct Tables {
   MoveTable mv;
 };
 
+// Working form of one env: the object slots stay in their packed 16-bit form, slot = place * 128 + mask
+// with place = slot >> 7: the cell of a lying object, (holder << 6) while held, kDeadPlace when dead.
+// One IMAD then moves mask and place of a slot together, and pack / the goal test need no re-assembly.
 template <int NOBJ>
 struct Env {
   uint32_t cell[GC_MAX_AGENTS];
-  uint32_t place[NOBJ];  // slot >> 7: cell of a lying object, (holder << 6) while held, kDeadPlace when dead
-  uint32_t mask[NOBJ];
+  uint32_t sl[NOBJ];
   uint32_t t;
 };
 
@@ -99,11 +101,7 @@ __device__ __forceinline__ void unpack(const uint4& s, Env<NOBJ>& e) {
   e.t = (s.x >> 24) & 127u;
   const uint32_t w[3] = {s.y, s.z, s.w};
 #pragma unroll
-  for (int k = 0; k < NOBJ; k++) {
-    const uint32_t sl = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
-    e.place[k] = sl >> 7;
-    e.mask[k] = sl & 0x7fu;
-  }
+  for (int k = 0; k < NOBJ; k++) e.sl[k] = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
 }
 
 template <int NA, int NOBJ>
@@ -114,9 +112,8 @@ __device__ __forceinline__ uint4 pack(const Env<NOBJ>& e, bool done) {
   uint32_t w[3] = {0xE000E000u, 0xE000E000u, 0xE000E000u};
 #pragma unroll
   for (int k = 0; k < NOBJ; k += 2) {
-    const uint32_t lo = e.place[k] * 128u + e.mask[k];
-    const uint32_t hi = (k + 1 < NOBJ) ? (e.place[k + 1] * 128u + e.mask[k + 1]) : 0xE000u;
-    w[k >> 1] = hi * 65536u + lo;
+    const uint32_t hi = (k + 1 < NOBJ) ? e.sl[k + 1] : 0xE000u;
+    w[k >> 1] = hi * 65536u + e.sl[k];
   }
   return make_uint4(x, w[0], w[1], w[2]);
 }
@@ -169,18 +166,19 @@ __device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], cons
     if (!cancel[i] && kind8[i] != 0u) {          // utils/interact.py:33-89
       const uint32_t hp = (uint32_t)(i + 1) << 6, tg = tgt[i];
       // 0/1 flags per slot once, then every gather / scatter is an IMAD on the (idle) FMA pipe
-      uint32_t fH[NOBJ], fT[NOBJ], mH = 0, mT = 0;
+      uint32_t fH[NOBJ], fT[NOBJ], gH = 0, gT = 0;
 #pragma unroll
       for (int k = 0; k < NOBJ; k++) {
-        fH[k] = e.place[k] == hp ? 1u : 0u;
-        fT[k] = e.place[k] == tg ? 1u : 0u;
-        mH = imad(fH[k], e.mask[k], mH);
-        mT = imad(fT[k], e.mask[k], mT);
+        const uint32_t place = e.sl[k] >> 7;
+        fH[k] = place == hp ? 1u : 0u;
+        fT[k] = place == tg ? 1u : 0u;
+        gH = imad(fH[k], e.sl[k], gH);
+        gT = imad(fT[k], e.sl[k], gT);
       }
       // at most one object is in a hand or lies on a counter / cutboard; a Delivery square may hold
-      // several (interact.py:38), whose masks add up here - keep the table index in range (the
-      // outcome on a Delivery square does not depend on what lies there, and m = p = 0 below)
-      mT &= 0x7Fu;
+      // several (interact.py:38), whose slots add up here - the low 7 bits keep the table index in range
+      // (the outcome on a Delivery square does not depend on what lies there, and m = p = 0 below)
+      const uint32_t mH = gH & 0x7Fu, mT = gT & 0x7Fu;
       const uint32_t idx = S.hprops[mH] + S.tprops[mT] + kind8[i];
       const uint32_t c = S.chop[idx], m = S.merge[idx], d = S.drop[idx], p = S.pick[idx];
       delivered += S.delivered[idx];
@@ -188,12 +186,11 @@ __device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], cons
       // square slot: picked up (square -> hand) or merged away (mask 0, dead place)
       const uint32_t dmaskH = imad(c, mH * 16u, m * mT), dplaceH = d * (tg - hp);
       const uint32_t dmaskT = m * (0u - mT), dplaceT = imad(p, hp - tg, m * (kDeadPlace - tg));
+      const uint32_t dslotH = imad(dplaceH, 128u, dmaskH), dslotT = imad(dplaceT, 128u, dmaskT);
 #pragma unroll
       for (int k = 0; k < NOBJ; k++) {
-        e.mask[k] = imad(fH[k], dmaskH, e.mask[k]);
-        e.mask[k] = imad(fT[k], dmaskT, e.mask[k]);
-        e.place[k] = imad(fH[k], dplaceH, e.place[k]);
-        e.place[k] = imad(fT[k], dplaceT, e.place[k]);
+        e.sl[k] = imad(fH[k], dslotH, e.sl[k]);
+        e.sl[k] = imad(fT[k], dslotT, e.sl[k]);
       }
     }
   }
@@ -205,7 +202,7 @@ __device__ __forceinline__ uint32_t step(Env<NOBJ>& e, uint32_t (&act)[NA], cons
     for (int g = 0; g < GC_MAX_GOALS; g++) {
       bool found = false;
 #pragma unroll
-      for (int k = 0; k < NOBJ; k++) found |= (e.place[k] * 128u + e.mask[k]) == L.goal_slot[g];
+      for (int k = 0; k < NOBJ; k++) found |= e.sl[k] == L.goal_slot[g];
       all_goals &= found;
     }
   }
