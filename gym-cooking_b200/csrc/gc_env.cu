@@ -294,7 +294,9 @@ struct StepLutParams {
 #endif
 // The plain step (no optional outputs) fits 40 registers without spilling for <= 2 agents and <= 4
 // objects (6 CTAs of 256 threads per SM) and 48 registers otherwise (5 CTAs; <4,6> spills 12 bytes).
-#ifndef GC_LUT_MIN_CTAS_PLAIN
+#ifdef GC_LUT_MIN_CTAS_PLAIN_ALL  // experiments: one bound for every instantiation
+#define GC_LUT_MIN_CTAS_PLAIN(NA, NOBJ) (GC_LUT_MIN_CTAS_PLAIN_ALL)
+#else
 #define GC_LUT_MIN_CTAS_PLAIN(NA, NOBJ) (((NA) <= 2 && (NOBJ) <= 4) ? 6 : 5)
 #endif
 #ifndef GC_LUT_THREADS
