@@ -117,13 +117,11 @@ def run_reference_arm(args):
         return  # only rank 0 runs the CPU arm
     cores = os.cpu_count() or 1
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
     import oracle as O
     import gym_cooking_b200 as gcb
     lv = O.parse_level(gcb.levels.level_text(LEVEL), HORIZON)
     st = O.reset_state(lv, N_AGENTS, N_ENVS)
-    rng = np.random.RandomState(SEED)
-    acts = [rng.randint(0, 5, size=(N_ENVS, N_AGENTS)).astype(np.uint8) for _ in range(8)]
+    acts = O.fill_actions(N_ENVS, N_AGENTS, 8, seed=SEED)  # the same philox stream our arm steps with
     k = 0
     for _ in range(args.warmup):
         O.step_batch(lv, st, acts[k % 8], N_AGENTS, n_threads=cores, want_collisions=False)
@@ -178,91 +176,99 @@ def run_ours(args):
     ring = [gcb.KitchenBatch(LEVEL, N_AGENTS, N_ENVS, HORIZON, device=dev) for _ in range(RING)]
     env0 = rank * RING * N_ENVS  # global env indices: results do not depend on the GPU count
     actions = [kb.random_actions(HORIZON, env0=env0 + r * N_ENVS, seed=SEED) for r, kb in enumerate(ring)]
-    local_t = [0] * RING
-    launches = 0
-    # per-step action views made once: at ~12 us per kernel the Python side of a step must stay well
-    # below that, or the loop measures the interpreter instead of the GPU
+    # per-step action views made once: at ~8 us per kernel the Python side of a step must stay well below
+    # that, or a launch loop measures the interpreter instead of the GPU
     views = [[actions[r][t] for t in range(HORIZON)] for r in range(RING)]
+    PERIOD = RING * HORIZON
 
+    # Step k of the run (k = 0, 1, ...) advances batch k % RING with the actions of episode time
+    # (k // RING) % HORIZON; a batch starts new episodes (gc_env_reset) when its episode time wraps.
     def do_step(k):
-        nonlocal launches
-        r = k % RING
-        t = local_t[r]
-        if t == HORIZON:  # every env of this batch has timed out: start new episodes
-            ring[r].reset()
-            t = 0
-            launches += 1  # gc_env_reset (the reward/done memset is torch's, not counted)
+        r, t = k % RING, (k // RING) % HORIZON
+        n = 1
+        if t == 0 and k >= RING:
+            ring[r].reset()  # gc_env_reset (the reward/done memset is torch's, not counted)
+            n = 2
         ring[r].step(views[r][t])
-        local_t[r] = t + 1
-        launches += 1
+        return n
 
     k = 0
     for _ in range(max(args.warmup, 3)):
         do_step(k)
         k += 1
-    # The kernel takes ~12 us; a Python loop that issues one launch per step is at the edge of keeping
-    # the GPU fed (8-10 us of host work per step on a good box, more on a busy one).  So the timed loop
-    # replays CUDA graphs of GRAPH_STEPS consecutive steps (the same launches in the same order: RING
-    # batches round-robin, resets where an episode horizon ends) and issues only the remainder one by
-    # one.  GC_BENCH_NO_GRAPH=1 times the plain loop.
-    GRAPH_T = 25                      # t-values per graph: 25 x RING = 400 steps
-    GRAPH_STEPS = GRAPH_T * RING
-    use_graphs = os.environ.get("GC_BENCH_NO_GRAPH") is None and args.steps >= GRAPH_STEPS
-    graphs = []
-    if use_graphs:
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for q in range(HORIZON // GRAPH_T):
-                g = torch.cuda.CUDAGraph()
-                n_launch = 0
+    # A plain Python loop issuing one launch per step is at the edge of keeping the GPU fed (the kernel takes
+    # ~8 us), so the timed steps are replayed as CUDA graphs - the same launches in the same order - whatever
+    # --steps is: chunks of GRAPH_STEPS consecutive steps aligned to the run's period (4 reusable graphs) plus
+    # one graph each for a ragged head / tail.  Graphs are captured and uploaded (cudaGraphUpload) before the
+    # timed region.  GC_BENCH_NO_GRAPH=1 times the plain loop instead; the other mode's rate is measured
+    # right after the timed region and reported as config.launch_ab.
+    GRAPH_STEPS = 400
+    use_graphs = os.environ.get("GC_BENCH_NO_GRAPH") is None
+    side = torch.cuda.Stream(device=dev)
+    graph_cache = {}
+
+    def capture(k_lo, k_hi):
+        key = (k_lo % PERIOD, k_hi - k_lo, k_lo >= RING)
+        if key not in graph_cache:
+            g = torch.cuda.CUDAGraph()
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
                 with torch.cuda.graph(g, stream=side):
-                    if q == 0:
-                        for kb in ring:
-                            kb.reset()
-                            n_launch += 1
-                    for t in range(q * GRAPH_T, (q + 1) * GRAPH_T):
-                        for r in range(RING):
-                            ring[r].step(views[r][t])
-                            n_launch += 1
-                graphs.append((g, n_launch))
-        torch.cuda.current_stream(dev).wait_stream(side)
-        for r in range(RING):          # the graphs start at t = 0 of every batch (graph 0 resets them)
-            local_t[r] = HORIZON
-        graphs[0][0].replay()          # one untimed replay: graph upload / first-launch costs
-        graphs[1][0].replay()
-        for r in range(RING):
-            local_t[r] = 2 * GRAPH_T
-    barrier()
+                    n = sum(do_step(kk) for kk in range(k_lo, k_hi))
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph_upload(g, torch.cuda.current_stream(dev))
+            graph_cache[key] = (g, n)
+        return graph_cache[key]
+
+    def plan_for(k_lo, k_hi):
+        plan, kk = [], k_lo
+        while kk < k_hi:
+            nxt = min(k_hi, (kk // GRAPH_STEPS + 1) * GRAPH_STEPS)
+            plan.append(capture(kk, nxt))
+            kk = nxt
+        return plan
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), n
+
+    def run_graphs(plan):
+        n = 0
+        for g, n_launch in plan:
+            g.replay()
+            n += n_launch
+        return n
+
+    def run_loop(k_lo, k_hi):
+        return sum(do_step(kk) for kk in range(k_lo, k_hi))
+
+    # capturing a graph does not execute it: the states are where the warm-up left them
+    plan = plan_for(k, k + args.steps) if use_graphs else None
     sampler = ClockSampler(local)
     sampler.start()
-    launches = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    remaining = args.steps
     if use_graphs:
-        q = 2
-        while remaining >= GRAPH_STEPS:
-            g, n_launch = graphs[q % len(graphs)]
-            g.replay()
-            launches += n_launch
-            remaining -= GRAPH_STEPS
-            q += 1
-        for r in range(RING):
-            local_t[r] = (q % len(graphs)) * GRAPH_T if q % len(graphs) else HORIZON
-        k = 0
-    for _ in range(remaining):
-        do_step(k)
-        k += 1
-    e1.record()
-    barrier()
+        ms, timed_launches = timed(lambda: run_graphs(plan))
+    else:
+        ms, timed_launches = timed(lambda: run_loop(k, k + args.steps))
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
+    k += args.steps
+    # the other launch mode over the next `steps` steps (bounded), for the A/B line
+    ab_steps = min(args.steps, 2000)
+    if use_graphs:
+        ab_ms, _ = timed(lambda: run_loop(k, k + ab_steps))
+    else:
+        ab_plan = plan_for(k, k + ab_steps)
+        ab_ms, _ = timed(lambda: run_graphs(ab_plan))
+    k += ab_steps
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, ab_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    timed_launches = launches
+        ms, ab_ms = (float(v) for v in t.tolist())
     value = world * args.steps * N_ENVS * N_AGENTS / (ms * 1e-3)
 
     # ---- end to end through the public API: host actions in, reward/done bytes out, per step ----
@@ -318,15 +324,18 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": dict(workload_config(world), launch=(
-                "CUDA graphs of %d consecutive steps replayed, remainder launched one by one" % GRAPH_STEPS
-                if use_graphs else "one launch per step")), "clocks": clocks,
+                "CUDA graphs of up to %d consecutive steps (captured and uploaded before the timed region)" % GRAPH_STEPS
+                if use_graphs else "one gc_env_step call per step from a Python loop"),
+                launch_ab={"mode": "python loop, one gc_env_step call per step" if use_graphs else "CUDA graphs",
+                           "steps": ab_steps, "us_per_step": ab_ms * 1e3 / ab_steps,
+                           "value": world * ab_steps * N_ENVS * N_AGENTS / (ab_ms * 1e-3)}), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_ENVS * N_AGENTS,
                     "d2h_bytes_per_step": (N_ENVS + 31) // 32 * 8 if env.PACKED_RESULTS else N_ENVS,
                     "results": "done / reward bit planes (2 bits per env)" if env.PACKED_RESULTS else "reward_done bytes",
                     "steps": e2e_steps, "warmup_steps": e2e_warmup,
                     "api": "OvercookedEnvironment(arglist, num_envs=2^20).step(pinned uint8[N][2])"},
             "gpu_launches": timed_launches,
-            "roofline": {"bound": "hbm", "kernel": "step_lut_kernel<2,4,EXTRAS=0,BITS=0> (gc_env_step)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "step2_kernel<NA=2,NOBJ=4,EXTRAS=0,BITS=0,MULTI=0> (gc_env_step, plain step)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "bytes_per_launch": BYTES_PER_ENV_STEP * N_ENVS, "launch_us": launch_s * 1e6,
                          "traffic": traffic},
@@ -340,6 +349,17 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def graph_upload(g, stream):
+    """cudaGraphUpload: move the first-launch cost of a captured graph out of the timed region."""
+    try:
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        rt.cudaGraphUpload.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        return rt.cudaGraphUpload(g.raw_cuda_graph_exec(), stream.cuda_stream) == 0
+    except Exception:
+        return False
 
 
 def hbm_peak_gbs():

@@ -11,6 +11,7 @@ from . import build as _build
 MAX_AGENTS, MAX_OBJECTS, MAX_GOALS, MAX_CELLS, MAX_SUBTASKS, MAX_LEVELS = 4, 6, 4, 64, 32, 16
 STATS_LEN = 133
 SLOT_DEAD = 0xE000
+PLACE_HELD, PLACE_DEAD = 0x40, 0x47
 
 
 class GcError(RuntimeError):
@@ -99,8 +100,8 @@ def load():
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(L, name)  # AttributeError here = header and library disagree
         fn.restype, fn.argtypes = res, args
-    if L.gc_version() != 1:
-        raise GcError("libgymcook.so ABI version %d, expected 1" % L.gc_version())
+    if L.gc_version() != 2:
+        raise GcError("libgymcook.so ABI version %d, expected 2" % L.gc_version())
     _lib = L
     return L
 

@@ -252,10 +252,13 @@ class BatchedDelegation:
 
     def _slots(self, state):
         """(mask, cell, holder) int64[N][6] of the six object slots"""
-        w = state.to(torch.int64) & 0xFFFFFFFF
-        sl = torch.stack([w[:, 1] & 0xFFFF, w[:, 1] >> 16, w[:, 2] & 0xFFFF, w[:, 2] >> 16, w[:, 3] & 0xFFFF,
-                          w[:, 3] >> 16], dim=1)
-        return sl & 0x7F, (sl >> 7) & 63, sl >> 13
+        w = state.to(torch.int64) & 0xFFFFFFFF  # byte planes: include/gymcook.h
+        place = torch.stack([(w[:, 1] >> (8 * k)) & 0xFF for k in range(4)] +
+                            [(w[:, 3] >> (8 * k)) & 0xFF for k in range(2)], dim=1)
+        mask = torch.stack([(w[:, 2] >> (8 * k)) & 0xFF for k in range(4)] +
+                           [(w[:, 3] >> (8 * (k + 2))) & 0xFF for k in range(2)], dim=1)
+        held = place >= 0x40
+        return mask, torch.where(held, torch.zeros_like(place), place), torch.where(held, place & 7, torch.zeros_like(place))
 
     def _agent_cells(self, state):
         w0 = state[:, 0].to(torch.int64) & 0xFFFFFFFF

@@ -55,14 +55,47 @@ struct Env {
   uint32_t t;
 };
 
+// ---- packed state <-> working slots -----------------------------------------------------------
+// In HBM an env keeps its objects as byte planes (include/gymcook.h: word 1 = place bytes of objects
+// 0..3, word 2 = their masks, word 3 = place, place, mask, mask of objects 4 and 5), the form the step
+// kernels compute on (gc_step2.cuh).  The planner / render kernels and the reference form of the step
+// below work on one 16-bit *slot* per object: bits 0-6 mask, 7-12 cell (0 while held), 13-15 holder
+// (0 lying, 1..4 agent, 7 dead; a dead slot is GC_SLOT_DEAD).  The two are converted here and only here.
+__device__ __forceinline__ uint32_t slot_from_bytes(uint32_t place, uint32_t mask) {
+  const uint32_t p9 = (place & GC_PLACE_HELD) ? ((place & 7u) << 6) : place;  // holder << 6 | cell
+  return (p9 << 7) | mask;
+}
+__device__ __forceinline__ uint32_t place_of_slot(uint32_t slot) {
+  const uint32_t holder = slot >> 13;
+  return holder ? (GC_PLACE_HELD | holder) : ((slot >> 7) & 63u);
+}
+// slot of object k (0..5) of a packed state
+__device__ __forceinline__ uint32_t slot_of(const uint4& s, int k) {
+  const uint32_t place = k < 4 ? (s.y >> (8 * k)) : (s.w >> (8 * (k - 4)));
+  const uint32_t mask = k < 4 ? (s.z >> (8 * k)) : (s.w >> (8 * (k - 2)));
+  return slot_from_bytes(place & 0x7Fu, mask & 0x7Fu);
+}
+// the three object words from six slots
+__device__ __forceinline__ void words_from_slots(const uint32_t (&sl)[GC_MAX_OBJECTS], uint32_t& y, uint32_t& z,
+                                                 uint32_t& w) {
+  uint32_t P[GC_MAX_OBJECTS], M[GC_MAX_OBJECTS];
+#pragma unroll
+  for (int k = 0; k < GC_MAX_OBJECTS; k++) {
+    P[k] = place_of_slot(sl[k]);
+    M[k] = sl[k] & 0x7Fu;
+  }
+  y = P[0] | (P[1] << 8) | (P[2] << 16) | (P[3] << 24);
+  z = M[0] | (M[1] << 8) | (M[2] << 16) | (M[3] << 24);
+  w = P[4] | (P[5] << 8) | (M[4] << 16) | (M[5] << 24);
+}
+
 template <int NA, int NOBJ>
 __device__ __forceinline__ void unpack(const uint4& s, Env<NOBJ>& e) {
 #pragma unroll
   for (int i = 0; i < NA; i++) e.cell[i] = (s.x >> (6 * i)) & 63u;
   e.t = (s.x >> 24) & 127u;
-  const uint32_t w[3] = {s.y, s.z, s.w};
 #pragma unroll
-  for (int k = 0; k < NOBJ; k++) e.slot[k] = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+  for (int k = 0; k < NOBJ; k++) e.slot[k] = slot_of(s, k);
 }
 
 template <int NA, int NOBJ>
@@ -70,13 +103,13 @@ __device__ __forceinline__ uint4 pack(const Env<NOBJ>& e, bool done) {
   uint32_t x = (e.t << 24) | (done ? 0x80000000u : 0u);
 #pragma unroll
   for (int i = 0; i < NA; i++) x |= e.cell[i] << (6 * i);
-  uint32_t w[3] = {0xE000E000u, 0xE000E000u, 0xE000E000u};
+  uint32_t sl[GC_MAX_OBJECTS];
 #pragma unroll
-  for (int k = 0; k < NOBJ; k += 2) {
-    uint32_t hi = (k + 1 < NOBJ) ? e.slot[k + 1] : 0xE000u;
-    w[k >> 1] = e.slot[k] | (hi << 16);
-  }
-  return make_uint4(x, w[0], w[1], w[2]);
+  for (int k = 0; k < GC_MAX_OBJECTS; k++) sl[k] = k < NOBJ ? e.slot[k] : GC_SLOT_DEAD;
+  uint4 r;
+  r.x = x;
+  words_from_slots(sl, r.y, r.z, r.w);
+  return r;
 }
 
 // (mask >> c) & 1 for a 64-bit bitboard: one funnel shift (SHF.R.U64) instead of building 1 << c
@@ -214,13 +247,12 @@ __device__ __forceinline__ void cswap(uint32_t& a, uint32_t& b) {
 // Always works on all six slots so that it is independent of the NOBJ specialisation.
 template <int NA>
 __device__ __forceinline__ unsigned long long state_hash(const uint4& s) {
-  const uint32_t w[3] = {s.y, s.z, s.w};
   uint32_t key[GC_MAX_OBJECTS];
   unsigned long long W0 = (unsigned long long)((s.x >> 24) & 127u) << 52;
   uint32_t hm[GC_MAX_AGENTS] = {0, 0, 0, 0};
 #pragma unroll
   for (int k = 0; k < GC_MAX_OBJECTS; k++) {
-    uint32_t sl = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+    uint32_t sl = slot_of(s, k);
     uint32_t holder = sl >> 13;
     uint32_t cell = (sl >> 7) & 63u, held = 0;
 #pragma unroll

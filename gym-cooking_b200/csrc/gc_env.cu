@@ -5,9 +5,12 @@
 // staged through shared memory when envs carry a per-env level id.
 #include "gc_device.cuh"
 #include "gc_host.h"
-#include "gc_step_lut.cuh"
+#include "gc_step2.cuh"
 
 #include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
 
 namespace {
 
@@ -66,7 +69,7 @@ reset_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restri
              uint4* __restrict__ state, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
-  const GcLevelDev& L = levels.lv[level_id ? level_id[i] : 0];
+  const GcLevelDev& L = levels.lv[level_id ? (level_id[i] & (GC_MAX_LEVELS - 1)) : 0];  // in bounds whatever the byte says
   state[i] = make_uint4(L.init[0], L.init[1], L.init[2], L.init[3]);
 }
 
@@ -99,7 +102,7 @@ step_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restric
   uint32_t a_next[NA];
   load_actions<NA>(actions, i, a_next);
   uint32_t lvl_next = 0;
-  if constexpr (MULTI) lvl_next = level_id[i];
+  if constexpr (MULTI) lvl_next = level_id[i] & (GC_MAX_LEVELS - 1);
 
   for (; i < n; i += stride) {
     uint4 s = s_next;
@@ -111,7 +114,7 @@ step_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restric
     if (inext < n) {  // prefetch
       s_next = gc::ld_stream(state + inext);
       load_actions<NA>(actions, inext, a_next);
-      if constexpr (MULTI) lvl_next = level_id[inext];
+      if constexpr (MULTI) lvl_next = level_id[inext] & (GC_MAX_LEVELS - 1);
     }
     const GcLevelDev& L = MULTI ? s_levels[lvl] : levels.lv[0];
 
@@ -155,7 +158,7 @@ rollout_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __rest
   }
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
-  const GcLevelDev& L = MULTI ? s_levels[level_id[i]] : levels.lv[0];
+  const GcLevelDev& L = MULTI ? s_levels[level_id[i] & (GC_MAX_LEVELS - 1)] : levels.lv[0];
 
   uint4 s = gc::ld_stream(state + i);
   gc::Env<NOBJ> e;
@@ -213,7 +216,7 @@ stats_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restri
   unsigned long long v[5] = {0, 0, 0, 0, 0};
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
     const uint32_t w0 = state[i].x;
-    const GcLevelDev& L = levels.lv[level_id ? level_id[i] : 0];
+    const GcLevelDev& L = levels.lv[level_id ? (level_id[i] & (GC_MAX_LEVELS - 1)) : 0];  // in bounds whatever the byte says
     const uint32_t t = (w0 >> 24) & 127u;
     const bool done = w0 >> 31;
     v[0] += 1;
@@ -258,10 +261,9 @@ inline void pack_rd(const uint8_t* rd, uint32_t* bits, int64_t n, cudaStream_t s
   pack_rd_kernel<<<(unsigned)((words * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(rd, bits, n);
 }
 
-// Grid of the step kernel.  Measured on B200 (profiles/r01_step_kernel.md): the kernel is bound
-// by the integer ALU pipe, not by DRAM latency, so one env per thread (a full grid) beats a
-// persistent grid-stride loop with register prefetch by ~10 %.  GC_STEP_CTAS_PER_SM=k (1..8)
-// switches to the persistent form with k CTAs per SM for experiments.
+// Grid of the generic (table-free) step kernel, the reference form kept for GC_STEP_GENERIC=1 and for the
+// A/B tests: one env per thread.  GC_STEP_CTAS_PER_SM=k (1..8) switches it to a persistent grid-stride form
+// with k CTAs per SM for experiments (profiles/r01_step_kernel_v1_ncu.csv is this kernel).
 inline unsigned step_grid(int64_t n) {
   static int sms = 0, per_sm = -1;
   if (per_sm < 0) {
@@ -280,290 +282,281 @@ inline unsigned step_grid(int64_t n) {
 }
 
 // ---------------------------------------------------------------------------------------
-// step, table-driven (single-level batches): see gc_step_lut.cuh
+// step on byte planes (gc_step2.cuh): the default form
 // ---------------------------------------------------------------------------------------
-__device__ const gclut::StaticTables g_static_tables = gclut::make_static_tables();
+// Tables in global memory, built once per (device, level set, n_agents) and cached: a step call passes one
+// pointer instead of rebuilding and shipping 2.6 KB of tables per launch (round 1: 640-byte kernel
+// parameters plus a 512-entry table fill on the host per call made a plain launch loop host-bound).
+struct DeviceTables {
+  gcs2::StaticTables st;
+  gcs2::LevelTables lv[GC_MAX_LEVELS];
+};
+constexpr size_t kTablesHead = sizeof(gcs2::StaticTables);
+__host__ __device__ constexpr size_t tables_bytes(int n_levels) { return kTablesHead + (size_t)n_levels * sizeof(gcs2::LevelTables); }
+static_assert(kTablesHead % 16 == 0 && sizeof(gcs2::LevelTables) % 16 == 0, "tables are copied as uint4");
 
-struct StepLutParams {
-  GcLevelDev lv;
-  gclut::MoveTable mv;
+struct TableCacheEntry {
+  int device, n_levels, n_agents;
+  uint64_t stamp;
+  gc_level levels[GC_MAX_LEVELS];
+  DeviceTables* dev_ptr;
+};
+constexpr int kTableCache = 16;
+TableCacheEntry g_table_cache[kTableCache];
+int g_table_cache_used = 0;
+uint64_t g_table_stamp = 0;
+std::mutex g_table_mutex;
+const gcs2::StaticTables g_static_tables_host = gcs2::make_static_tables();
+
+// device tables for this level set (nullptr + gc_last_error on failure).  The first call for a level set
+// allocates and copies (synchronously: do it outside a stream capture - KitchenBatch's constructor does,
+// through gc_env_reset); later calls are a memcmp.
+const DeviceTables* tables_for(const gc_level* levels, int n_levels, int n_agents) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    gc_fail(GC_E_CUDA, "cudaGetDevice failed");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lock(g_table_mutex);
+  for (int k = 0; k < g_table_cache_used; k++) {
+    TableCacheEntry& e = g_table_cache[k];
+    if (e.device == dev && e.n_levels == n_levels && e.n_agents == n_agents &&
+        memcmp(e.levels, levels, sizeof(gc_level) * (size_t)n_levels) == 0) {
+      e.stamp = ++g_table_stamp;
+      return e.dev_ptr;
+    }
+  }
+  int slot = g_table_cache_used;
+  if (slot == kTableCache) {  // evict the least recently used entry (cudaFree waits for kernels using it)
+    slot = 0;
+    for (int k = 1; k < kTableCache; k++)
+      if (g_table_cache[k].stamp < g_table_cache[slot].stamp) slot = k;
+    cudaSetDevice(g_table_cache[slot].device);
+    cudaFree(g_table_cache[slot].dev_ptr);
+    cudaSetDevice(dev);
+  }
+  static DeviceTables host;  // under the mutex
+  host.st = g_static_tables_host;
+  for (int l = 0; l < n_levels; l++) gcs2::fill_level_tables(levels[l], n_agents, &host.lv[l]);
+  DeviceTables* d = nullptr;
+  cudaError_t err = cudaMalloc(&d, tables_bytes(n_levels));
+  if (err == cudaSuccess) err = cudaMemcpy(d, &host, tables_bytes(n_levels), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    gc_fail(GC_E_CUDA, "level tables: %s (the first step of a level set cannot run inside a stream capture)",
+            cudaGetErrorString(err));
+    cudaGetLastError();
+    if (d) cudaFree(d);
+    if (slot < g_table_cache_used) {  // the evicted entry is gone: compact
+      g_table_cache[slot] = g_table_cache[g_table_cache_used - 1];
+      g_table_cache_used--;
+    }
+    return nullptr;
+  }
+  TableCacheEntry& e = g_table_cache[slot];
+  e.device = dev;
+  e.n_levels = n_levels;
+  e.n_agents = n_agents;
+  e.stamp = ++g_table_stamp;
+  memcpy(e.levels, levels, sizeof(gc_level) * (size_t)n_levels);
+  e.dev_ptr = d;
+  if (slot == g_table_cache_used) g_table_cache_used++;
+  return d;
+}
+
+#ifndef GC_STEP2_THREADS
+#define GC_STEP2_THREADS 256
+#endif
+// resident CTAs per SM the register allocation aims at: 6 (40 registers) for the plain step of <= 2 agents,
+// 5 (48) for 3-4 agents, 4 (64) with the optional outputs (the hash alone needs ~30 live registers)
+#ifdef GC_STEP2_MIN_CTAS_ALL  // experiments: one bound for every instantiation
+#define GC_STEP2_MIN_CTAS(NA, EXTRAS) (GC_STEP2_MIN_CTAS_ALL)
+#else
+#define GC_STEP2_MIN_CTAS(NA, EXTRAS) ((EXTRAS) ? 4 : ((NA) <= 2 ? 6 : 5))
+#endif
+constexpr int kS2Threads = GC_STEP2_THREADS;
+
+struct Step2Args {
+  const DeviceTables* tables;
+  uint4* state;
+  const uint8_t* actions;
+  uint8_t* reward_done;      // plain step: required; with EXTRAS: nullable
+  unsigned long long* hash;  // EXTRAS, nullable
+  uint32_t* collisions;      // EXTRAS, nullable
+  uint8_t* executed;         // EXTRAS, nullable
+  uint32_t* rd_bits;         // BITS
+  const uint8_t* level_id;   // MULTI
+  uint32_t n;                // < 2^31: the host slices larger batches
+  int n_levels;
 };
 
-#ifndef GC_LUT_MIN_CTAS
-#define GC_LUT_MIN_CTAS 4
-#endif
-// The plain step (no optional outputs) fits 40 registers without spilling for <= 2 agents and <= 4
-// objects (6 CTAs of 256 threads per SM) and 48 registers otherwise (5 CTAs; <4,6> spills 12 bytes).
-#ifdef GC_LUT_MIN_CTAS_PLAIN_ALL  // experiments: one bound for every instantiation
-#define GC_LUT_MIN_CTAS_PLAIN(NA, NOBJ) (GC_LUT_MIN_CTAS_PLAIN_ALL)
-#else
-#define GC_LUT_MIN_CTAS_PLAIN(NA, NOBJ) (((NA) <= 2 && (NOBJ) <= 4) ? 6 : 5)
-#endif
-#ifndef GC_LUT_THREADS
-#define GC_LUT_THREADS 256
-#endif
-#ifndef GC_LUT_L2_PREFETCH
-#define GC_LUT_L2_PREFETCH 1  // tiles per thread prefetched into L2 ahead of griddepcontrol.wait
-#endif
-constexpr int kLutThreads = GC_LUT_THREADS;  // block size of the single-level table-driven step kernel
-// EXTRAS = false is the plain gym step (state in place + reward/done byte): the optional outputs
-// (hash, collision counters, executed actions) and everything computed only for them drop out of
-// the loop at compile time instead of costing uniform branches and registers.
+template <int NA>
+__device__ __forceinline__ void store_action_word(uint8_t* __restrict__ out, uint32_t i, uint32_t w) {
+  if constexpr (NA == 1) {
+    out[i] = (uint8_t)w;
+  } else if constexpr (NA == 2) {
+    reinterpret_cast<uint16_t*>(out)[i] = (uint16_t)w;
+  } else if constexpr (NA == 4) {
+    reinterpret_cast<uint32_t*>(out)[i] = w;
+  } else {
+    uint8_t* p = out + (size_t)i * 3;
+    p[0] = (uint8_t)w;
+    p[1] = (uint8_t)(w >> 8);
+    p[2] = (uint8_t)(w >> 16);
+  }
+}
+
+// one env of the persistent loop: transition (or the frozen outcome of a finished episode) and the outputs.
+// EXTRAS = false is the plain gym step (state in place + the reward/done byte): the optional outputs (hash,
+// collision counters, executed actions) and everything computed only for them drop out at compile time.
 // BITS (plain step only) also writes the results as two bit planes per 32 envs - rd_bits[2*w] = done,
 // rd_bits[2*w+1] = reward of envs 32w..32w+31, the format gc_env_step_host sends over PCIe - with two
-// ballots per warp; the warp then walks its tiles in lockstep (lanes past n idle but vote).
+// ballots per warp; lanes past n (valid == false) idle but vote.
 template <int NA, int NOBJ, bool EXTRAS, bool BITS>
-__global__ void __launch_bounds__(kLutThreads, EXTRAS ? GC_LUT_MIN_CTAS : GC_LUT_MIN_CTAS_PLAIN(NA, NOBJ))
-step_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ state,
-                const uint8_t* __restrict__ actions, uint8_t* __restrict__ reward_done,
-                unsigned long long* __restrict__ hash, uint32_t* __restrict__ collisions,
-                uint8_t* __restrict__ executed, uint32_t* __restrict__ rd_bits,
-                uint32_t n) {  // n < 2^31: the host splits larger batches
-  static_assert(!(EXTRAS && BITS), "bit planes come with the plain step only");
-  __shared__ __align__(16) gclut::Tables T;
-  __shared__ __align__(16) uint4 s_stage[kLutThreads];  // each thread's NEXT state, filled by cp.async
-  // Persistent CTAs: the 5.9 KB of tables are loaded once per CTA and reused for every env the CTA
-  // walks (a one-env-per-thread grid spent ~20 % of its instructions refilling them).  DRAM latency
-  // is hidden by software pipelining WITHOUT registers: while a thread computes env i, the 16-byte
-  // state of its next env streams into its private shared-memory slot with cp.async (LDGSTS), and
-  // the next action word waits in one register.  (A register-prefetch variant pushed the kernel
-  // over 32 registers / 100 % occupancy and lost more than it won.)
-  const uint32_t stride = gridDim.x * kLutThreads;  // 32-bit indices: one IMAD.WIDE per address
-  uint32_t i = blockIdx.x * kLutThreads + threadIdx.x;
-  const uint32_t slot = (uint32_t)__cvta_generic_to_shared(&s_stage[threadIdx.x]);
-  uint32_t a_next = 0x04040404u;  // raw action word of the next env (all "stay")
-  // Programmatic dependent launch: the tables do not depend on earlier kernels, so this grid may
-  // start (and fill them) while the previous kernel of the stream drains; everything that can
-  // have been written by it (state, actions) is read only after griddepcontrol.wait.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  gclut::load_tables<kLutThreads>(&T, &g_static_tables, P.mv);
-#if GC_LUT_L2_PREFETCH > 0
-  // While the previous kernel drains, pull this CTA's first tiles from DRAM into L2.  L2 is the
-  // coherence point of the device, so a line prefetched there can never be stale: whatever the
-  // previous kernel still writes lands in the same L2 line.  Nothing is READ before the wait.
-#pragma unroll
-  for (int d = 0; d < GC_LUT_L2_PREFETCH; d++) {
-    const uint32_t ip = i + (uint32_t)d * stride;
-    if (ip < n && ip >= i) {
-      if ((threadIdx.x & 7u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(state + ip));
-      if ((threadIdx.x & 31u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(actions + (size_t)ip * NA));
-    }
-  }
-#endif
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (i < n) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + i) : "memory");
-    a_next = load_actions_raw<NA>(actions, i);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  __syncthreads();
-  const GcLevelDev& L = P.lv;
-  const uint32_t lane = threadIdx.x & 31u;
-  for (; BITS ? (i - lane < n) : (i < n); i += stride) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    uint4 s = s_stage[threadIdx.x];  // written by this thread's own cp.async: no CTA barrier needed
-    const bool valid = !BITS || i < n;
-    if (BITS && !valid) s.x = 0x80000000u;  // a lane past the end: nothing to compute, nothing stored
-    uint32_t act[NA];
-    unpack_actions<NA>(a_next, act);
-    const uint32_t inext = i + stride;
-    if (inext < n) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + inext) : "memory");
-      a_next = load_actions_raw<NA>(actions, inext);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    bool done, success;
-    if (s.x >> 31) {
-      const uint32_t t = (s.x >> 24) & 127u;
-      done = true;
-      success = !(L.max_t != 0u && t >= L.max_t);
-#pragma unroll
-      for (int k = 0; k < NA; k++) act[k] = 4u;
-    } else {
-      gclut::Env<NOBJ> e;
-      gclut::unpack<NA, NOBJ>(s, e);
-      const uint32_t ncoll = gclut::step<NA, NOBJ>(e, act, T.st, T.mv.v, L, done, success);
-      s = gclut::pack<NA, NOBJ>(e, done);
-      gc::st_stream(state + i, s);
-      if constexpr (EXTRAS) {
-        if (collisions && ncoll) collisions[i] += ncoll;
-      }
-    }
-    const uint8_t rd = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
+__device__ __forceinline__ void step2_one(const gcs2::StaticTables& S, const gcs2::LevelTables& L, const Step2Args& A,
+                                          uint4 s, uint32_t aw, uint32_t i, bool valid) {
+  bool done, success;
+  uint32_t exec = 0x04040404u;
+  if (s.x >> 31) {
+    // sticky done: the episode is over, nothing mutates; re-report the stored outcome
+    done = true;
+    success = !(L.max_t24 != 0u && (s.x & 0x7F000000u) >= L.max_t24);
+  } else {
+    gcs2::Env<NOBJ> e;
+    gcs2::unpack<NOBJ>(s.x, s.y, s.z, s.w, e);
+    const uint32_t ncoll = gcs2::step<NA, NOBJ, EXTRAS>(e, aw, S, L, done, success, exec);
+    gcs2::pack<NOBJ>(e, s.x, s.y, s.z, s.w);
+    gc::st_stream(A.state + i, s);
     if constexpr (EXTRAS) {
-      if (reward_done) reward_done[i] = rd;
-      if (hash) hash[i] = gc::state_hash<NA>(s);
-      if (executed) store_actions<NA>(executed, i, act);
-    } else {
-      if (valid) reward_done[i] = rd;
-      if constexpr (BITS) {
-        const uint32_t d = __ballot_sync(0xffffffffu, done && valid), r = __ballot_sync(0xffffffffu, success && valid);
-        if (lane == 0u) *reinterpret_cast<uint2*>(rd_bits + 2u * (i >> 5)) = make_uint2(d, r);
-      }
+      if (A.collisions && ncoll) A.collisions[i] += ncoll;
+    }
+  }
+  const uint8_t rd = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
+  if constexpr (EXTRAS) {
+    if (A.reward_done) A.reward_done[i] = rd;
+    if (A.hash) A.hash[i] = gc::state_hash<NA>(s);
+    if (A.executed) store_action_word<NA>(A.executed, i, exec);
+  } else {
+    if (valid) A.reward_done[i] = rd;
+    if constexpr (BITS) {
+      const uint32_t d = __ballot_sync(0xffffffffu, done && valid), r = __ballot_sync(0xffffffffu, success && valid);
+      if ((threadIdx.x & 31u) == 0u) *reinterpret_cast<uint2*>(A.rd_bits + 2u * (i >> 5)) = make_uint2(d, r);
     }
   }
 }
 
-
-// Table-driven step for multi-level batches (per-env level_id).  Same pipeline as step_lut_kernel;
-// the level tables (64 B of bitboards / goals each) arrive as a kernel parameter, every CTA stages
-// them in shared memory and derives one 512 B move table per level in its prologue - nothing is
-// uploaded per launch.  Dynamic shared memory: n_levels x 512 B.
-struct MultiShared {
-  gclut::StaticTables st;
-  GcLevelDev lv[GC_MAX_LEVELS];
-};
-
-template <int NA, int NOBJ, bool EXTRAS>
-__global__ void __launch_bounds__(kThreads, EXTRAS ? 4 : 5)
-step_lut_multi_kernel(const __grid_constant__ GcLevelsDev P, int n_levels, const uint8_t* __restrict__ level_id,
-                      uint4* __restrict__ state, const uint8_t* __restrict__ actions,
-                      uint8_t* __restrict__ reward_done, unsigned long long* __restrict__ hash,
-                      uint32_t* __restrict__ collisions, uint8_t* __restrict__ executed, uint32_t n) {
-  __shared__ __align__(16) MultiShared S;
-  __shared__ __align__(16) uint4 s_stage[kThreads];
-  extern __shared__ __align__(16) uint8_t s_mv[];  // [n_levels][kMoveBytes]
-  const uint32_t stride = gridDim.x * kThreads;
-  uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-  const uint32_t slot = (uint32_t)__cvta_generic_to_shared(&s_stage[threadIdx.x]);
+// Persistent CTAs (as many as are resident at once) walk tiles of kS2Threads envs with a grid stride; a warp's
+// 32 states are one coalesced 512-byte transaction each way.  The loop is software-pipelined in registers
+// and unrolled by two: the loads of a thread's NEXT env are issued before the current one is computed, so
+// DRAM latency hides behind ~160 instructions of every resident warp.  (Round 1 staged the next state
+// through shared memory with cp.async to save registers; on sm_100a every LDGSTS drags three predicated-off
+// LDS fillers along, and the byte-plane step needs so few registers that five more fit under the
+// 6-CTAs-per-SM bound.)  Programmatic dependent launch: the tables do not depend on earlier kernels, so
+// this grid may start, stage them and prefetch its first tile into L2 while the previous kernel of the
+// stream drains; everything an earlier kernel can have written is read only after griddepcontrol.wait
+// (L2 is the coherence point: a prefetched line cannot be stale).
+template <int NA, int NOBJ, bool EXTRAS, bool BITS, bool MULTI>
+__global__ void __launch_bounds__(kS2Threads, GC_STEP2_MIN_CTAS(NA, EXTRAS))
+step2_kernel(const __grid_constant__ Step2Args A) {
+  static_assert(!(EXTRAS && BITS) && !(MULTI && BITS), "bit planes come with the plain single-level step only");
+  extern __shared__ __align__(16) uint8_t s_tables[];  // StaticTables, then n_levels x LevelTables
+  const gcs2::StaticTables& S = *reinterpret_cast<const gcs2::StaticTables*>(s_tables);
+  const gcs2::LevelTables* LV = reinterpret_cast<const gcs2::LevelTables*>(s_tables + kTablesHead);
+  const uint32_t stride = gridDim.x * kS2Threads;  // 32-bit indices: one IMAD.WIDE per address
+  const uint32_t n = A.n;
+  uint32_t i = blockIdx.x * kS2Threads + threadIdx.x;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   {
-    gclut::load_static_tables<kThreads>(&S.st, &g_static_tables);
-    const uint32_t* ls = reinterpret_cast<const uint32_t*>(&P);
-    uint32_t* ld = reinterpret_cast<uint32_t*>(S.lv);
-#pragma unroll 1
-    for (int k = threadIdx.x; k < n_levels * (int)(sizeof(GcLevelDev) / 4); k += kThreads) ld[k] = ls[k];
-    __syncthreads();
-    for (int l = 0; l < n_levels; l++) gclut::fill_move_table_dev<kThreads>(S.lv[l], s_mv + l * gclut::kMoveBytes);
+    const uint4* src = reinterpret_cast<const uint4*>(A.tables);
+    uint4* dst = reinterpret_cast<uint4*>(s_tables);
+    const int n4 = (int)(tables_bytes(MULTI ? A.n_levels : 1) / 16);
+    for (int k = (int)threadIdx.x; k < n4; k += kS2Threads) dst[k] = __ldg(src + k);
+  }
+  if (i < n) {
+    if ((threadIdx.x & 7u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.state + i));
+    if ((threadIdx.x & 31u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.actions + (size_t)i * NA));
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  uint32_t a_next = 0x04040404u, l_next = 0;
+  const uint4 frozen = make_uint4(0x80000000u, 0u, 0u, 0u);  // a lane past the end: nothing to compute or store
+  uint4 s0 = frozen, s1 = frozen;
+  uint32_t a0 = 0, a1 = 0, l0 = 0, l1 = 0;
   if (i < n) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + i) : "memory");
-    a_next = load_actions_raw<NA>(actions, i);
-    l_next = level_id[i];
+    s0 = gc::ld_stream(A.state + i);
+    a0 = load_actions_raw<NA>(A.actions, i);
+    if constexpr (MULTI) l0 = A.level_id[i];
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
   __syncthreads();
-  for (; i < n; i += stride) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    uint4 s = s_stage[threadIdx.x];
-    uint32_t act[NA];
-    unpack_actions<NA>(a_next, act);
-    const uint32_t lvl = min(l_next, (uint32_t)(n_levels - 1));
-    const uint32_t inext = i + stride;
-    if (inext < n) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(state + inext) : "memory");
-      a_next = load_actions_raw<NA>(actions, inext);
-      l_next = level_id[inext];
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lmax = MULTI ? (uint32_t)(A.n_levels - 1) : 0u;
+  // BITS: the warp walks its tiles in lockstep (every lane votes), so the bound is the warp's first env
+  while (BITS ? (i - lane < n) : (i < n)) {
+    const uint32_t i1 = i + stride;
+    s1 = frozen;
+    if (i1 < n) {
+      s1 = gc::ld_stream(A.state + i1);
+      a1 = load_actions_raw<NA>(A.actions, i1);
+      if constexpr (MULTI) l1 = A.level_id[i1];
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    const GcLevelDev& L = S.lv[lvl];
-    bool done, success;
-    if (s.x >> 31) {
-      const uint32_t t = (s.x >> 24) & 127u;
-      done = true;
-      success = !(L.max_t != 0u && t >= L.max_t);
-#pragma unroll
-      for (int k = 0; k < NA; k++) act[k] = 4u;
-    } else {
-      gclut::Env<NOBJ> e;
-      gclut::unpack<NA, NOBJ>(s, e);
-      const uint32_t ncoll = gclut::step<NA, NOBJ>(e, act, S.st, s_mv + lvl * gclut::kMoveBytes, L, done, success);
-      s = gclut::pack<NA, NOBJ>(e, done);
-      gc::st_stream(state + i, s);
-      if constexpr (EXTRAS) {
-        if (collisions && ncoll) collisions[i] += ncoll;
-      }
+    step2_one<NA, NOBJ, EXTRAS, BITS>(S, LV[MULTI ? min(l0, lmax) : 0u], A, s0, a0, i, !BITS || i < n);
+    if (BITS ? (i1 - lane >= n) : (i1 >= n)) break;
+    i = i1 + stride;
+    s0 = frozen;
+    if (i < n) {
+      s0 = gc::ld_stream(A.state + i);
+      a0 = load_actions_raw<NA>(A.actions, i);
+      if constexpr (MULTI) l0 = A.level_id[i];
     }
-    const uint8_t rd = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
-    if constexpr (EXTRAS) {
-      if (reward_done) reward_done[i] = rd;
-      if (hash) hash[i] = gc::state_hash<NA>(s);
-      if (executed) store_actions<NA>(executed, i, act);
-    } else {
-      reward_done[i] = rd;
-    }
+    step2_one<NA, NOBJ, EXTRAS, BITS>(S, LV[MULTI ? min(l1, lmax) : 0u], A, s1, a1, i1, !BITS || i1 < n);
   }
 }
 
-// Fused rollout, table-driven form (single-level batches): same philox stream and the same
-// transitions as rollout_kernel, with gclut::step instead of gc::step.
+// Fused rollout on byte planes (single-level batches): same philox stream and the same transitions as
+// rollout_kernel, state in registers between steps.
 template <int NA, int NOBJ>
 __global__ void __launch_bounds__(kThreads)
-rollout_lut_kernel(const __grid_constant__ StepLutParams P, uint4* __restrict__ state,
-                   uint8_t* __restrict__ reward_done, unsigned long long* __restrict__ hash_trace,
-                   uint32_t* __restrict__ collisions, int64_t n, int n_steps, uint32_t t0, int64_t env0,
-                   unsigned long long seed) {
-  __shared__ __align__(16) gclut::Tables T;
-  gclut::load_tables<kThreads>(&T, &g_static_tables, P.mv);
+rollout2_kernel(const DeviceTables* __restrict__ tables, uint4* __restrict__ state, uint8_t* __restrict__ reward_done,
+                unsigned long long* __restrict__ hash_trace, uint32_t* __restrict__ collisions, int64_t n,
+                int n_steps, uint32_t t0, int64_t env0, unsigned long long seed) {
+  __shared__ __align__(16) uint8_t s_tables[tables_bytes(1)];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(tables);
+    uint4* dst = reinterpret_cast<uint4*>(s_tables);
+    for (int k = (int)threadIdx.x; k < (int)(tables_bytes(1) / 16); k += kThreads) dst[k] = __ldg(src + k);
+  }
   __syncthreads();
+  const gcs2::StaticTables& S = *reinterpret_cast<const gcs2::StaticTables*>(s_tables);
+  const gcs2::LevelTables& L = *reinterpret_cast<const gcs2::LevelTables*>(s_tables + kTablesHead);
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
-  const GcLevelDev& L = P.lv;
   uint4 s = gc::ld_stream(state + i);
-  gclut::Env<NOBJ> e;
-  gclut::unpack<NA, NOBJ>(s, e);
+  gcs2::Env<NOBJ> e;
+  gcs2::unpack<NOBJ>(s.x, s.y, s.z, s.w, e);
   bool done = s.x >> 31;
-  bool success = done && !(L.max_t != 0u && e.t >= L.max_t);
+  bool success = done && !(L.max_t24 != 0u && (s.x & 0x7F000000u) >= L.max_t24);
   uint32_t ncoll = 0;
   for (int k = 0; k < n_steps; k++) {
     if (!done) {
-      uint32_t r[4], act[NA];
+      uint32_t r[4], aw = 0, exec;
       gc::philox_actions(seed, t0 + (uint32_t)k, (unsigned long long)(env0 + i), r);
 #pragma unroll
-      for (int a = 0; a < NA; a++) act[a] = r[a];
-      ncoll += gclut::step<NA, NOBJ>(e, act, T.st, T.mv.v, L, done, success);
+      for (int a = 0; a < NA; a++) aw |= r[a] << (8 * a);
+      ncoll += gcs2::step<NA, NOBJ, true>(e, aw, S, L, done, success, exec);
     }
-    if (hash_trace) hash_trace[(int64_t)k * n + i] = gc::state_hash<NA>(gclut::pack<NA, NOBJ>(e, done));
+    if (hash_trace) {
+      gcs2::pack<NOBJ>(e, s.x, s.y, s.z, s.w);
+      hash_trace[(int64_t)k * n + i] = gc::state_hash<NA>(s);
+    }
   }
-  gc::st_stream(state + i, gclut::pack<NA, NOBJ>(e, done));
+  gcs2::pack<NOBJ>(e, s.x, s.y, s.z, s.w);
+  gc::st_stream(state + i, s);
   if (reward_done) reward_done[i] = (uint8_t)((done ? GC_RD_DONE : 0) | (success ? GC_RD_REWARD : 0));
   if (collisions && ncoll) collisions[i] += ncoll;
 }
 
-// host: move[cell*8 + action] = target | kind(target) << 6 from the level's bitboards
-void fill_move_table(const GcLevelDev& L, gclut::MoveTable* mv) {
-  static const int delta[5] = {8, -8, -1, 1, 0};
-  for (int c = 0; c < 64; c++)
-    for (int a = 0; a < 8; a++) {
-      const int t = (c + delta[a < 5 ? a : 4]) & 63;
-      const unsigned long long b = 1ull << t;
-      const int kind = (L.floor_mask & b) ? 0 : (L.cut_mask & b) ? 2 : (L.deliv_mask & b) ? 3 : 1;
-      mv->v[c * 8 + a] = (uint8_t)(t | (kind << 6));
-    }
-}
-
-// persistent grid of step_lut_kernel: as many CTAs as are resident at once (occupancy of the
-// instantiation: 5 per SM for the plain step at 48 registers, 4 with the optional outputs), unless
-// GC_LUT_CTAS_PER_SM overrides it
-template <int NA, int NOBJ, bool EXTRAS, bool BITS>
-unsigned lut_step_grid(int64_t n) {
+// persistent grid of step2_kernel: as many CTAs as are resident at once (from the occupancy of the
+// instantiation), unless GC_LUT_CTAS_PER_SM overrides it
+template <int NA, int NOBJ, bool EXTRAS, bool BITS, bool MULTI>
+unsigned step2_grid(int64_t n, size_t dyn_smem) {
   static int resident = 0;  // CTAs per device
-  if (!resident) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-    const char* e = getenv("GC_LUT_CTAS_PER_SM");
-    if (e) per_sm = atoi(e);
-    if (per_sm < 1 || per_sm > 8) {
-      per_sm = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_lut_kernel<NA, NOBJ, EXTRAS, BITS>, kLutThreads, 0) !=
-              cudaSuccess || per_sm < 1) {
-        cudaGetLastError();
-        per_sm = 4;
-      }
-    }
-    resident = sms * per_sm;
-  }
-  const unsigned full = (unsigned)((n + kLutThreads - 1) / kLutThreads);
-  return full < (unsigned)resident ? full : (unsigned)resident;
-}
-
-template <int NA, int NOBJ, bool EXTRAS>
-unsigned lut_multi_grid(int64_t n, size_t dyn_smem) {
-  static int resident = 0;
   static size_t resident_smem = 0;
   if (!resident || resident_smem != dyn_smem) {
     int dev = 0, sms = 0, per_sm = 0;
@@ -574,7 +567,7 @@ unsigned lut_multi_grid(int64_t n, size_t dyn_smem) {
     if (e) per_sm = atoi(e);
     if (per_sm < 1 || per_sm > 8) {
       per_sm = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_lut_multi_kernel<NA, NOBJ, EXTRAS>, kThreads,
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step2_kernel<NA, NOBJ, EXTRAS, BITS, MULTI>, kS2Threads,
                                                         dyn_smem) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         per_sm = 4;
@@ -583,8 +576,24 @@ unsigned lut_multi_grid(int64_t n, size_t dyn_smem) {
     resident = sms * per_sm;
     resident_smem = dyn_smem;
   }
-  const unsigned full = (unsigned)((n + kThreads - 1) / kThreads);
+  const unsigned full = (unsigned)((n + kS2Threads - 1) / kS2Threads);
   return full < (unsigned)resident ? full : (unsigned)resident;
+}
+
+template <int NA, int NOBJ, bool EXTRAS, bool BITS, bool MULTI>
+cudaError_t launch_step2(const Step2Args& A, cudaStream_t st) {
+  static const bool pdl = getenv("GC_STEP_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kS2Threads);
+  cfg.dynamicSmemBytes = tables_bytes(MULTI ? A.n_levels : 1);
+  cfg.gridDim = dim3(step2_grid<NA, NOBJ, EXTRAS, BITS, MULTI>(A.n, cfg.dynamicSmemBytes));
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, step2_kernel<NA, NOBJ, EXTRAS, BITS, MULTI>, A);
 }
 
 inline bool use_generic_step() {
@@ -597,68 +606,44 @@ inline bool use_generic_step() {
 }
 
 template <int NA, int NOBJ>
-int launch_step(bool multi, int n_levels, const GcLevelsDev& lv, const uint8_t* level_id, uint32_t* state,
+int launch_step(const gc_level* levels, int n_levels, const GcLevelsDev& lv, const uint8_t* level_id, uint32_t* state,
                 const uint8_t* actions, uint8_t* rd, uint64_t* hash, uint32_t* coll, uint8_t* executed,
-                uint32_t* rd_bits, int64_t n, cudaStream_t st) {
+                uint32_t* rd_bits, int64_t n, int n_agents, cudaStream_t st) {
   auto* s4 = reinterpret_cast<uint4*>(state);
   auto* h = reinterpret_cast<unsigned long long*>(hash);
-  if (!multi && !use_generic_step()) {
-    StepLutParams P;
-    P.lv = lv.lv[0];
-    fill_move_table(P.lv, &P.mv);
-    static const bool pdl = getenv("GC_STEP_NO_PDL") == nullptr;
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(kLutThreads);
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+  const bool multi = n_levels > 1;
+  if (!use_generic_step()) {
+    const DeviceTables* tables = tables_for(levels, n_levels, n_agents);
+    if (!tables) return GC_E_CUDA;
+    const bool extras = !rd || h || coll || executed;
+    const bool bits = rd_bits && !extras && !multi;  // the plain single-level step writes the bit planes itself
     // the kernel indexes with 32 bits: batches beyond 2^30 envs go in slices
     const int64_t slice = (int64_t)1 << 30;
     for (int64_t lo = 0; lo < n; lo += slice) {
       const int64_t m = n - lo < slice ? n - lo : slice;
-      const bool extras = !rd || h || coll || executed;
-      const bool bits = rd_bits && !extras;
-      cfg.gridDim = dim3(extras ? lut_step_grid<NA, NOBJ, true, false>(m)
-                                : bits ? lut_step_grid<NA, NOBJ, false, true>(m) : lut_step_grid<NA, NOBJ, false, false>(m));
-      const cudaError_t err = cudaLaunchKernelEx(
-          &cfg,
-          extras ? step_lut_kernel<NA, NOBJ, true, false>
-                 : bits ? step_lut_kernel<NA, NOBJ, false, true> : step_lut_kernel<NA, NOBJ, false, false>,
-          P, s4 + lo, actions + lo * NA, rd ? rd + lo : nullptr, h ? h + lo : nullptr, coll ? coll + lo : nullptr,
-          executed ? executed + lo * NA : nullptr, bits ? rd_bits + lo / 16 : nullptr, (uint32_t)m);
+      Step2Args A;
+      A.tables = tables;
+      A.state = s4 + lo;
+      A.actions = actions + lo * NA;
+      A.reward_done = rd ? rd + lo : nullptr;
+      A.hash = h ? h + lo : nullptr;
+      A.collisions = coll ? coll + lo : nullptr;
+      A.executed = executed ? executed + lo * NA : nullptr;
+      A.rd_bits = bits ? rd_bits + lo / 16 : nullptr;
+      A.level_id = multi ? level_id + lo : nullptr;
+      A.n = (uint32_t)m;
+      A.n_levels = n_levels;
+      cudaError_t err;
+      if (multi)
+        err = extras ? launch_step2<NA, NOBJ, true, false, true>(A, st) : launch_step2<NA, NOBJ, false, false, true>(A, st);
+      else if (extras)
+        err = launch_step2<NA, NOBJ, true, false, false>(A, st);
+      else
+        err = bits ? launch_step2<NA, NOBJ, false, true, false>(A, st) : launch_step2<NA, NOBJ, false, false, false>(A, st);
       if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step: launch failed: %s", cudaGetErrorString(err));
       if (rd_bits && !bits) pack_rd(rd + lo, rd_bits + lo / 16, m, st);
     }
-    return gc_check_launch("gc_env_step");
-  }
-  if (multi && !use_generic_step()) {
-    static const bool pdl = getenv("GC_STEP_NO_PDL") == nullptr;
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = (size_t)n_levels * gclut::kMoveBytes;
-    const bool extras = !rd || h || coll || executed;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    const int64_t slice = (int64_t)1 << 30;
-    for (int64_t lo = 0; lo < n; lo += slice) {
-      const int64_t m = n - lo < slice ? n - lo : slice;
-      cfg.gridDim = dim3(extras ? lut_multi_grid<NA, NOBJ, true>(m, cfg.dynamicSmemBytes)
-                                : lut_multi_grid<NA, NOBJ, false>(m, cfg.dynamicSmemBytes));
-      const cudaError_t err = cudaLaunchKernelEx(
-          &cfg, extras ? step_lut_multi_kernel<NA, NOBJ, true> : step_lut_multi_kernel<NA, NOBJ, false>, lv, n_levels, level_id + lo, s4 + lo, actions + lo * NA,
-          rd ? rd + lo : nullptr, h ? h + lo : nullptr, coll ? coll + lo : nullptr,
-          executed ? executed + lo * NA : nullptr, (uint32_t)m);
-      if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step: launch failed: %s", cudaGetErrorString(err));
-    }
-    if (rd_bits) pack_rd(rd, rd_bits, n, st);
-    return gc_check_launch("gc_env_step");
+    return GC_OK;
   }
   if (multi)
     step_kernel<NA, NOBJ, true><<<step_grid(n), kThreads, 0, st>>>(lv, level_id, s4, actions, rd, h, coll, executed, n);
@@ -669,17 +654,17 @@ int launch_step(bool multi, int n_levels, const GcLevelsDev& lv, const uint8_t* 
 }
 
 template <int NA, int NOBJ>
-int launch_rollout(bool multi, const GcLevelsDev& lv, const uint8_t* level_id, uint32_t* state, uint8_t* rd,
-                   uint64_t* hash_trace, uint32_t* coll, int64_t n, int n_steps, int t0, int64_t env0,
-                   uint64_t seed, cudaStream_t st) {
+int launch_rollout(const gc_level* levels, int n_levels, const GcLevelsDev& lv, const uint8_t* level_id, uint32_t* state,
+                   uint8_t* rd, uint64_t* hash_trace, uint32_t* coll, int64_t n, int n_agents, int n_steps, int t0,
+                   int64_t env0, uint64_t seed, cudaStream_t st) {
   auto* s4 = reinterpret_cast<uint4*>(state);
   auto* h = reinterpret_cast<unsigned long long*>(hash_trace);
+  const bool multi = n_levels > 1;
   if (!multi && !use_generic_step()) {
-    StepLutParams P;
-    P.lv = lv.lv[0];
-    fill_move_table(P.lv, &P.mv);
-    rollout_lut_kernel<NA, NOBJ><<<grid_for(n), kThreads, 0, st>>>(P, s4, rd, h, coll, n, n_steps, (uint32_t)t0, env0,
-                                                                   seed);
+    const DeviceTables* tables = tables_for(levels, 1, n_agents);
+    if (!tables) return GC_E_CUDA;
+    rollout2_kernel<NA, NOBJ><<<grid_for(n), kThreads, 0, st>>>(tables, s4, rd, h, coll, n, n_steps, (uint32_t)t0, env0,
+                                                                seed);
     return gc_check_launch("gc_env_rollout");
   }
   if (multi)
@@ -734,10 +719,10 @@ static int env_step_impl(const gc_level* levels, int n_levels, const uint8_t* le
   if (n_levels > 1 && !level_id) return gc_fail(GC_E_ARG, "gc_env_step: n_levels > 1 needs level_id");
   if (n == 0) return GC_OK;
   if (int rc = gc_require_device()) return rc;
-  const bool multi = n_levels > 1;
   if (rd_bits && !reward_done) return gc_fail(GC_E_ARG, "gc_env_step: bit planes need the reward_done buffer");
-  GC_DISPATCH_NA_NOBJ(launch_step, multi, n_levels, lv, level_id, state, actions, reward_done, hash, collisions, executed,
-                      rd_bits, n, (cudaStream_t)stream);
+  if (rd_bits && ((uintptr_t)rd_bits & 7u)) return gc_fail(GC_E_ARG, "gc_env_step_host: rd_bits_dev must be 8-byte aligned");
+  GC_DISPATCH_NA_NOBJ(launch_step, levels, n_levels, lv, level_id, state, actions, reward_done, hash, collisions, executed,
+                      rd_bits, n, n_agents, (cudaStream_t)stream);
   return gc_fail(GC_E_ARG, "gc_env_step: n_agents must be 1..4");
 }
 
@@ -787,9 +772,8 @@ int gc_env_rollout(const gc_level* levels, int n_levels, const uint8_t* level_id
   if (n_levels > 1 && !level_id) return gc_fail(GC_E_ARG, "gc_env_rollout: n_levels > 1 needs level_id");
   if (n == 0) return GC_OK;
   if (int rc = gc_require_device()) return rc;
-  const bool multi = n_levels > 1;
-  GC_DISPATCH_NA_NOBJ(launch_rollout, multi, lv, level_id, state, reward_done, hash_trace, collisions, n, n_steps,
-                      t0, env0, seed, (cudaStream_t)stream);
+  GC_DISPATCH_NA_NOBJ(launch_rollout, levels, n_levels, lv, level_id, state, reward_done, hash_trace, collisions, n,
+                      n_agents, n_steps, t0, env0, seed, (cudaStream_t)stream);
   return gc_fail(GC_E_ARG, "gc_env_rollout: n_agents must be 1..4");
 }
 

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "gc_device.cuh"
+#include "gc_step2.cuh"
 
 static_assert(sizeof(gc_level) == 256, "gc_level is part of the ABI: 256 bytes");
 
@@ -66,14 +67,7 @@ int gc_levels_to_dev(const gc_level* levels, int n_levels, int n_agents, GcLevel
       d.goal_slot[g] = (uint32_t)s.goal_mask[g < s.n_goals ? g : 0] | ((uint32_t)s.delivery_cell << 7);
     d.n_goals = (uint32_t)s.n_goals;
     d.max_t = (uint32_t)s.max_timesteps;
-    uint32_t w0 = 0;
-    for (int i = 0; i < n_agents; i++) w0 |= (uint32_t)(s.agent_cell[i] & 63) << (6 * i);
-    d.init[0] = w0;
-    for (int k = 0; k < GC_MAX_OBJECTS; k += 2) {
-      uint32_t lo = k < s.n_objects ? s.object_init[k] : GC_SLOT_DEAD;
-      uint32_t hi = k + 1 < s.n_objects ? s.object_init[k + 1] : GC_SLOT_DEAD;
-      d.init[1 + k / 2] = lo | (hi << 16);
-    }
+    gcs2::initial_state(s, n_agents, d.init);
     if (s.n_objects > *max_objs) *max_objs = s.n_objects;
   }
   return GC_OK;

@@ -56,10 +56,8 @@ __device__ __forceinline__ void fill_floor_distances(unsigned long long walkable
   }
 }
 
-__device__ __forceinline__ uint32_t slot_of(const uint4& s, int k) {
-  const uint32_t w = k < 2 ? s.y : (k < 4 ? s.z : s.w);
-  return (k & 1) ? (w >> 16) : (w & 0xffffu);
-}
+// working slot (mask | cell << 7 | holder << 13) of object k: the byte planes are decoded in gc_device.cuh
+__device__ __forceinline__ uint32_t slot_of(const uint4& s, int k) { return gc::slot_of(s, k); }
 
 // distance from floor square `from` to graph node (square c, approach a); a == 4 means c is
 // itself a floor square.  kFar where networkx would raise (node missing / no path).

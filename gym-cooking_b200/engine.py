@@ -45,6 +45,11 @@ class KitchenBatch:
             if level_id is None:
                 raise ValueError("several levels need a per-env level_id tensor")
             self.level_id = level_id.to(self.device, torch.uint8).contiguous()
+            # the kernels index the level tables with this byte: check it once, here
+            if self.level_id.shape != (self.num_envs,):
+                raise ValueError("level_id must have one entry per env (%d), got %s" % (self.num_envs, tuple(self.level_id.shape)))
+            if self.num_envs and int(self.level_id.max()) >= self.n_levels:
+                raise ValueError("level_id has values >= n_levels (%d)" % self.n_levels)
         else:
             self.level_id = None
         self.reset()
@@ -101,6 +106,8 @@ class KitchenBatch:
             raise ValueError("actions must be [%d, %d]" % (self.num_envs, self.num_agents))
         if actions.dtype is not torch.uint8 or not actions.is_cuda or not actions.is_contiguous():
             raise _lib.GcError("actions must be a contiguous uint8 CUDA tensor: libgymcook has no CPU path")
+        if actions.device != self.device:
+            raise _lib.GcError("actions are on %s, the batch is on %s" % (actions.device, self.device))
         # hot call: at 2^20 envs the kernel takes ~12 us, so the marshalling is kept to pointer reads
         # (the device guard is entered only when this batch is not on the current device)
         dev = self.device
@@ -129,6 +136,17 @@ class KitchenBatch:
         if actions_host.shape != (self.num_envs, self.num_agents) or actions_host.dtype is not torch.uint8 \
                 or actions_host.is_cuda or not actions_host.is_contiguous():
             raise ValueError("actions_host must be a contiguous uint8 host tensor [%d, %d]" % (self.num_envs, self.num_agents))
+        n_words = (self.num_envs + 31) // 32
+        for name, t, numel, on_dev in (("actions_dev", actions_dev, self.num_envs * self.num_agents, True),
+                                       ("reward_done_host", reward_done_host, self.num_envs, False),
+                                       ("bits_dev", bits_dev, 2 * n_words, True), ("bits_host", bits_host, 2 * n_words, False)):
+            if t is None:
+                continue
+            if t.is_cuda != on_dev or (on_dev and t.device != self.device) or not t.is_contiguous() \
+                    or t.numel() * t.element_size() < numel * (1 if "bits" not in name else 4):
+                raise ValueError("%s: wrong device, layout or size" % name)
+        if bits_dev is not None and bits_dev.data_ptr() % 8:
+            raise ValueError("bits_dev must be 8-byte aligned (the kernel stores one uint2 per 32 envs)")
         dev = self.device
         guard = None
         if torch.cuda.current_device() != dev.index:
@@ -210,10 +228,28 @@ class KitchenBatch:
         return (self.reward_done >> 1) & 1
 
 
+def slots_of_words(words):
+    """The six objects of one packed state (byte planes, include/gymcook.h) as 16-bit working slots
+    mask | cell << 7 | holder << 13 (holder 1..4 = held by that agent, 7 = dead: slot 0xE000)."""
+    w = [int(v) & 0xFFFFFFFF for v in words]
+    place = [(w[1] >> (8 * k)) & 0xFF for k in range(4)] + [(w[3] >> (8 * k)) & 0xFF for k in range(2)]
+    mask = [(w[2] >> (8 * k)) & 0xFF for k in range(4)] + [(w[3] >> (8 * (k + 2))) & 0xFF for k in range(2)]
+    return [(((p & 7) << 13) if p >= _lib.PLACE_HELD else (p << 7)) | m for p, m in zip(place, mask)]
+
+
+def words_from_slots(w0, slots):
+    """Inverse of slots_of_words: word 0 and up to six working slots -> the four packed words."""
+    slots = list(slots) + [_lib.SLOT_DEAD] * (_lib.MAX_OBJECTS - len(slots))
+    place = [(_lib.PLACE_HELD | (s >> 13)) if (s >> 13) else (s >> 7) & 63 for s in slots]
+    mask = [s & 0x7F for s in slots]
+    return [int(w0) & 0xFFFFFFFF, sum(place[k] << (8 * k) for k in range(4)), sum(mask[k] << (8 * k) for k in range(4)),
+            place[4] | place[5] << 8 | mask[4] << 16 | mask[5] << 24]
+
+
 def decode_state(words, num_agents):
     """One packed state (4 ints) -> dict(t, done, agents=[(x, y, hold_mask)], objects=[(mask, x, y, holder)])."""
     w = [int(v) & 0xFFFFFFFF for v in words]
-    slots = [(w[1 + k // 2] >> (16 * (k % 2))) & 0xFFFF for k in range(_lib.MAX_OBJECTS)]
+    slots = slots_of_words(w)
     cells = [(w[0] >> (6 * i)) & 63 for i in range(num_agents)]
     agents = []
     for i, c in enumerate(cells):

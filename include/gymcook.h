@@ -26,16 +26,22 @@
  *   w[0]  bits  0-5   agent-1 cell      bits  6-11 agent-2 cell
  *         bits 12-17  agent-3 cell      bits 18-23 agent-4 cell   (unused agents: 0)
  *         bits 24-30  t (env.t, saturates at 127)                  bit 31 done (sticky)
- *   w[1..3]  six 16-bit object slots, slot k = (w[1 + k/2] >> 16*(k%2)) & 0xffff
- *         bits 0-6   content mask: bit0 Tomato, bit1 Lettuce, bit2 Onion, bit3 Plate present;
- *                                  bit4/5/6 Tomato/Lettuce/Onion chopped
- *         bits 7-12  cell of the object when it lies on a counter/cutboard/delivery square,
- *                    0 while held
- *         bits 13-15 holder: 0 = not held, 1..4 = held by agent-<holder>, 7 = dead slot
- *                    (its contents were merged into another object; whole slot = 0xE000)
- *   Slots are created in level-file scan order (row by row; env.load_level :149-174).  On a
+ *   w[1]  place bytes of objects 0..3 (object k in byte k), w[2] their content-mask bytes,
+ *   w[3]  objects 4 and 5: byte 0 = place 4, byte 1 = place 5, byte 2 = mask 4, byte 3 = mask 5.
+ *         mask byte:  bit0 Tomato, bit1 Lettuce, bit2 Onion, bit3 Plate present;
+ *                     bit4/5/6 Tomato/Lettuce/Onion chopped; bit 7 clear
+ *         place byte: 0..63 = cell of an object lying on a counter/cutboard/delivery square,
+ *                     GC_PLACE_HELD + h (0x41..0x44) = held by agent-<h>,
+ *                     GC_PLACE_DEAD (0x47) = dead object (its contents were merged into another
+ *                     object; mask 0); bit 7 clear
+ *         A state without objects 4 and 5 has w[3] = GC_W3_EMPTY.
+ *   Byte planes are what the step kernel computes on: "which object is in this hand / on this
+ *   square" is one SIMD byte compare over a plane, gathering its mask one dot product (dp4a).
+ *   Objects are created in level-file scan order (row by row; env.load_level :149-174).  On a
  *   merge the HELD object absorbs the counter object (SimAgent.acquire, utils/agent.py:408-414)
- *   so the held slot survives and the counter slot dies.
+ *   so the held object survives and the counter object dies.
+ *   (ABI version 1 packed each object as a 16-bit slot mask | cell << 7 | holder << 13; that form
+ *   survives as gc_level.object_init and as the planners' internal working form.)
  *
  * Canonical item key (used by the hash and by parity tests, independent of slot order):
  *   key = mask<<7 | cell<<1 | held, with cell = holder's cell for held objects; live items
@@ -50,7 +56,7 @@
 extern "C" {
 #endif
 
-#define GC_ABI_VERSION 1
+#define GC_ABI_VERSION 2
 
 #define GC_MAX_AGENTS 4
 #define GC_MAX_OBJECTS 6
@@ -85,6 +91,11 @@ extern "C" {
 #define GC_M_CHOP_L 0x20
 #define GC_M_CHOP_O 0x40
 #define GC_SLOT_DEAD 0xE000u
+/* place byte of an object (packed state words 1..3): 0..63 = the cell it lies on,
+ * GC_PLACE_HELD + h = held by agent-<h> (h = 1..4), GC_PLACE_DEAD = merged into another object */
+#define GC_PLACE_HELD 0x40u
+#define GC_PLACE_DEAD 0x47u
+#define GC_W3_EMPTY 0x00004747u /* word 3 of a state without objects 4 and 5 */
 
 /* subtask kinds (recipe_planner/utils.py:114-162).  GC_ST_NONE is the `None` subtask. */
 #define GC_ST_NONE 0
@@ -119,7 +130,7 @@ typedef struct gc_level {
   int32_t n_subtasks;                    /* filled by gc_level_set_subtasks (host recipe planner) */
   uint8_t cell_type[GC_MAX_CELLS];       /* GC_CELL_*, index y*8+x; cells outside the map = COUNTER */
   uint8_t agent_cell[GC_MAX_AGENTS];     /* start cells (file order) */
-  uint16_t object_init[GC_MAX_OBJECTS];  /* slot encodings at reset; unused = GC_SLOT_DEAD */
+  uint16_t object_init[GC_MAX_OBJECTS];  /* objects at reset: mask | cell << 7; unused = GC_SLOT_DEAD */
   uint8_t goal_mask[GC_MAX_GOALS];       /* content mask that must lie on delivery_cell */
   gc_subtask subtask[GC_MAX_SUBTASKS];   /* recipe subtasks in the host's order */
   uint8_t recipe_code[GC_MAX_GOALS];     /* 1 SimpleTomato 2 SimpleLettuce 3 Salad 4 OnionSalad */
@@ -170,7 +181,7 @@ int gc_env_step(const gc_level* levels, int n_levels, const uint8_t* level_id /*
  * n * n_agents / n bytes.  Results come back as bytes (`reward_done_host`, n bytes, nullable) and/or
  * as two bit planes per 32 envs (`rd_bits_dev` / `rd_bits_host`, uint32[(n+31)/32][2], nullable
  * pair: word 0 = done bits, word 1 = reward bits of envs 32w .. 32w+31) - a quarter of the bytes
- * over PCIe. */
+ * over PCIe.  `rd_bits_dev` must be 8-byte aligned (one 8-byte store per 32 envs). */
 int gc_env_step_host(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
                      uint32_t* state /*device*/, const uint8_t* actions_host, uint8_t* actions_dev,
                      uint8_t* reward_done_dev, uint8_t* reward_done_host, uint32_t* rd_bits_dev,

@@ -304,21 +304,34 @@ int gco_step(const gco_level* lv, gco_env* e, const uint8_t* actions, uint8_t* e
 /* ------------------------------------------------------------------------------------ */
 /* packed form (include/gymcook.h)                                                        */
 
+/* place byte / mask byte of object k (include/gymcook.h: word 1 = places of objects 0..3, word 2 =
+ * their masks, word 3 = place 4, place 5, mask 4, mask 5) */
+static int place_byte(const uint32_t w[4], int k) {
+  return (int)((k < 4 ? w[1] >> (8 * k) : w[3] >> (8 * (k - 4))) & 0xff);
+}
+static int mask_byte(const uint32_t w[4], int k) {
+  return (int)((k < 4 ? w[2] >> (8 * k) : w[3] >> (8 * (k - 2))) & 0xff);
+}
+enum { PLACE_HELD = 0x40, PLACE_DEAD = 0x47 };
+
 void gco_pack(const gco_env* e, uint32_t w[4]) {
   w[0] = w[1] = w[2] = w[3] = 0;
   for (int i = 0; i < e->n_agents; i++) w[0] |= (uint32_t)(e->ag[i].y * 8 + e->ag[i].x) << (6 * i);
   w[0] |= (uint32_t)(e->t & 127) << 24;
   w[0] |= (uint32_t)(e->done ? 1u : 0u) << 31;
   for (int k = 0; k < GCO_MAX_OBJS; k++) {
-    uint32_t s = 0xE000u;
+    uint32_t place = PLACE_DEAD, mask = 0;
     if (k < e->n_objs && e->ob[k].alive) {
       const gco_obj* o = &e->ob[k];
-      if (o->held_by >= 0)
-        s = (uint32_t)o->mask | ((uint32_t)(o->held_by + 1) << 13);
-      else
-        s = (uint32_t)o->mask | ((uint32_t)(o->y * 8 + o->x) << 7);
+      mask = (uint32_t)o->mask;
+      place = o->held_by >= 0 ? (uint32_t)(PLACE_HELD + o->held_by + 1) : (uint32_t)(o->y * 8 + o->x);
     }
-    w[1 + k / 2] |= s << (16 * (k % 2));
+    if (k < 4) {
+      w[1] |= place << (8 * k);
+      w[2] |= mask << (8 * k);
+    } else {
+      w[3] |= (place << (8 * (k - 4))) | (mask << (8 * (k - 2)));
+    }
   }
 }
 
@@ -335,18 +348,18 @@ void gco_unpack(const uint32_t w[4], int n_agents, gco_env* e) {
     e->ag[i].hold = -1;
   }
   for (int k = 0; k < GCO_MAX_OBJS; k++) {
-    uint32_t s = (w[1 + k / 2] >> (16 * (k % 2))) & 0xffff;
+    const int place = place_byte(w, k);
     gco_obj* o = &e->ob[k];
-    int holder = s >> 13;
-    if (holder == 7) {
+    if (place == PLACE_DEAD) {
       o->alive = 0;
       o->held_by = -1;
       continue;
     }
+    const int holder = place >= PLACE_HELD ? place - PLACE_HELD : 0;
     o->alive = 1;
-    o->mask = s & 0x7f;
-    o->x = (s >> 7) & 7;
-    o->y = (s >> 10) & 7;
+    o->mask = mask_byte(w, k);
+    o->x = holder ? 0 : (place & 7);
+    o->y = holder ? 0 : (place >> 3);
     o->held_by = holder - 1;
     if (holder >= 1 && holder <= n_agents) e->ag[holder - 1].hold = k;
   }
@@ -355,15 +368,14 @@ void gco_unpack(const uint32_t w[4], int n_agents, gco_env* e) {
 int gco_canonical_keys(const uint32_t w[4], uint16_t keys[GCO_MAX_OBJS]) {
   int n = 0;
   for (int k = 0; k < GCO_MAX_OBJS; k++) {
-    uint32_t s = (w[1 + k / 2] >> (16 * (k % 2))) & 0xffff;
-    int holder = s >> 13;
-    if (holder == 7) continue;
-    int cell = (s >> 7) & 63, held = 0;
-    if (holder) {
-      cell = (w[0] >> (6 * (holder - 1))) & 63;
+    const int place = place_byte(w, k);
+    if (place == PLACE_DEAD) continue;
+    int cell = place, held = 0;
+    if (place >= PLACE_HELD) {
+      cell = (w[0] >> (6 * (place - PLACE_HELD - 1))) & 63;
       held = 1;
     }
-    keys[n++] = (uint16_t)(((s & 0x7f) << 7) | (cell << 1) | held);
+    keys[n++] = (uint16_t)((mask_byte(w, k) << 7) | (cell << 1) | held);
   }
   for (int i = 1; i < n; i++) { /* insertion sort */
     uint16_t k = keys[i];
@@ -394,10 +406,8 @@ uint64_t gco_hash_packed(const uint32_t w[4], int n_agents) {
   uint64_t W0 = (uint64_t)((w[0] >> 24) & 127) << 52;
   for (int i = 0; i < n_agents; i++) {
     uint64_t cell = (w[0] >> (6 * i)) & 63, hm = 0;
-    for (int k = 0; k < GCO_MAX_OBJS; k++) {
-      uint32_t s = (w[1 + k / 2] >> (16 * (k % 2))) & 0xffff;
-      if ((int)(s >> 13) == i + 1) hm = s & 0x7f;
-    }
+    for (int k = 0; k < GCO_MAX_OBJS; k++)
+      if (place_byte(w, k) == PLACE_HELD + i + 1) hm = (uint64_t)mask_byte(w, k);
     W0 |= (cell | (hm << 6)) << (13 * i);
   }
   uint64_t W1 = (uint64_t)keys[0] | ((uint64_t)keys[1] << 14) | ((uint64_t)keys[2] << 28);
@@ -432,6 +442,16 @@ void gco_philox_actions(uint64_t seed, uint32_t t, uint64_t env, uint8_t out[4])
   uint32_t c[4] = {t, (uint32_t)env, (uint32_t)(env >> 32), 0};
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
   for (int i = 0; i < 4; i++) out[i] = (uint8_t)(((uint64_t)c[i] * 5u) >> 32);
+}
+
+/* the same stream materialised: actions[n_steps][n][n_agents] (the CPU twin of gc_fill_random_actions) */
+void gco_fill_actions(uint8_t* actions, int64_t n, int n_agents, int n_steps, int t0, int64_t env0, uint64_t seed) {
+  for (int k = 0; k < n_steps; k++)
+    for (int64_t i = 0; i < n; i++) {
+      uint8_t a[4];
+      gco_philox_actions(seed, (uint32_t)(t0 + k), (uint64_t)(env0 + i), a);
+      for (int j = 0; j < n_agents; j++) actions[((int64_t)k * n + i) * n_agents + j] = a[j];
+    }
 }
 
 /* ------------------------------------------------------------------------------------ */

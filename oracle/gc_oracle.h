@@ -78,6 +78,9 @@ int gco_canonical_keys(const uint32_t w[4], uint16_t keys[GCO_MAX_OBJS]);
 /* philox4x32-10 action stream shared with gc_env_rollout / gc_fill_random_actions */
 void gco_philox_actions(uint64_t seed, uint32_t t, uint64_t env, uint8_t out[4]);
 
+/* the same stream materialised: actions[n_steps][n][n_agents] */
+void gco_fill_actions(uint8_t* actions, int64_t n, int n_agents, int n_steps, int t0, int64_t env0, uint64_t seed);
+
 /* whole-episode replay from reset (tests) */
 void gco_replay(const gco_level* lv, int n_agents, const uint8_t* actions, int n_steps,
                 uint32_t* states, uint8_t* reward_done, uint8_t* ncoll, uint8_t* executed);

@@ -42,10 +42,8 @@ def pack_env(env):
             slots.append(m | ((i + 1) << 13))
         else:
             slots.append(m | ((y * 8 + x) << 7))
-    slots += [0xE000] * (6 - len(slots))
-    for k, s in enumerate(slots):
-        w[1 + k // 2] |= s << (16 * (k % 2))
-    return w
+    import oracle as O
+    return O.words_of(w[0], slots)
 
 
 def subtask_masks(subtask):

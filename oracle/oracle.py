@@ -143,6 +143,16 @@ def rollout_batch(lv, state, n_agents, n_steps, t0=0, env0=0, seed=1234, n_threa
     return rd, coll, ht
 
 
+def fill_actions(n, n_agents, n_steps, t0=0, env0=0, seed=1234):
+    """uint8[n_steps][n][n_agents]: the philox action stream of cfg-2, materialised on the CPU."""
+    out = np.empty((n_steps, n, n_agents), dtype=np.uint8)
+    L = lib()
+    L.gco_fill_actions.argtypes = [C.POINTER(C.c_uint8), C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_uint64]
+    L.gco_fill_actions.restype = None
+    L.gco_fill_actions(_p(out, C.c_uint8), n, n_agents, n_steps, t0, env0, seed)
+    return out
+
+
 def replay(lv, n_agents, actions):
     """actions uint8[T][4] -> (states uint32[T+1][4], reward_done[T+1], ncoll[T+1], executed[T+1][4])."""
     actions = np.ascontiguousarray(actions, dtype=np.uint8)
@@ -156,6 +166,39 @@ def replay(lv, n_agents, actions):
     return states, rd, nc, ex
 
 
+def slots_of(state):
+    """Packed states uint32[n][4] (byte planes, include/gymcook.h) -> int64[n][6] object slots in the
+    16-bit working form mask | cell << 7 | holder << 13 (holder 7 = dead, slot 0xE000)."""
+    st = np.asarray(state, dtype=np.uint32).astype(np.int64).reshape(-1, 4)
+    place = np.stack([(st[:, 1] >> (8 * k)) & 0xFF for k in range(4)] +
+                     [(st[:, 3] >> (8 * k)) & 0xFF for k in range(2)], axis=1)
+    mask = np.stack([(st[:, 2] >> (8 * k)) & 0xFF for k in range(4)] +
+                    [(st[:, 3] >> (8 * (k + 2))) & 0xFF for k in range(2)], axis=1)
+    return np.where(place >= 0x40, (place & 7) << 13, place << 7) | mask
+
+
+def words_of(w0, slots):
+    """Inverse of slots_of for one env: word 0 and six working slots -> the four packed words."""
+    slots = list(slots) + [0xE000] * (MAX_OBJS - len(slots))
+    place = [(0x40 | (s >> 13)) if (s >> 13) else (s >> 7) & 63 for s in slots]
+    mask = [s & 0x7F for s in slots]
+    w1 = sum(place[k] << (8 * k) for k in range(4))
+    w2 = sum(mask[k] << (8 * k) for k in range(4))
+    w3 = place[4] | place[5] << 8 | mask[4] << 16 | mask[5] << 24
+    return [int(w0) & 0xFFFFFFFF, w1, w2, w3]
+
+
+def v1_to_v2(state):
+    """ABI-1 packed states (six 16-bit slots in words 1..3) -> the byte-plane form; used once, by
+    oracle/convert_golden_v2.py, on the fixtures generated before the layout change."""
+    st = np.asarray(state, dtype=np.uint32).reshape(-1, 4)
+    out = np.empty_like(st)
+    for i in range(st.shape[0]):
+        w = [int(x) for x in st[i]]
+        out[i] = words_of(w[0], [(w[1 + k // 2] >> (16 * (k % 2))) & 0xFFFF for k in range(MAX_OBJS)])
+    return out
+
+
 def decode_batch(state, n_agents):
     """Vectorised `decode`: state uint32[n][4] -> (t[n], done[n], agents[n][n_agents][2],
     keys uint16[n][6] sorted, 0x3FFF padded)."""
@@ -163,8 +206,7 @@ def decode_batch(state, n_agents):
     w0 = state[:, 0].astype(np.int64)
     t = (w0 >> 24) & 127
     done = (w0 >> 31) & 1
-    slots = np.stack([(state[:, 1 + k // 2].astype(np.int64) >> (16 * (k % 2))) & 0xFFFF
-                      for k in range(MAX_OBJS)], axis=1)
+    slots = slots_of(state)
     holder = slots >> 13
     mask = slots & 0x7F
     cells = np.stack([(w0 >> (6 * i)) & 63 for i in range(4)], axis=1)
@@ -207,7 +249,7 @@ def decode(w, n_agents):
     tuple the golden fixtures store."""
     w = [int(x) for x in w]
     t, done = (w[0] >> 24) & 127, (w[0] >> 31) & 1
-    slots = [(w[1 + k // 2] >> (16 * (k % 2))) & 0xFFFF for k in range(MAX_OBJS)]
+    slots = [int(v) for v in slots_of(np.array([w], dtype=np.uint32))[0]]
     agents = []
     for i in range(n_agents):
         hm = 0

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libgymcook.so does not export %s" % name
     assert sorted(_lib.ABI_SYMBOLS) == declared
-    assert lib.gc_version() == 1
+    assert lib.gc_version() == 2
 
 
 def test_level_loader_matches_oracle():

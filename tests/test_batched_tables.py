@@ -85,9 +85,9 @@ def test_alive_mask_and_priors_match_a_python_restatement():
 
 
 def test_plan_cache_key_ignores_time_and_done():
-    w = np.array([[5 | 9 << 6 | 17 << 24 | 1 << 31, 0x12345678, 0x9ABCDEF0, 0xE000E000],
-                  [5 | 9 << 6 | 99 << 24, 0x12345678, 0x9ABCDEF0, 0xE000E000],
-                  [6 | 9 << 6 | 17 << 24, 0x12345678, 0x9ABCDEF0, 0xE000E000]], dtype=np.uint32)
+    w = np.array([[5 | 9 << 6 | 17 << 24 | 1 << 31, 0x12345678, 0x1ABCDEF0, 0x00004747],
+                  [5 | 9 << 6 | 99 << 24, 0x12345678, 0x1ABCDEF0, 0x00004747],
+                  [6 | 9 << 6 | 17 << 24, 0x12345678, 0x1ABCDEF0, 0x00004747]], dtype=np.uint32)
     k = ba.PlanCache.key_of(torch.from_numpy(w.view(np.int32)))
     assert torch.equal(k[0], k[1]) and not torch.equal(k[0], k[2])
     back = k.contiguous().view(torch.int32).numpy().view(np.uint32)

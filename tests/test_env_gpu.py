@@ -66,6 +66,80 @@ def test_golden_traces_bit_exact(traces):
     assert checked > (30000 if meta.shape[0] > 100 else 3000)
 
 
+def test_golden_traces_plain_step(traces):
+    """The same reference episodes through the PLAIN call - kb.step(actions) with no optional output,
+    i.e. step2_kernel<.., EXTRAS=0, BITS=0>, the instantiation bench.py times: states (canonical form), done
+    and reward at every step."""
+    meta, length = traces["meta"], traces["length"]
+    groups = {}
+    for r in range(meta.shape[0]):
+        groups.setdefault((int(meta[r, 0]), int(meta[r, 1]), int(meta[r, 2])), []).append(r)
+    checked = 0
+    for (lvl, n_agents, max_t), rows in sorted(groups.items()):
+        rows = np.array(rows)
+        kb = gcb.KitchenBatch(level_source(str(traces["levels"][lvl]))[1], n_agents, len(rows), max_t)
+        assert kb.collisions is None
+        L = length[rows]
+        for s in range(1, int(L.max()) + 1):
+            kb.step(torch.from_numpy(traces["actions"][rows, s - 1, :n_agents].copy()).to(kb.device))
+            live = L >= s
+            t, done, agents, keys = O.decode_batch(_u32(kb.state), n_agents)
+            assert (t[live] == traces["t"][rows, s][live]).all()
+            assert (agents[live] == traces["agents"][rows, s, :n_agents][live]).all()
+            assert (keys[live] == traces["keys"][rows, s][live]).all()
+            rd = kb.reward_done.cpu().numpy()
+            assert ((rd & 1)[live] == traces["done"][rows, s][live]).all()
+            assert ((rd >> 1)[live] == traces["reward"][rows, s][live]).all()
+            checked += int(live.sum())
+    assert checked > (30000 if meta.shape[0] > 100 else 3000)
+
+
+@pytest.mark.parametrize("level,n_agents", [
+    ("partial-divider_tl", 2), ("full-divider_salad", 3), ("open-divider_salad", 4), ("onion-8x8", 2), ("onion-8x8", 4),
+])
+def test_plain_step_matches_oracle_on_random_batches(level, n_agents):
+    """cfg-2's kernel as bench.py launches it (plain step: no collision counters, hash or executed
+    actions): 65536 envs x 100 uniform-random steps against the oracle, every step."""
+    n = 1 << 16
+    text, src = level_source(level)
+    kb = gcb.KitchenBatch(src, n_agents, n, 100)
+    lv = O.parse_level(text, 100)
+    ost = O.reset_state(lv, n_agents, n)
+    acts = kb.random_actions(100, seed=1234)
+    for s in range(100):
+        kb.step(acts[s])
+        rd, _ = O.step_batch(lv, ost, acts[s].cpu().numpy(), n_agents, n_threads=8, want_collisions=False)
+        assert (_u32(kb.state) == ost).all(), "step %d" % s
+        assert (kb.reward_done.cpu().numpy() == rd).all(), "step %d" % s
+
+
+def test_plain_multi_level_step_matches_oracle():
+    """cfg-5's env half through the plain call: 4 agents, per-env level id over the nine levels plus the
+    6-object custom level in a second batch (step2_kernel<4, 4 / 6, EXTRAS=0, MULTI=1>)."""
+    n, n_agents = 9 * 2048, 4
+    g = torch.Generator().manual_seed(11)
+    for names in (list(gcb.levels.LEVEL_NAMES), ["onion-8x8", "open-divider_salad", "full-divider_tl"]):
+        srcs = [level_source(nm) for nm in names]
+        level_id = torch.randint(0, len(names), (n,), generator=g, dtype=torch.uint8)
+        kb = gcb.KitchenBatch([s[1] for s in srcs], n_agents, n, 100, level_id=level_id)
+        acts = kb.random_actions(100, seed=1236)
+        lid = level_id.numpy()
+        osts, idxs = [], []
+        for l, (text, _) in enumerate(srcs):
+            idx = np.nonzero(lid == l)[0]
+            idxs.append(idx)
+            osts.append((O.parse_level(text, 100), O.reset_state(O.parse_level(text, 100), n_agents, len(idx))))
+        for s in range(100):
+            kb.step(acts[s])
+            a = acts[s].cpu().numpy()
+            got, rd = _u32(kb.state), kb.reward_done.cpu().numpy()
+            for (lv, ost), idx in zip(osts, idxs):
+                ord_, _ = O.step_batch(lv, ost, a[idx], n_agents, n_threads=8, want_collisions=False)
+                if s % 7 == 0 or s == 99:
+                    assert (got[idx] == ost).all(), "step %d" % s
+                    assert (rd[idx] == ord_).all(), "step %d" % s
+
+
 @pytest.mark.parametrize("level,n_agents", [
     ("onion-8x8", 2), ("onion-8x8", 4),
     ("partial-divider_tl", 2), ("full-divider_salad", 3), ("open-divider_salad", 2), ("open-divider_salad", 4),
@@ -200,8 +274,7 @@ def test_delivery_square_holding_several_objects():
     deliv, dish_l = 3 * 8 + 0, 2 | 8 | 32
     full = 0x7F  # every content bit: two of them overflow a 7-bit sum (the table-driven kernel adds masks)
     slots = [full | deliv << 7, full | deliv << 7, dish_l | 1 << 13, 8 | (6 * 8 + 5) << 7]  # goals stay open
-    w = np.array([(3 * 8 + 1) | (1 * 8 + 4) << 6 | 5 << 24, slots[0] | slots[1] << 16, slots[2] | slots[3] << 16,
-                  0xE000E000], dtype=np.uint32)
+    w = np.array(O.words_of((3 * 8 + 1) | (1 * 8 + 4) << 6 | 5 << 24, slots), dtype=np.uint32)
     acts = np.array([[a, b] for a in range(5) for b in range(5)], dtype=np.uint8)
     ost = np.tile(w, (25, 1))
     kb = gcb.KitchenBatch(level, n_agents, 25, 100)
@@ -211,8 +284,8 @@ def test_delivery_square_holding_several_objects():
         rd, _ = O.step_batch(lv, ost, acts, n_agents)
         assert (_u32(kb.state) == ost).all(), rep
         assert (kb.reward_done.cpu().numpy() == rd).all(), rep
-    delivered = [(int(s[1]) & 0xFFFF, int(s[1]) >> 16, int(s[2]) & 0xFFFF) for s in ost]
-    assert any(all((x >> 7) & 63 == deliv and (x >> 13) == 0 for x in d) for d in delivered)  # the third dish got there
+    delivered = O.slots_of(ost)[:, :3]
+    assert (((delivered >> 7) & 63 == deliv) & (delivered >> 13 == 0)).all(axis=1).any()  # the third dish got there
 
 
 def _planes(rd, n):
