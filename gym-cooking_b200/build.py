@@ -6,7 +6,8 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libgymcook.so")
+# GC_LIBGYMCOOK=<path>: load / build another copy of the library (kernel experiments: scripts/build_variants.sh)
+LIB_PATH = os.environ.get("GC_LIBGYMCOOK") or os.path.join(PKG_DIR, "libgymcook.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -27,6 +28,8 @@ def _deps():
 def is_stale():
     if not os.path.exists(LIB_PATH):
         return True
+    if os.environ.get("GC_LIBGYMCOOK"):
+        return False  # an explicitly named copy (a kernel variant) is used as it is
     t = os.path.getmtime(LIB_PATH)
     return any(os.path.getmtime(p) > t for p in _deps())
 

@@ -301,6 +301,10 @@ struct TableCacheEntry {
   gc_level levels[GC_MAX_LEVELS];
   DeviceTables* dev_ptr;
 };
+// Every CTA of a launch copies the tables into its shared memory at the same moment: kTableCopies copies at
+// different addresses spread those reads over the L2 slices instead of queueing ~900 CTAs on the same 59
+// lines (GC_STEP_TABLE_COPIES=1 restores the single copy for A/B timing).
+constexpr int kTableCopies = 32;
 constexpr int kTableCache = 16;
 TableCacheEntry g_table_cache[kTableCache];
 int g_table_cache_used = 0;
@@ -339,8 +343,10 @@ const DeviceTables* tables_for(const gc_level* levels, int n_levels, int n_agent
   host.st = g_static_tables_host;
   for (int l = 0; l < n_levels; l++) gcs2::fill_level_tables(levels[l], n_agents, &host.lv[l]);
   DeviceTables* d = nullptr;
-  cudaError_t err = cudaMalloc(&d, tables_bytes(n_levels));
-  if (err == cudaSuccess) err = cudaMemcpy(d, &host, tables_bytes(n_levels), cudaMemcpyHostToDevice);
+  const size_t stride = tables_bytes(n_levels);
+  cudaError_t err = cudaMalloc(&d, stride * kTableCopies);
+  for (int c = 0; c < kTableCopies && err == cudaSuccess; c++)
+    err = cudaMemcpy(reinterpret_cast<uint8_t*>(d) + c * stride, &host, stride, cudaMemcpyHostToDevice);
   if (err != cudaSuccess) {
     gc_fail(GC_E_CUDA, "level tables: %s (the first step of a level set cannot run inside a stream capture)",
             cudaGetErrorString(err));
@@ -387,6 +393,7 @@ struct Step2Args {
   const uint8_t* level_id;   // MULTI
   uint32_t n;                // < 2^31: the host slices larger batches
   int n_levels;
+  int table_copies;          // copies of the tables behind `tables` (tables_bytes(n_levels) apart)
 };
 
 template <int NA>
@@ -444,6 +451,17 @@ __device__ __forceinline__ void step2_one(const gcs2::StaticTables& S, const gcs
   }
 }
 
+#ifndef GC_STEP2_L2_AHEAD
+#define GC_STEP2_L2_AHEAD 1  // pull the tile after next into L2 while the next one loads into registers (-0.3 us per 2^20-env launch)
+#endif
+template <int NA>
+__device__ __forceinline__ void l2_prefetch(const Step2Args& A, uint32_t i, uint32_t n) {
+  if (i < n) {
+    if ((threadIdx.x & 7u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.state + i));
+    if ((threadIdx.x & 31u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.actions + (size_t)i * NA));
+  }
+}
+
 // Persistent CTAs (as many as are resident at once) walk tiles of kS2Threads envs with a grid stride; a warp's
 // 32 states are one coalesced 512-byte transaction each way.  The loop is software-pipelined in registers
 // and unrolled by two: the loads of a thread's NEXT env are issued before the current one is computed, so
@@ -466,9 +484,9 @@ step2_kernel(const __grid_constant__ Step2Args A) {
   uint32_t i = blockIdx.x * kS2Threads + threadIdx.x;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   {
-    const uint4* src = reinterpret_cast<const uint4*>(A.tables);
-    uint4* dst = reinterpret_cast<uint4*>(s_tables);
     const int n4 = (int)(tables_bytes(MULTI ? A.n_levels : 1) / 16);
+    const uint4* src = reinterpret_cast<const uint4*>(A.tables) + (size_t)(blockIdx.x % (unsigned)A.table_copies) * n4;
+    uint4* dst = reinterpret_cast<uint4*>(s_tables);
     for (int k = (int)threadIdx.x; k < n4; k += kS2Threads) dst[k] = __ldg(src + k);
   }
   if (i < n) {
@@ -477,35 +495,39 @@ step2_kernel(const __grid_constant__ Step2Args A) {
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint4 frozen = make_uint4(0x80000000u, 0u, 0u, 0u);  // a lane past the end: nothing to compute or store
-  uint4 s0 = frozen, s1 = frozen;
-  uint32_t a0 = 0, a1 = 0, l0 = 0, l1 = 0;
+  uint4 s_next = frozen;
+  uint32_t a_next = 0, l_next = 0;
   if (i < n) {
-    s0 = gc::ld_stream(A.state + i);
-    a0 = load_actions_raw<NA>(A.actions, i);
-    if constexpr (MULTI) l0 = A.level_id[i];
+    s_next = gc::ld_stream(A.state + i);
+    a_next = load_actions_raw<NA>(A.actions, i);
+    if constexpr (MULTI) l_next = A.level_id[i];
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lmax = MULTI ? (uint32_t)(A.n_levels - 1) : 0u;
-  // BITS: the warp walks its tiles in lockstep (every lane votes), so the bound is the warp's first env
-  while (BITS ? (i - lane < n) : (i < n)) {
-    const uint32_t i1 = i + stride;
-    s1 = frozen;
-    if (i1 < n) {
-      s1 = gc::ld_stream(A.state + i1);
-      a1 = load_actions_raw<NA>(A.actions, i1);
-      if constexpr (MULTI) l1 = A.level_id[i1];
+  // BITS: the warp walks its tiles in lockstep (every lane votes), so the bound is the warp's first env.
+  // The copies s = s_next, aw = a_next at the top are the point: they read the registers the previous
+  // iteration's loads wrote, so the wait for that data sits BEFORE this iteration's loads are issued.  ptxas
+  // tracks all of a warp's global loads with one counting scoreboard, and waiting on it means "every load
+  // issued so far has landed": with the loads issued first (an unrolled ping-pong of two register sets, the
+  // first version of this loop) the first use of the current state also waited for the loads just issued -
+  // a prefetch distance of zero, 7.3 warps per issue slot parked on the long scoreboard
+  // (profiles/r02_step2_v1_ncu.csv).
+#pragma unroll 1
+  for (; BITS ? (i - lane < n) : (i < n); i += stride) {
+    const uint4 s = s_next;
+    const uint32_t aw = a_next, lvl = l_next;
+    const uint32_t inext = i + stride;
+    if constexpr (BITS) s_next = frozen;
+    if (inext < n) {
+      s_next = gc::ld_stream(A.state + inext);
+      a_next = load_actions_raw<NA>(A.actions, inext);
+      if constexpr (MULTI) l_next = A.level_id[inext];
     }
-    step2_one<NA, NOBJ, EXTRAS, BITS>(S, LV[MULTI ? min(l0, lmax) : 0u], A, s0, a0, i, !BITS || i < n);
-    if (BITS ? (i1 - lane >= n) : (i1 >= n)) break;
-    i = i1 + stride;
-    s0 = frozen;
-    if (i < n) {
-      s0 = gc::ld_stream(A.state + i);
-      a0 = load_actions_raw<NA>(A.actions, i);
-      if constexpr (MULTI) l0 = A.level_id[i];
-    }
-    step2_one<NA, NOBJ, EXTRAS, BITS>(S, LV[MULTI ? min(l1, lmax) : 0u], A, s1, a1, i1, !BITS || i1 < n);
+#if GC_STEP2_L2_AHEAD
+    l2_prefetch<NA>(A, inext + stride, n);
+#endif
+    step2_one<NA, NOBJ, EXTRAS, BITS>(S, LV[MULTI ? min(lvl, lmax) : 0u], A, s, aw, i, !BITS || i < n);
   }
 }
 
@@ -577,7 +599,13 @@ unsigned step2_grid(int64_t n, size_t dyn_smem) {
     resident_smem = dyn_smem;
   }
   const unsigned full = (unsigned)((n + kS2Threads - 1) / kS2Threads);
-  return full < (unsigned)resident ? full : (unsigned)resident;
+  if (full <= (unsigned)resident) return full;
+  static const int balanced = getenv("GC_STEP_BALANCED") ? atoi(getenv("GC_STEP_BALANCED")) : 0;
+  if (balanced) {  // experiment: the same number of tiles for every CTA (k = ceil(tiles / resident))
+    const unsigned k = (full + (unsigned)resident - 1) / (unsigned)resident;
+    return (full + k - 1) / k;
+  }
+  return (unsigned)resident;
 }
 
 template <int NA, int NOBJ, bool EXTRAS, bool BITS, bool MULTI>
@@ -633,6 +661,8 @@ int launch_step(const gc_level* levels, int n_levels, const GcLevelsDev& lv, con
       A.level_id = multi ? level_id + lo : nullptr;
       A.n = (uint32_t)m;
       A.n_levels = n_levels;
+      static const int copies = getenv("GC_STEP_TABLE_COPIES") ? atoi(getenv("GC_STEP_TABLE_COPIES")) : kTableCopies;
+      A.table_copies = copies >= 1 && copies <= kTableCopies ? copies : kTableCopies;
       cudaError_t err;
       if (multi)
         err = extras ? launch_step2<NA, NOBJ, true, false, true>(A, st) : launch_step2<NA, NOBJ, false, false, true>(A, st);

@@ -137,8 +137,13 @@ GC_HD void unpack(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, Env<NOBJ>&
   e.x = w0;
   e.P = w1;
   e.M = w2;
-  e.P2 = w3 & 0xFFFFu;
-  e.M2 = w3 >> 16;
+  if (NOBJ > 4) {
+    e.P2 = w3 & 0xFFFFu;
+    e.M2 = w3 >> 16;
+  } else {
+    e.P2 = w3;  // carried through to pack() untouched (GC_W3_EMPTY in a well-formed state).  Keeping the loaded
+    e.M2 = 0;   // word live matters: a dead fourth register of the prefetching 128-bit load gets reused as a
+  }             // scratch register while the load is in flight, and that write waits for the load (WAW)
 }
 
 // one agent's interaction with the square it faces, branch-free: k8 == 0 (floor ahead, stay, or a vetoed
@@ -254,7 +259,7 @@ GC_HD void pack(const Env<NOBJ>& e, uint32_t& w0, uint32_t& w1, uint32_t& w2, ui
   w0 = e.x;
   w1 = e.P;
   w2 = e.M;
-  w3 = NOBJ > 4 ? (e.P2 | (e.M2 << 16)) : GC_W3_EMPTY;
+  w3 = NOBJ > 4 ? (e.P2 | (e.M2 << 16)) : e.P2;
 }
 
 // the level's reset state in packed form (env.reset :201-250): agents on their start cells, objects lying

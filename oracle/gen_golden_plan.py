@@ -259,9 +259,21 @@ def _bd_job(args):
             env.step({names[i]: DELTA[a] for i, a in enumerate(acts)})
     except (AssertionError, AttributeError):
         return None
-    calls, soft = [], []
+    calls, soft, rowrec = [], [], []
     real_softmax = bd.sp.special.softmax
     real_pna = dele.prob_nav_actions
+    real_q = brtdp.E2E_BRTDP.Q  # patched on the class: get_other_agent_planners copy.copy()s the planner
+    q_actions = []
+    state_tm1 = pack_env(env.obs_tm1)
+    executed = [DELTA.index(tuple(env.agent_actions[nm])) for nm in names]
+
+    def rec_q(self, state, action, value_f):
+        if self is planner:
+            q_actions.append(action)
+        return real_q(self, state=state, action=action, value_f=value_f)
+
+    def act_code(a, joint):
+        return 5 * DELTA.index(tuple(a[0])) + DELTA.index(tuple(a[1])) if joint else DELTA.index(tuple(a))
 
     def rec_softmax(x, *a, **k):
         out = real_softmax(x, *a, **k)
@@ -270,13 +282,28 @@ def _bd_job(args):
 
     def rec_pna(**kw):
         n0 = len(soft)
+        del q_actions[:]
         p = real_pna(**kw)
         assert len(soft) == n0 + 1
         calls.append((kw["subtask"], tuple(kw["subtask_agent_names"]), float(p), soft[-1]))
+        # the row construction, observed: prob_nav_actions calls planner.Q once for the taken action
+        # (bd:665) and then once per (filtered) valid action, in order (bd:681-683)
+        st, ag = kw["subtask"], tuple(kw["subtask_agent_names"])
+        idx = [names.index(a) for a in ag]
+        if st is None:
+            rowrec.append(dict(kind=0, masks=(0, 0, 0, 0), i=idx[0], j=255, level1=0, valid=[], n_valid=len(soft[-1][0])))
+        else:
+            joint = len(ag) == 2
+            valid = [act_code(a, joint) for a in q_actions[1:]]
+            assert len(valid) == len(soft[-1][0]) and act_code(q_actions[0], joint) in valid
+            rowrec.append(dict(kind=2 if joint else 1, masks=subtask_masks(st), i=idx[0], j=idx[1] if joint else 255,
+                               level1=int(planner.planner_level == brtdp.PlannerLevel.LEVEL1),
+                               valid=valid, n_valid=len(valid)))
         return p
 
     bd.sp.special.softmax = rec_softmax
     dele.prob_nav_actions = rec_pna
+    brtdp.E2E_BRTDP.Q = rec_q
     prior_keys = list(keys)
     prior = dict(dele.probs.probs)
     t0 = time.time()
@@ -287,13 +314,16 @@ def _bd_job(args):
         return None
     finally:
         bd.sp.special.softmax = real_softmax
+        brtdp.E2E_BRTDP.Q = real_q
     post = dict(dele.probs.probs)
     # distinct likelihood rows
-    pair_index, pair_rows = {}, []
-    for (st, agents, p, (x, out)) in calls:
+    pair_index, pair_rows, rows_out = {}, [], []
+    for (st, agents, p, (x, out)), rr in zip(calls, rowrec):
         key = (str(st), agents)
         if key in pair_index:
             continue
+        rr["act_idx"] = int(np.argmin(np.abs(out - p)))
+        rows_out.append(rr)
         act_idx = int(np.argmin(np.abs(out - p)))
         assert abs(out[act_idx] - p) < 1e-15
         pair_index[key] = len(pair_rows)
@@ -310,7 +340,8 @@ def _bd_job(args):
                 entries.append(pair_index[(str(t.subtask), tuple(t.subtask_agent_names))])
         hyps.append((prior[k], alive, entries, post.get(k, 0.0)))
     return dict(level=level, n_agents=n_agents, model=model, observer=observer, hyps=hyps, pairs=pair_rows,
-                seconds=time.time() - t0, n_calls=len(calls))
+                seconds=time.time() - t0, n_calls=len(calls), rows=rows_out, state=state_tm1, executed=executed,
+                subtasks=[subtask_masks(t) for t in env.all_subtasks])
 
 
 def gen_bd():
@@ -351,6 +382,42 @@ def gen_bd():
                         n_valid=n_valid, act_idx=act_idx)
     print("bd posteriors:", n, "updates; H<=%d P<=%d A<=%d; total s %.0f" % (H_max, P_max, A_max,
                                                                                  sum(r["seconds"] for r in res)))
+    # the row construction of prob_nav_actions (bd:618-689) for the same calls: obs_tm1, the executed joint
+    # action, and per likelihood row the reference's (filtered) valid-action list and taken-action index
+    levels = sorted(set(r["level"] for r in res))
+    S_max = max(len(r["subtasks"]) for r in res)
+    job_level = np.array([levels.index(r["level"]) for r in res], dtype=np.uint8)
+    job_agents = np.array([r["n_agents"] for r in res], dtype=np.uint8)
+    job_observer = np.array([r["observer"] for r in res], dtype=np.uint8)
+    job_model = np.array([r["model"] for r in res])
+    job_state = np.array([r["state"] for r in res], dtype=np.uint32)
+    job_exec = np.full((n, 4), 4, dtype=np.uint8)
+    job_subtasks = np.zeros((n, S_max, 4), dtype=np.uint8)
+    job_n_subtasks = np.zeros(n, dtype=np.uint8)
+    row_kind = np.zeros((n, P_max), dtype=np.uint8)
+    row_masks = np.zeros((n, P_max, 4), dtype=np.uint8)
+    row_i = np.full((n, P_max), 255, dtype=np.uint8)
+    row_j = np.full((n, P_max), 255, dtype=np.uint8)
+    row_level1 = np.zeros((n, P_max), dtype=np.uint8)
+    row_valid = np.full((n, P_max, 25), 255, dtype=np.uint8)
+    row_n_valid = np.zeros((n, P_max), dtype=np.uint8)
+    row_act_idx = np.zeros((n, P_max), dtype=np.uint8)
+    for r, rec in enumerate(res):
+        job_exec[r, :rec["n_agents"]] = rec["executed"]
+        job_n_subtasks[r] = len(rec["subtasks"])
+        job_subtasks[r, :len(rec["subtasks"])] = rec["subtasks"]
+        assert len(rec["rows"]) == len(rec["pairs"])
+        for p, rr in enumerate(rec["rows"]):
+            row_kind[r, p], row_masks[r, p], row_i[r, p], row_j[r, p] = rr["kind"], rr["masks"], rr["i"], rr["j"]
+            row_level1[r, p], row_n_valid[r, p], row_act_idx[r, p] = rr["level1"], rr["n_valid"], rr["act_idx"]
+            row_valid[r, p, :len(rr["valid"])] = rr["valid"]
+            assert rr["n_valid"] == n_valid[r, p] and rr["act_idx"] == act_idx[r, p]
+    np.savez_compressed(os.path.join(GOLDEN, "bd_rows.npz"), levels=np.array(levels), level=job_level,
+                        n_agents=job_agents, observer=job_observer, model=job_model, state=job_state,
+                        state_layout=np.array("abi2-byte-planes"), executed=job_exec, subtasks=job_subtasks,
+                        n_subtasks=job_n_subtasks, row_kind=row_kind, row_masks=row_masks, row_i=row_i, row_j=row_j,
+                        row_level1=row_level1, row_valid=row_valid, row_n_valid=row_n_valid, row_act_idx=row_act_idx)
+    print("bd rows:", int((row_n_valid > 0).sum()), "rows")
 
 
 def main(what):
