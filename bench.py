@@ -271,35 +271,44 @@ def run_ours(args):
         ms, ab_ms = (float(v) for v in t.tolist())
     value = world * args.steps * N_ENVS * N_AGENTS / (ms * 1e-3)
 
-    # ---- end to end through the public API: host actions in, reward/done bytes out, per step ----
+    # ---- end to end through the public API: host actions in, reward/done bits out, per step ----
+    # Two host-side action formats through the same call, OvercookedEnvironment.step(pinned host tensor):
+    # one joint index per env (uint8[N] = 5 * a_1 + a_2, the planners' joint-action index: 1 MB per step)
+    # - the headline e2e - and the per-agent bytes (uint8[N][2]: 2 MB per step).
     ns = argparse.Namespace(level=LEVEL, num_agents=N_AGENTS, max_num_timesteps=HORIZON, max_num_subtasks=14,
                             seed=1, model1=None, model2=None, model3=None, model4=None)
     env = gcb.OvercookedEnvironment(ns, num_envs=N_ENVS, device=dev, track_collisions=False)
-    env.reset()
-    host_actions = [actions[0][s].cpu().pin_memory() for s in range(8)]
+    byte_actions = [actions[0][s].cpu().pin_memory() for s in range(8)]
+    joint_actions = [(actions[0][s][:, 0] * 5 + actions[0][s][:, 1]).to(torch.uint8).cpu().pin_memory() for s in range(8)]
     e2e_steps = max(1, min(args.steps, 400))
     # warm-up: one untimed block of the same length.  The first few hundred host-driven steps run up to
     # 30-45 % slower than the steady state (PCIe link / copy-engine / host ramp; scripts/e2e_numa_probe.py:
     # blocks of 400 steps measure 1.3-1.8e10, then 2.4e10 for every later block), so 3 steps are not enough
     e2e_warmup = max(args.warmup, 3, e2e_steps)
-    for s in range(e2e_warmup):
-        if s and s % HORIZON == 0:
-            env.reset()
-        env.step(host_actions[s % 8])
-    env.reset()
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(e2e_steps):
-        if s and s % HORIZON == 0:
-            env.reset()
-        env.step(host_actions[s % 8])
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * e2e_steps * N_ENVS * N_AGENTS / e2e_s
+
+    def e2e_run(host_actions):
+        env.reset()
+        for s in range(e2e_warmup):
+            if s and s % HORIZON == 0:
+                env.reset()
+            env.step(host_actions[s % 8])
+        env.reset()
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(e2e_steps):
+            if s and s % HORIZON == 0:
+                env.reset()
+            env.step(host_actions[s % 8])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * e2e_steps * N_ENVS * N_AGENTS / dt
+
+    e2e_bytes_value = e2e_run(byte_actions)
+    e2e_value = e2e_run(joint_actions)
 
     # ---- the one collective of this path: reduce the episode statistics over ranks ----
     stats = torch.zeros(gcb._lib.STATS_LEN, dtype=torch.int64, device=dev)
@@ -329,11 +338,14 @@ def run_ours(args):
                 launch_ab={"mode": "python loop, one gc_env_step call per step" if use_graphs else "CUDA graphs",
                            "steps": ab_steps, "us_per_step": ab_ms * 1e3 / ab_steps,
                            "value": world * ab_steps * N_ENVS * N_AGENTS / (ab_ms * 1e-3)}), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_ENVS * N_AGENTS,
-                    "d2h_bytes_per_step": (N_ENVS + 31) // 32 * 8 if env.PACKED_RESULTS else N_ENVS,
-                    "results": "done / reward bit planes (2 bits per env)" if env.PACKED_RESULTS else "reward_done bytes",
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_ENVS,
+                    "d2h_bytes_per_step": (N_ENVS + 31) // 32 * 8,
+                    "results": "done / reward bit planes (2 bits per env)",
                     "steps": e2e_steps, "warmup_steps": e2e_warmup,
-                    "api": "OvercookedEnvironment(arglist, num_envs=2^20).step(pinned uint8[N][2])"},
+                    "api": "OvercookedEnvironment(arglist, num_envs=2^20).step(pinned uint8[N]): one joint action "
+                           "index per env (5 * a_1 + a_2)",
+                    "per_agent_bytes": {"value": e2e_bytes_value, "h2d_bytes_per_step": N_ENVS * N_AGENTS,
+                                        "api": "the same call with pinned uint8[N][2] (one byte per agent)"}},
             "gpu_launches": timed_launches,
             "roofline": {"bound": "hbm", "kernel": "step2_kernel<NA=2,NOBJ=4,EXTRAS=0,BITS=0,MULTI=0> (gc_env_step, plain step)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,

@@ -12,6 +12,7 @@ MAX_AGENTS, MAX_OBJECTS, MAX_GOALS, MAX_CELLS, MAX_SUBTASKS, MAX_LEVELS = 4, 6, 
 STATS_LEN = 133
 SLOT_DEAD = 0xE000
 PLACE_HELD, PLACE_DEAD = 0x40, 0x47
+PLAN_JOINT_ACTIONS = 1
 
 
 class GcError(RuntimeError):
@@ -51,6 +52,10 @@ _SIGNATURES = {
                               _VOIDP, C.c_int64, C.c_int, _VOIDP]),
     "gc_env_step_host": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP,
                                    _VOIDP, _VOIDP, C.c_int64, C.c_int, _VOIDP]),
+    "gc_step_plan_create": (C.c_int, [C.POINTER(Level), _VOIDP, _VOIDP, C.c_int64, C.c_int, C.c_int, C.POINTER(_VOIDP)]),
+    "gc_step_plan_run": (C.c_int, [_VOIDP, _VOIDP, _VOIDP]),
+    "gc_step_plan_run_host": (C.c_int, [_VOIDP, _VOIDP, _VOIDP, _VOIDP]),
+    "gc_step_plan_destroy": (None, [_VOIDP]),
     "gc_env_rollout": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP,
                                  C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_uint64, _VOIDP]),
     "gc_fill_random_actions": (C.c_int, [_VOIDP, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64,
@@ -124,7 +129,15 @@ def ptr(t, dtype=None):
     return t.data_ptr()
 
 
+try:  # ~0.2 us instead of ~1 us for torch.cuda.current_stream(device).cuda_stream: it is on the step path
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # pragma: no cover
+    _raw_stream = None
+
+
 def stream_ptr(device=None):
+    if _raw_stream is not None and device is not None and device.index is not None:
+        return _raw_stream(device.index)
     return torch.cuda.current_stream(device).cuda_stream
 
 

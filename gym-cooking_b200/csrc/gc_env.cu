@@ -472,10 +472,31 @@ __device__ __forceinline__ void l2_prefetch(const Step2Args& A, uint32_t i, uint
 // this grid may start, stage them and prefetch its first tile into L2 while the previous kernel of the
 // stream drains; everything an earlier kernel can have written is read only after griddepcontrol.wait
 // (L2 is the coherence point: a prefetched line cannot be stale).
-template <int NA, int NOBJ, bool EXTRAS, bool BITS, bool MULTI>
+// joint-action form (GC_PLAN_JOINT_ACTIONS): one index per env, j = sum_i action_i * 5^(NA-1-i) (for two
+// agents 5 * a_1 + a_2, the planners' joint-action index) in a uint8 (NA <= 3) or uint16 (NA = 4) - half /
+// a third / half of the bytes a caller with host-resident actions sends over PCIe
+template <int NA>
+__device__ __forceinline__ uint32_t load_joint_raw(const uint8_t* __restrict__ actions, uint32_t i) {
+  if constexpr (NA == 4) return reinterpret_cast<const uint16_t*>(actions)[i];
+  return actions[i];
+}
+template <int NA>
+__device__ __forceinline__ uint32_t joint_to_bytes(uint32_t j) {
+  uint32_t aw = 0;
+#pragma unroll
+  for (int i = NA - 1; i >= 0; i--) {
+    const uint32_t q = (j * 0xCCCDu) >> 18;  // j / 5 for j < 2^16
+    aw |= (j - 5u * q) << (8 * i);
+    j = q;
+  }
+  return aw | (j ? 0x04040404u : 0u);  // an index >= 5^NA: everybody stays
+}
+
+template <int NA, int NOBJ, bool EXTRAS, bool BITS, bool MULTI, bool JOINT = false>
 __global__ void __launch_bounds__(kS2Threads, GC_STEP2_MIN_CTAS(NA, EXTRAS))
 step2_kernel(const __grid_constant__ Step2Args A) {
   static_assert(!(EXTRAS && BITS) && !(MULTI && BITS), "bit planes come with the plain single-level step only");
+  static_assert(!JOINT || (!EXTRAS && !MULTI), "joint-action indices come with the plain single-level step only");
   extern __shared__ __align__(16) uint8_t s_tables[];  // StaticTables, then n_levels x LevelTables
   const gcs2::StaticTables& S = *reinterpret_cast<const gcs2::StaticTables*>(s_tables);
   const gcs2::LevelTables* LV = reinterpret_cast<const gcs2::LevelTables*>(s_tables + kTablesHead);
@@ -491,7 +512,8 @@ step2_kernel(const __grid_constant__ Step2Args A) {
   }
   if (i < n) {
     if ((threadIdx.x & 7u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.state + i));
-    if ((threadIdx.x & 31u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.actions + (size_t)i * NA));
+    if ((threadIdx.x & 31u) == 0u)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(A.actions + (size_t)i * (JOINT ? (NA == 4 ? 2 : 1) : NA)));
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint4 frozen = make_uint4(0x80000000u, 0u, 0u, 0u);  // a lane past the end: nothing to compute or store
@@ -499,7 +521,7 @@ step2_kernel(const __grid_constant__ Step2Args A) {
   uint32_t a_next = 0, l_next = 0;
   if (i < n) {
     s_next = gc::ld_stream(A.state + i);
-    a_next = load_actions_raw<NA>(A.actions, i);
+    a_next = JOINT ? load_joint_raw<NA>(A.actions, i) : load_actions_raw<NA>(A.actions, i);
     if constexpr (MULTI) l_next = A.level_id[i];
   }
   __syncthreads();
@@ -516,16 +538,16 @@ step2_kernel(const __grid_constant__ Step2Args A) {
 #pragma unroll 1
   for (; BITS ? (i - lane < n) : (i < n); i += stride) {
     const uint4 s = s_next;
-    const uint32_t aw = a_next, lvl = l_next;
+    const uint32_t aw = JOINT ? joint_to_bytes<NA>(a_next) : a_next, lvl = l_next;
     const uint32_t inext = i + stride;
     if constexpr (BITS) s_next = frozen;
     if (inext < n) {
       s_next = gc::ld_stream(A.state + inext);
-      a_next = load_actions_raw<NA>(A.actions, inext);
+      a_next = JOINT ? load_joint_raw<NA>(A.actions, inext) : load_actions_raw<NA>(A.actions, inext);
       if constexpr (MULTI) l_next = A.level_id[inext];
     }
 #if GC_STEP2_L2_AHEAD
-    l2_prefetch<NA>(A, inext + stride, n);
+    l2_prefetch<JOINT ? (NA == 4 ? 2 : 1) : NA>(A, inext + stride, n);
 #endif
     step2_one<NA, NOBJ, EXTRAS, BITS>(S, LV[MULTI ? min(lvl, lmax) : 0u], A, s, aw, i, !BITS || i < n);
   }
@@ -576,7 +598,7 @@ rollout2_kernel(const DeviceTables* __restrict__ tables, uint4* __restrict__ sta
 
 // persistent grid of step2_kernel: as many CTAs as are resident at once (from the occupancy of the
 // instantiation), unless GC_LUT_CTAS_PER_SM overrides it
-template <int NA, int NOBJ, bool EXTRAS, bool BITS, bool MULTI>
+template <int NA, int NOBJ, bool EXTRAS, bool BITS, bool MULTI, bool JOINT = false>
 unsigned step2_grid(int64_t n, size_t dyn_smem) {
   static int resident = 0;  // CTAs per device
   static size_t resident_smem = 0;
@@ -589,7 +611,7 @@ unsigned step2_grid(int64_t n, size_t dyn_smem) {
     if (e) per_sm = atoi(e);
     if (per_sm < 1 || per_sm > 8) {
       per_sm = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step2_kernel<NA, NOBJ, EXTRAS, BITS, MULTI>, kS2Threads,
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step2_kernel<NA, NOBJ, EXTRAS, BITS, MULTI, JOINT>, kS2Threads,
                                                         dyn_smem) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         per_sm = 4;
@@ -608,20 +630,20 @@ unsigned step2_grid(int64_t n, size_t dyn_smem) {
   return (unsigned)resident;
 }
 
-template <int NA, int NOBJ, bool EXTRAS, bool BITS, bool MULTI>
+template <int NA, int NOBJ, bool EXTRAS, bool BITS, bool MULTI, bool JOINT = false>
 cudaError_t launch_step2(const Step2Args& A, cudaStream_t st) {
   static const bool pdl = getenv("GC_STEP_NO_PDL") == nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kS2Threads);
   cfg.dynamicSmemBytes = tables_bytes(MULTI ? A.n_levels : 1);
-  cfg.gridDim = dim3(step2_grid<NA, NOBJ, EXTRAS, BITS, MULTI>(A.n, cfg.dynamicSmemBytes));
+  cfg.gridDim = dim3(step2_grid<NA, NOBJ, EXTRAS, BITS, MULTI, JOINT>(A.n, cfg.dynamicSmemBytes));
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, step2_kernel<NA, NOBJ, EXTRAS, BITS, MULTI>, A);
+  return cudaLaunchKernelEx(&cfg, step2_kernel<NA, NOBJ, EXTRAS, BITS, MULTI, JOINT>, A);
 }
 
 inline bool use_generic_step() {
@@ -723,6 +745,34 @@ int launch_rollout(const gc_level* levels, int n_levels, const GcLevelsDev& lv, 
 
 }  // namespace
 
+// ---- prepared steps -------------------------------------------------------------------------------
+// Everything gc_env_step derives per call (level validation, table lookup, argument block, launch
+// configuration) fixed once; a step is then one cudaLaunchKernelEx.
+struct gc_step_plan {
+  int device, n_agents, flags;
+  int64_t n;
+  Step2Args args;
+  cudaError_t (*launch)(const Step2Args&, cudaStream_t);       // plain step
+  cudaError_t (*launch_bits)(const Step2Args&, cudaStream_t);  // plain step + result bit planes
+  uint8_t* actions_dev;  // staging of gc_step_plan_run_host (owned)
+  uint32_t* bits_dev;
+  size_t action_bytes;
+};
+
+namespace {
+template <int NA, int NOBJ>
+int plan_bind(gc_step_plan* p) {
+  if (p->flags & GC_PLAN_JOINT_ACTIONS) {
+    p->launch = launch_step2<NA, NOBJ, false, false, false, true>;
+    p->launch_bits = launch_step2<NA, NOBJ, false, true, false, true>;
+  } else {
+    p->launch = launch_step2<NA, NOBJ, false, false, false, false>;
+    p->launch_bits = launch_step2<NA, NOBJ, false, true, false, false>;
+  }
+  return GC_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int gc_env_reset(const gc_level* levels, int n_levels, const uint8_t* level_id, uint32_t* state, int64_t n,
@@ -790,6 +840,81 @@ int gc_env_step_host(const gc_level* levels, int n_levels, const uint8_t* level_
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_env_step_host: copy out failed: %s", cudaGetErrorString(e));
   return GC_OK;
+}
+
+int gc_step_plan_create(const gc_level* level, uint32_t* state, uint8_t* reward_done, int64_t n, int n_agents,
+                        int flags, gc_step_plan** out) {
+  if (!out) return gc_fail(GC_E_ARG, "gc_step_plan_create: null out");
+  *out = nullptr;
+  GcLevelsDev lv;
+  int max_objs = 0;
+  if (int rc = gc_levels_to_dev(level, 1, n_agents, &lv, &max_objs)) return rc;
+  if (!state || !reward_done || n < 1 || n > ((int64_t)1 << 30))
+    return gc_fail(GC_E_ARG, "gc_step_plan_create: need state, reward_done and 1 <= n <= 2^30");
+  if (int rc = gc_require_device()) return rc;
+  const DeviceTables* tables = tables_for(level, 1, n_agents);
+  if (!tables) return GC_E_CUDA;
+  gc_step_plan* p = new gc_step_plan();
+  cudaGetDevice(&p->device);
+  p->n_agents = n_agents;
+  p->flags = flags;
+  p->n = n;
+  p->args = Step2Args();
+  p->args.tables = tables;
+  p->args.state = reinterpret_cast<uint4*>(state);
+  p->args.reward_done = reward_done;
+  p->args.n = (uint32_t)n;
+  p->args.n_levels = 1;
+  p->args.table_copies = kTableCopies;
+  p->action_bytes = (flags & GC_PLAN_JOINT_ACTIONS) ? (size_t)n * (n_agents == 4 ? 2 : 1) : (size_t)n * n_agents;
+  auto bind = [&]() -> int {
+    GC_DISPATCH_NA_NOBJ(plan_bind, p);
+    return gc_fail(GC_E_ARG, "gc_step_plan_create: n_agents must be 1..4");
+  };
+  if (int rc = bind()) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return GC_OK;
+}
+
+int gc_step_plan_run(const gc_step_plan* p, const uint8_t* actions, void* stream) {
+  if (!p || !actions) return gc_fail(GC_E_ARG, "gc_step_plan_run: null plan / actions");
+  Step2Args A = p->args;
+  A.actions = actions;
+  const cudaError_t err = p->launch(A, (cudaStream_t)stream);
+  if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_step_plan_run: launch failed: %s", cudaGetErrorString(err));
+  return GC_OK;
+}
+
+int gc_step_plan_run_host(gc_step_plan* p, const uint8_t* actions_host, uint32_t* rd_bits_host, void* stream) {
+  if (!p || !actions_host || !rd_bits_host) return gc_fail(GC_E_ARG, "gc_step_plan_run_host: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bits_bytes = (size_t)((p->n + 31) / 32) * 8;
+  cudaError_t e = cudaSuccess;
+  if (!p->actions_dev) {  // staging buffers on first use
+    e = cudaMalloc(&p->actions_dev, p->action_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&p->bits_dev, bits_bytes);
+    if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_step_plan_run_host: staging: %s", cudaGetErrorString(e));
+  }
+  e = cudaMemcpyAsync(p->actions_dev, actions_host, p->action_bytes, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_step_plan_run_host: copy in failed: %s", cudaGetErrorString(e));
+  Step2Args A = p->args;
+  A.actions = p->actions_dev;
+  A.rd_bits = p->bits_dev;
+  e = p->launch_bits(A, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(rd_bits_host, p->bits_dev, bits_bytes, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_step_plan_run_host: %s", cudaGetErrorString(e));
+  return GC_OK;
+}
+
+void gc_step_plan_destroy(gc_step_plan* p) {
+  if (!p) return;
+  if (p->actions_dev) cudaFree(p->actions_dev);
+  if (p->bits_dev) cudaFree(p->bits_dev);
+  delete p;
 }
 
 int gc_env_rollout(const gc_level* levels, int n_levels, const uint8_t* level_id, uint32_t* state,

@@ -52,7 +52,46 @@ class KitchenBatch:
                 raise ValueError("level_id has values >= n_levels (%d)" % self.n_levels)
         else:
             self.level_id = None
+        self._plans = {}  # prepared steps (gc_step_plan), by action format
         self.reset()
+
+    def __del__(self):
+        for plan in getattr(self, "_plans", {}).values():
+            try:
+                self.lib.gc_step_plan_destroy(plan)
+            except Exception:
+                pass
+
+    def _plan(self, joint):
+        """gc_step_plan of the plain step for this batch (one per action format), or None when the batch
+        is outside the plans' envelope (several levels, collision counters)."""
+        plan = self._plans.get(joint)
+        if plan is None:
+            if self.n_levels != 1 or self.collisions is not None or self.num_envs < 1:
+                return None
+            out = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.gc_step_plan_create(self._lv(), self.state.data_ptr(), self.reward_done.data_ptr(),
+                                                        self.num_envs, self.num_agents,
+                                                        _lib.PLAN_JOINT_ACTIONS if joint else 0, C.byref(out)))
+            plan = self._plans[joint] = out.value
+        return plan
+
+    def _check_actions(self, actions, on_device):
+        """-> True for the joint-index form (1-D: uint8 for <= 3 agents, int16 for 4), False for bytes"""
+        joint = actions.dim() == 1
+        if joint:
+            want = torch.int16 if self.num_agents == 4 else torch.uint8
+            ok = actions.shape[0] == self.num_envs and actions.dtype is want
+        else:
+            ok = actions.shape == (self.num_envs, self.num_agents) and actions.dtype is torch.uint8
+        if not ok or not actions.is_contiguous() or actions.is_cuda != on_device:
+            raise ValueError("actions must be a contiguous %s tensor: uint8[%d][%d], or one joint index per env "
+                             "(uint8[%d], int16 for 4 agents)" % ("CUDA" if on_device else "host", self.num_envs,
+                                                                  self.num_agents, self.num_envs))
+        if on_device and actions.device != self.device:
+            raise _lib.GcError("actions are on %s, the batch is on %s" % (actions.device, self.device))
+        return joint
 
     @staticmethod
     def _attach_subtasks(lv):
@@ -101,16 +140,23 @@ class KitchenBatch:
         return self.state
 
     def step(self, actions, hash_out=None, executed_out=None):
-        """actions: uint8[N][num_agents] CUDA tensor, values 0..4.  In place on self.state."""
-        if actions.shape != (self.num_envs, self.num_agents):
-            raise ValueError("actions must be [%d, %d]" % (self.num_envs, self.num_agents))
-        if actions.dtype is not torch.uint8 or not actions.is_cuda or not actions.is_contiguous():
-            raise _lib.GcError("actions must be a contiguous uint8 CUDA tensor: libgymcook has no CPU path")
-        if actions.device != self.device:
-            raise _lib.GcError("actions are on %s, the batch is on %s" % (actions.device, self.device))
-        # hot call: at 2^20 envs the kernel takes ~12 us, so the marshalling is kept to pointer reads
-        # (the device guard is entered only when this batch is not on the current device)
+        """actions: uint8[N][num_agents] CUDA tensor, values 0..4 - or one joint index per env
+        (uint8[N], int16[N] for 4 agents: sum_i a_i * 5^(num_agents-1-i)).  In place on self.state."""
+        if not actions.is_cuda:
+            raise _lib.GcError("actions must be a CUDA tensor: libgymcook has no CPU path (step_host takes host actions)")
+        joint = self._check_actions(actions, True)
+        # hot call: at 2^20 envs the kernel takes ~9 us, so the plain step goes through a prepared plan
+        # (one launch, three arguments) and the marshalling is kept to pointer reads
         dev = self.device
+        if hash_out is None and executed_out is None and torch.cuda.current_device() == dev.index:
+            plan = self._plan(joint)
+            if plan is not None:
+                rc = self.lib.gc_step_plan_run(plan, actions.data_ptr(), _lib.stream_ptr(dev))
+                if rc != 0:
+                    _lib.check(rc)
+                return self.reward_done
+        if joint:
+            raise _lib.GcError("joint-index actions need the plain single-level step (no hash / executed / collision outputs)")
         guard = None
         if torch.cuda.current_device() != dev.index:
             guard = torch.cuda.device(dev)
@@ -127,6 +173,21 @@ class KitchenBatch:
         if rc != 0:
             _lib.check(rc)
         return self.reward_done
+
+    def step_host_bits(self, actions_host, bits_host):
+        """gc_step_plan_run_host: actions from a (pinned) host tensor - bytes [N][num_agents] or joint indices
+        [N] - results as the done / reward bit planes in `bits_host` (pinned int32[(N+31)//32][2]); returns
+        when the copies and the step are done.  None when the batch is outside the plans' envelope."""
+        joint = self._check_actions(actions_host, False)
+        if bits_host.is_cuda or not bits_host.is_contiguous() or bits_host.numel() * bits_host.element_size() < (self.num_envs + 31) // 32 * 8:
+            raise ValueError("bits_host must be a contiguous host tensor of (N+31)//32 x 2 32-bit words")
+        plan = self._plan(joint)
+        if plan is None:
+            return None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gc_step_plan_run_host(plan, actions_host.data_ptr(), bits_host.data_ptr(),
+                                                      _lib.stream_ptr(self.device)))
+        return bits_host
 
     def step_host(self, actions_host, actions_dev, reward_done_host=None, bits_dev=None, bits_host=None):
         """gc_env_step_host: actions from a (pinned) host tensor, results into pinned host memory -

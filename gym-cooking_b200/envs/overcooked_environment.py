@@ -342,13 +342,15 @@ class OvercookedEnvironment(_ReferenceSurface):
         elif self.PIPELINE_CHUNKS <= 1 or n < self.PIPELINE_MIN_ENVS or kb.n_levels > 1:
             # host actions in, reward/done bytes out: one library call (gc_env_step_host) that copies
             # in (async when `acts` is pinned), steps, copies out and waits for the stream
-            if acts.dtype is torch.uint8 and acts.is_contiguous() and acts.shape == (n, self.num_agents):
-                if self.PACKED_RESULTS:
+            joint = acts.dim() == 1  # one joint index per env (engine.KitchenBatch.step): fewer bytes over PCIe
+            if acts.is_contiguous() and (joint or (acts.dtype is torch.uint8 and acts.shape == (n, self.num_agents))):
+                if self.PACKED_RESULTS or joint:
                     if self._pinned_bits is None:
                         words = (n + 31) // 32
                         self._pinned_bits = torch.zeros((words, 2), dtype=torch.int32).pin_memory()
                         self._dev_bits = torch.zeros((words, 2), dtype=torch.int32, device=kb.device)
-                    kb.step_host(acts, self._dev_actions, None, self._dev_bits, self._pinned_bits)
+                    if kb.step_host_bits(acts, self._pinned_bits) is None:  # outside the prepared-step envelope
+                        kb.step_host(acts, self._dev_actions, None, self._dev_bits, self._pinned_bits)
                     obs = self._obs()
                     done = BitFlag(self._pinned_bits, 0, n, True)
                     reward = BitFlag(self._pinned_bits, 1, n, False)

@@ -291,14 +291,15 @@ def _bd_job(args):
         st, ag = kw["subtask"], tuple(kw["subtask_agent_names"])
         idx = [names.index(a) for a in ag]
         if st is None:
-            rowrec.append(dict(kind=0, masks=(0, 0, 0, 0), i=idx[0], j=255, level1=0, valid=[], n_valid=len(soft[-1][0])))
+            rowrec.append(dict(kind=0, masks=(0, 0, 0, 0), i=idx[0], j=255, level1=0, valid=[], n_valid=len(soft[-1][0]),
+                               act_idx=0 if executed[idx[0]] == 4 else 1))
         else:
             joint = len(ag) == 2
             valid = [act_code(a, joint) for a in q_actions[1:]]
             assert len(valid) == len(soft[-1][0]) and act_code(q_actions[0], joint) in valid
             rowrec.append(dict(kind=2 if joint else 1, masks=subtask_masks(st), i=idx[0], j=idx[1] if joint else 255,
                                level1=int(planner.planner_level == brtdp.PlannerLevel.LEVEL1),
-                               valid=valid, n_valid=len(valid)))
+                               valid=valid, n_valid=len(valid), act_idx=valid.index(act_code(q_actions[0], joint))))
         return p
 
     bd.sp.special.softmax = rec_softmax
@@ -322,7 +323,7 @@ def _bd_job(args):
         key = (str(st), agents)
         if key in pair_index:
             continue
-        rr["act_idx"] = int(np.argmin(np.abs(out - p)))
+        assert abs(out[rr["act_idx"]] - p) < 1e-15  # the softmax entry prob_nav_actions returned (bd:689)
         rows_out.append(rr)
         act_idx = int(np.argmin(np.abs(out - p)))
         assert abs(out[act_idx] - p) < 1e-15
@@ -411,12 +412,16 @@ def gen_bd():
             row_kind[r, p], row_masks[r, p], row_i[r, p], row_j[r, p] = rr["kind"], rr["masks"], rr["i"], rr["j"]
             row_level1[r, p], row_n_valid[r, p], row_act_idx[r, p] = rr["level1"], rr["n_valid"], rr["act_idx"]
             row_valid[r, p, :len(rr["valid"])] = rr["valid"]
-            assert rr["n_valid"] == n_valid[r, p] and rr["act_idx"] == act_idx[r, p]
+            assert rr["n_valid"] == n_valid[r, p]
+            act_idx[r, p] = rr["act_idx"]  # the true index (the argmin-by-value above picks the first of equal entries)
     np.savez_compressed(os.path.join(GOLDEN, "bd_rows.npz"), levels=np.array(levels), level=job_level,
                         n_agents=job_agents, observer=job_observer, model=job_model, state=job_state,
                         state_layout=np.array("abi2-byte-planes"), executed=job_exec, subtasks=job_subtasks,
                         n_subtasks=job_n_subtasks, row_kind=row_kind, row_masks=row_masks, row_i=row_i, row_j=row_j,
                         row_level1=row_level1, row_valid=row_valid, row_n_valid=row_n_valid, row_act_idx=row_act_idx)
+    np.savez_compressed(os.path.join(GOLDEN, "bd_posteriors.npz"), meta=np.array(meta), beta=1.3, prior=prior,
+                        posterior=post, alive=alive, hyp_pair=hyp_pair, pair_w=pair_w, qdiff=qdiff,
+                        n_valid=n_valid, act_idx=act_idx)
     print("bd rows:", int((row_n_valid > 0).sum()), "rows")
 
 

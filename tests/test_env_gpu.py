@@ -328,3 +328,39 @@ def test_step_host_bit_planes(n, kind):
         assert np.array_equal(bits_host.numpy().view(np.uint32), expect), "step %d" % s
         seen_done += int(expect[:, 0].any())
     assert seen_done > 0
+
+
+@pytest.mark.parametrize("level,n_agents,n", [("partial-divider_tl", 2, 70001), ("full-divider_salad", 3, 4099),
+                                              ("open-divider_salad", 4, 33333), ("onion-8x8", 1, 1000)])
+def test_prepared_plans_and_joint_actions(level, n_agents, n):
+    """The prepared-step path (gc_step_plan_run / _run_host) and the joint-index action format
+    (j = sum_i a_i * 5^(NA-1-i); uint8, int16 for 4 agents) against gc_env_step on action bytes - which the
+    tests above hold against the oracle: same states, reward/done bytes and bit planes at every step; an
+    out-of-range joint index means "everybody stays"."""
+    text, src = level_source(level)
+    max_t = 14
+    a = gcb.KitchenBatch(src, n_agents, n, max_t)                           # plan, bytes
+    b = gcb.KitchenBatch(src, n_agents, n, max_t)                           # plan, joint indices
+    c = gcb.KitchenBatch(src, n_agents, n, max_t)                           # plan, host joint indices -> bit planes
+    ref = gcb.KitchenBatch(src, n_agents, n, max_t, track_collisions=True)  # gc_env_step (outside the plans' envelope)
+    assert ref._plan(False) is None and a._plan(False) is not None
+    acts = ref.random_actions(18, seed=33)
+    weights = torch.tensor([5 ** (n_agents - 1 - i) for i in range(n_agents)], device=a.device)
+    bits = torch.zeros(((n + 31) // 32, 2), dtype=torch.int32).pin_memory()
+    for s in range(18):
+        by = acts[s].clone()
+        joint = (by.long() * weights).sum(1)
+        if s == 3:  # out-of-range codes: bytes > 4 are "stay" per agent, a joint index >= 5^NA is "all stay"
+            by[::7] = 4
+            joint[::7] = 5 ** n_agents + (torch.arange(joint[::7].numel(), device=a.device) % 3)
+        joint = joint.to(torch.int16 if n_agents == 4 else torch.uint8)
+        ref.step(by)
+        a.step(by)
+        b.step(joint)
+        c.step_host_bits(joint.cpu().pin_memory(), bits)
+        torch.cuda.synchronize()
+        for kb in (a, b, c):
+            assert torch.equal(kb.state, ref.state), "step %d" % s
+        assert torch.equal(a.reward_done, ref.reward_done) and torch.equal(b.reward_done, ref.reward_done)
+        assert np.array_equal(bits.numpy().view(np.uint32), _planes(ref.reward_done.cpu().numpy(), n)), "step %d" % s
+    assert bool(ref.done.all())  # the horizon was reached: done / timeout bits were part of the comparison
