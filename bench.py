@@ -383,8 +383,9 @@ def hbm_peak_gbs():
 
 
 def secondary_metrics(gcb, torch, dev):
-    """The other two hot paths of BASELINE.json's metric, timed on resident synthetic inputs (CUDA events,
-    3 warm-up + 10 timed launches each): BD posterior updates/s (cfg-4 shape) and subtask values/s (cfg-3)."""
+    """The other two hot paths of BASELINE.json's metric at the sizes SURVEY 8d states: BD posterior updates/s
+    (cfg-4 shape, CUDA events, 3 warm-up + 10 timed launches), the whole delegation loop of cfg-4 (2^18 envs x 100)
+    and the planner on cfg-3 (2^20 envs)."""
     import itertools
 
     def timed(fn, iters, warm=3):
@@ -416,26 +417,30 @@ def secondary_metrics(gcb, torch, dev):
                 "bytes_per_update": bytes_per, "achieved_gbs": n * bytes_per / t / 1e9,
                 "roofline_frac": n * bytes_per / t / 1e9 / hbm_peak_gbs()[0]})
     del probs, hyp, w, qd, nv, ai
-    # cfg-3 as a whole: the device-resident Bayesian-Delegation loop (lower bounds + exact Q through the
-    # planning-state memo + posterior + action selection + env step), wall clock with a sync on both sides
+    # cfg-4: the device-resident Bayesian-Delegation loop (2-agent open-divider_salad, bd/bd): lower bounds +
+    # exact Q through the planning-state memo + posterior + action selection + env step, 2^18 envs x 100
+    # loop steps as SURVEY 8d states it, wall clock with a sync on both sides
     from gym_cooking_b200 import batched_agents
-    n_loop, loop_steps = 1 << 16, 40
+    n_loop, loop_steps = 1 << 18, 100
     loop = batched_agents.BatchedDelegation("open-divider_salad", n_loop, ("bd", "bd"), seed=1, device=dev)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(loop_steps):
-        loop.step()
+    done_steps = loop.run(max_steps=loop_steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     st = loop.kb.stats().cpu().tolist()
-    out.append({"metric": "bd_loop_agent_steps_per_sec", "value": n_loop * 2 * loop_steps / dt, "unit": "agent-steps/s",
-                "config": "cfg-3: 2-agent open-divider_salad, bd/bd, 2^16 envs x %d steps from reset, cold planner memo"
-                          % loop_steps,
-                "posterior_updates_per_sec": loop.posterior_updates / dt, "seconds": dt,
-                "delivered_by_step_%d" % loop_steps: st[1], "planning_states_solved": loop.cache.solved_states})
+    out.append({"metric": "bd_loop_agent_steps_per_sec", "value": loop.agent_steps / dt, "unit": "agent-steps/s",
+                "config": "cfg-4: 2-agent open-divider_salad, bd/bd, 2^18 envs, horizon %d, from reset with a cold planner "
+                          "memo; finished envs leave the working batch" % loop_steps,
+                "posterior_updates_per_sec": loop.posterior_updates / dt, "seconds": dt, "loop_steps": done_steps,
+                "delivered": st[1], "mean_steps_of_delivered": st[2] / max(st[1], 1),
+                "completed_subtasks": st[133], "planning_states_solved": loop.cache.solved_states,
+                "planner_lookups": loop.cache.lookups})
     del loop
-    # path B: cfg-3 (3 agents, full-divider_salad), envs diversified by k = env % 41 random steps
-    n = 1 << 12  # bounded sample: the joint solver runs up to 25 searches per (env, pair)
+    # path B: cfg-3 (3 agents, full-divider_salad, 2^20 envs diversified by k = env % 41 random steps): lower
+    # bounds of all 54 (subtask, agent set) pairs, then exact V* + Q[25] of every pair that is doable somewhere
+    # in the batch, each distinct planning state solved once (subtask_q_unique)
+    n = 1 << 20
     kb = gcb.KitchenBatch("full-divider_salad", 3, n, HORIZON, device=dev)
     acts = kb.random_actions(40, seed=1235)
     idx = torch.arange(n, device=dev) % 41
@@ -443,21 +448,39 @@ def secondary_metrics(gcb, torch, dev):
         a = acts[s_].clone()
         a[idx <= s_] = 4
         kb.step(a)
+    del acts
     ns = len(kb.subtasks[0])
     sets = [(i, None) for i in range(3)] + list(itertools.combinations(range(3), 2))
     pairs = [(s_, i, j) for s_ in range(ns) for (i, j) in sets]
     t = timed(lambda: gcb.lower_bound(kb, pairs), 5)
+    lb_bytes = n * len(pairs) * 20  # 16 B state + 4 B bound per (env, pair)
     out.append({"metric": "lower_bounds_per_sec", "value": n * len(pairs) / t, "unit": "(env,pair)/s",
-                "config": "cfg-3: 3-agent full-divider_salad, 2^12 envs x %d pairs" % len(pairs)})
+                "config": "cfg-3: 3-agent full-divider_salad, 2^20 envs x %d pairs" % len(pairs),
+                "roofline": {"bound": "hbm", "kernel": "lower_bound_kernel", "bytes_per_unit": 20,
+                             "achieved": lb_bytes / t / 1e9, "peak": hbm_peak_gbs()[0], "unit": "GB/s",
+                             "frac": lb_bytes / t / 1e9 / hbm_peak_gbs()[0],
+                             "note": "the state is read once per env, not per pair: compulsory traffic is 16 B + 4 B x 54"}})
     lb = gcb.lower_bound(kb, pairs)
-    doable = [p for k, p in enumerate(pairs) if bool((lb[:, k] < 28).any())][:GC_BENCH_MAX_PAIRS]
-    res = {}
-    t = timed(lambda: res.update(r=gcb.subtask_q(kb, doable)), 1, warm=1)
-    status = res["r"][2]
+    doable = [p for k, p in enumerate(pairs) if bool((lb[:, k] < 28).any())]
+    del lb
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    v, q, status, n_unique = gcb.subtask_q_unique(kb, doable)
+    torch.cuda.synchronize()
+    t = time.perf_counter() - t0
+    hist = torch.bincount(status.flatten().long(), minlength=5).tolist()
+    n_joint = sum(1 for p in doable if p[2] is not None)
+    q_bytes = n * (n_joint * 120 + (len(doable) - n_joint) * 40)  # 40 B single / 120 B joint
     out.append({"metric": "subtask_values_per_sec", "value": n * len(doable) / t, "unit": "(env,pair)/s",
-                "config": "cfg-3: 2^12 envs x %d doable pairs (%d joint), exact V* + Q[25]" % (
-                    len(doable), sum(1 for p in doable if p[2] is not None)),
-                "status_histogram": torch.bincount(status.flatten().long(), minlength=5).tolist()})
+                "non_trivial_per_sec": (n * len(doable) - hist[2]) / t, "seconds": t,
+                "config": "cfg-3: 2^20 envs x %d doable pairs (%d joint), exact V* + Q[25]; %d distinct planning states "
+                          "solved once each (%.1fx)" % (len(doable), n_joint, n_unique, n / n_unique),
+                "status_histogram": hist,
+                "status_legend": "0 ok, 1 goal met at start, 2 unreachable (early exit), 3 search budget exceeded",
+                "roofline": {"bound": "hbm", "kernel": "joint_tree_kernel + subtask_q_kernel", "achieved": q_bytes / t / 1e9,
+                             "peak": hbm_peak_gbs()[0], "unit": "GB/s", "frac": q_bytes / t / 1e9 / hbm_peak_gbs()[0],
+                             "note": "search-bound, not bandwidth-bound: the joint solver's open / closed sets live in a "
+                                     "global-memory arena (profiles/r02_joint_tree_ncu.csv)"}})
     return out
 
 

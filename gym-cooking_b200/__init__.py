@@ -21,4 +21,4 @@ try:  # pragma: no cover - gym is not in this image
     _register(id=ENV_ID, entry_point="gym_cooking_b200.envs:OvercookedEnvironment")
 except Exception:
     pass
-from .planning import bd_likelihood_rows, bd_posterior, lower_bound, subtask_q  # noqa: F401,E402
+from .planning import bd_likelihood_rows, bd_posterior, lower_bound, subtask_q, subtask_q_unique  # noqa: F401,E402

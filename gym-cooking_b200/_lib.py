@@ -9,7 +9,7 @@ import torch
 from . import build as _build
 
 MAX_AGENTS, MAX_OBJECTS, MAX_GOALS, MAX_CELLS, MAX_SUBTASKS, MAX_LEVELS = 4, 6, 4, 64, 32, 16
-STATS_LEN = 133
+STATS_LEN = 134
 SLOT_DEAD = 0xE000
 PLACE_HELD, PLACE_DEAD = 0x40, 0x47
 PLAN_JOINT_ACTIONS = 1

@@ -249,6 +249,7 @@ class BatchedDelegation:
         self.executed = torch.full((N, NA), 4, dtype=torch.uint8, device=dev)
         self.prev = None
         self.posterior_updates = 0
+        self.agent_steps = 0  # counted by run(): live envs x agents per loop step
 
     def _slots(self, state):
         """(mask, cell, holder) int64[N][6] of the six object slots"""
@@ -501,7 +502,9 @@ class BatchedDelegation:
         every env's final state when this returns."""
         limit = max_steps if max_steps is not None else self.kb.max_num_timesteps + 1
         steps = 0
+        done = int((self.wkb.reward_done & 1).sum()) if getattr(self, "wkb", None) is not None else 0
         while steps < limit:
+            self.agent_steps += (self.N - done) * self.NA  # envs still running take this step
             rd = self.step()
             steps += 1
             done = int((rd & 1).sum())
@@ -509,5 +512,6 @@ class BatchedDelegation:
                 break
             if compact and self.N >= 4096 and 2 * done >= self.N:
                 self._compact()
+                done = 0  # the working batch now holds running envs only
         self._write_back()
         return steps

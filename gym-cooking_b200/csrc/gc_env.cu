@@ -204,19 +204,52 @@ hash_kernel(const uint4* __restrict__ state, unsigned long long* __restrict__ ha
 // episode statistics: warp-shuffle reduce -> shared-memory histogram -> one atomic per bin
 // per CTA.  stats layout: include/gymcook.h (GC_STATS_LEN).
 // ---------------------------------------------------------------------------------------
+// the levels' subtasks in mask form (gc_level.subtask), for the completed-subtask count of the statistics
+struct StatsSubtasks {
+  uint8_t n[GC_MAX_LEVELS];
+  gc_subtask st[GC_MAX_LEVELS][GC_MAX_SUBTASKS];
+};
+
+// Subtasks a state has completed, read off the objects (the batched stand-in for the Bag's
+// num_completed_subtasks, metrics_bag.py:55-61, which intersects the agents' own incomplete lists):
+// Chop(X) once some live object carries X chopped, Merge(a, b) once some live object contains a | b,
+// Deliver(m) once an object with mask m lies on a Delivery square.  Monotone along an episode, like the
+// agents' bookkeeping (RealAgent.refresh_subtasks never re-adds a subtask, utils/agent.py:151-171).
+__device__ __forceinline__ uint32_t completed_subtasks(const uint4& s, const GcLevelDev& L, const gc_subtask* st, int n_st) {
+  uint32_t done = 0;
+  for (int q = 0; q < n_st; q++) {
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < GC_MAX_OBJECTS; k++) {
+      const uint32_t sl = gc::slot_of(s, k), m = sl & 0x7fu, holder = sl >> 13;
+      if (holder == 7u) continue;
+      if (st[q].kind == GC_ST_DELIVER)
+        hit |= holder == 0u && m == st[q].goal && ((L.deliv_mask >> ((sl >> 7) & 63u)) & 1ull);
+      else
+        hit |= (m & st[q].goal) == st[q].goal;
+    }
+    done += hit ? 1u : 0u;
+  }
+  return done;
+}
+
 __global__ void __launch_bounds__(kThreads)
-stats_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restrict__ level_id,
-             const uint4* __restrict__ state, const uint32_t* __restrict__ collisions,
-             unsigned long long* __restrict__ stats, int64_t n) {
+stats_kernel(const __grid_constant__ GcLevelsDev levels, const __grid_constant__ StatsSubtasks subtasks,
+             const uint8_t* __restrict__ level_id, const uint4* __restrict__ state,
+             const uint32_t* __restrict__ collisions, unsigned long long* __restrict__ stats, int64_t n) {
+  constexpr int kAcc = 6;
   __shared__ unsigned int s_hist[128];
-  __shared__ unsigned long long s_acc[5];
+  __shared__ unsigned long long s_acc[kAcc];
   for (int k = threadIdx.x; k < 128; k += kThreads) s_hist[k] = 0;
-  if (threadIdx.x < 5) s_acc[threadIdx.x] = 0;
+  if (threadIdx.x < kAcc) s_acc[threadIdx.x] = 0;
   __syncthreads();
-  unsigned long long v[5] = {0, 0, 0, 0, 0};
+  unsigned long long v[kAcc] = {0, 0, 0, 0, 0, 0};
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-    const uint32_t w0 = state[i].x;
-    const GcLevelDev& L = levels.lv[level_id ? (level_id[i] & (GC_MAX_LEVELS - 1)) : 0];  // in bounds whatever the byte says
+    const uint4 s = state[i];
+    const uint32_t w0 = s.x;
+    const uint32_t lvl = level_id ? (level_id[i] & (GC_MAX_LEVELS - 1)) : 0;  // in bounds whatever the byte says
+    const GcLevelDev& L = levels.lv[lvl];
+    v[5] += completed_subtasks(s, L, subtasks.st[lvl], subtasks.n[lvl]);
     const uint32_t t = (w0 >> 24) & 127u;
     const bool done = w0 >> 31;
     v[0] += 1;
@@ -230,13 +263,14 @@ stats_kernel(const __grid_constant__ GcLevelsDev levels, const uint8_t* __restri
     if (collisions) v[3] += collisions[i];
   }
 #pragma unroll
-  for (int k = 0; k < 5; k++) {
+  for (int k = 0; k < kAcc; k++) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
     if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(&s_acc[k], v[k]);
   }
   __syncthreads();
   if (threadIdx.x < 5 && s_acc[threadIdx.x]) atomicAdd(&stats[threadIdx.x], s_acc[threadIdx.x]);
+  if (threadIdx.x == 5 && s_acc[5]) atomicAdd(&stats[133], s_acc[5]);  // after the histogram: the layout only grows
   for (int k = threadIdx.x; k < 128; k += kThreads)
     if (s_hist[k]) atomicAdd(&stats[5 + k], (unsigned long long)s_hist[k]);
 }
@@ -757,6 +791,8 @@ struct gc_step_plan {
   uint8_t* actions_dev;  // staging of gc_step_plan_run_host (owned)
   uint32_t* bits_dev;
   size_t action_bytes;
+  const void* zc_host;   // last rd_bits_host seen and its device alias (pinned, mapped memory), or null
+  uint32_t* zc_dev;
 };
 
 namespace {
@@ -900,11 +936,28 @@ int gc_step_plan_run_host(gc_step_plan* p, const uint8_t* actions_host, uint32_t
   }
   e = cudaMemcpyAsync(p->actions_dev, actions_host, p->action_bytes, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_step_plan_run_host: copy in failed: %s", cudaGetErrorString(e));
+  // Results: when `rd_bits_host` is pinned, mapped host memory (any cudaHostAlloc / torch pin_memory buffer
+  // under unified addressing) the kernel stores the bit planes straight into it - posted writes over PCIe,
+  // visible to the host once the stream has drained - and the device-to-host copy with its ~10 us of
+  // launch and completion latency disappears from the step.  Opt-in (GC_E2E_ZEROCOPY=1): on the measured box
+  // the 32 K eight-byte PCIe writes cost more than the copy they replace (84 vs 65 us per 2^20-env step,
+  // scripts/e2e_ab.sh), so the default keeps the device-to-host copy.
+  if (p->zc_host != rd_bits_host) {
+    static const bool no_zc = getenv("GC_E2E_ZEROCOPY") == nullptr;  // opt-in: measured slower (below)
+    p->zc_host = rd_bits_host;
+    p->zc_dev = nullptr;
+    cudaPointerAttributes at;
+    if (!no_zc && cudaPointerGetAttributes(&at, rd_bits_host) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+        at.devicePointer && ((uintptr_t)at.devicePointer & 7u) == 0)
+      p->zc_dev = static_cast<uint32_t*>(at.devicePointer);
+    cudaGetLastError();
+  }
   Step2Args A = p->args;
   A.actions = p->actions_dev;
-  A.rd_bits = p->bits_dev;
+  A.rd_bits = p->zc_dev ? p->zc_dev : p->bits_dev;
   e = p->launch_bits(A, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(rd_bits_host, p->bits_dev, bits_bytes, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && !p->zc_dev)
+    e = cudaMemcpyAsync(rd_bits_host, p->bits_dev, bits_bytes, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_step_plan_run_host: %s", cudaGetErrorString(e));
   return GC_OK;
@@ -970,7 +1023,14 @@ int gc_stats_reduce(const uint32_t* state, const uint32_t* collisions, const gc_
   if (int rc = gc_require_device()) return rc;
   unsigned grid = grid_for(n);
   if (grid > 148u * 8u) grid = 148u * 8u;  // grid-stride: one resident wave
-  stats_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(lv, n_levels > 1 ? level_id : nullptr,
+  static StatsSubtasks sub;  // 2 KB: filled per call, passed by value
+  memset(&sub, 0, sizeof(sub));
+  for (int l = 0; l < n_levels; l++) {
+    const int ns = levels[l].n_subtasks < 0 ? 0 : (levels[l].n_subtasks > GC_MAX_SUBTASKS ? GC_MAX_SUBTASKS : levels[l].n_subtasks);
+    sub.n[l] = (uint8_t)ns;
+    for (int q = 0; q < ns; q++) sub.st[l][q] = levels[l].subtask[q];
+  }
+  stats_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(lv, sub, n_levels > 1 ? level_id : nullptr,
                                                             reinterpret_cast<const uint4*>(state), collisions,
                                                             reinterpret_cast<unsigned long long*>(stats), n);
   return gc_check_launch("gc_stats_reduce");

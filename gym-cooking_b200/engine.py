@@ -269,7 +269,7 @@ class KitchenBatch:
         return out
 
     def stats(self, out=None):
-        """Episode statistics vector (int64[133], include/gymcook.h GC_STATS_LEN); `out` is
+        """Episode statistics vector (int64[134], include/gymcook.h GC_STATS_LEN); `out` is
         accumulated into, so several shards / calls can share one vector."""
         with torch.cuda.device(self.device):
             if out is None:

@@ -106,11 +106,53 @@ def subtask_q(batch, pairs, want_q=True):
                                     _lib.ptr(status), batch.num_envs, batch.num_agents, batch._stream()))
         if has_joint:
             need = lib.gc_joint_q_scratch_bytes(batch.num_envs, len(pairs), None)
-            scratch = getattr(batch, "_joint_scratch", None)
+            owner = getattr(batch, "_batch", batch)  # a state view keeps the arena on its KitchenBatch
+            scratch = getattr(owner, "_joint_scratch", None)
             if scratch is None or scratch.numel() < need:
-                scratch = batch._joint_scratch = torch.empty(need, dtype=torch.uint8, device=batch.device)
+                scratch = owner._joint_scratch = torch.empty(need, dtype=torch.uint8, device=batch.device)
             _lib.check(lib.gc_joint_q(batch._lv(), batch.n_levels, _lib.ptr(batch.level_id), _lib.ptr(batch.state),
                                       arr.ctypes.data_as(C.c_void_p), len(pairs), _lib.ptr(v), _lib.ptr(q),
                                       _lib.ptr(status), _lib.ptr(scratch), scratch.numel(), batch.num_envs,
                                       batch.num_agents, batch._stream()))
     return v, (q if want_q else None), status
+
+
+_T_MASK = ~0xFF000000  # clears t and done of word 0 inside the low int64 of a packed state
+
+
+class _StateView:
+    """What the planner entry points need from a KitchenBatch, over another state tensor of the same level(s)."""
+
+    def __init__(self, batch, state, level_id=None):
+        self._batch = batch
+        self.num_agents, self.n_levels, self.device = batch.num_agents, batch.n_levels, batch.device
+        self.state, self.num_envs, self.level_id = state, state.shape[0], level_id
+
+    def _lv(self):
+        return self._batch._lv()
+
+    def _stream(self):
+        return self._batch._stream()
+
+
+def subtask_q_unique(batch, pairs, want_q=True, chunk=1 << 16):
+    """subtask_q with every distinct PLANNING state of the batch solved once: the value of a (subtask, agents)
+    pair does not depend on t or the done bit, and in a large batch most envs share their planning state
+    with others (the batched form of the reference memoising v_l / v_u by state repr, e2e:216-352).
+    Returns (v[N][P], q[N][P][25] or None, status[N][P], n_unique).  Single-level batches."""
+    if batch.n_levels != 1:
+        raise _lib.GcError("subtask_q_unique needs a single-level batch")
+    key = batch.state.contiguous().view(torch.int64).clone()
+    key[:, 0] &= _T_MASK
+    uk, inv = torch.unique(key, dim=0, return_inverse=True)
+    U = uk.shape[0]
+    ustate = uk.contiguous().view(torch.int32)
+    vs, qs, ss = [], [], []
+    for lo in range(0, U, chunk):  # bounded scratch arena of the joint solver
+        v, q, st = subtask_q(_StateView(batch, ustate[lo:lo + chunk].contiguous()), pairs, want_q)
+        vs.append(v)
+        qs.append(q)
+        ss.append(st)
+    v, st = torch.cat(vs), torch.cat(ss)
+    q = torch.cat(qs) if want_q else None
+    return v[inv], (q[inv] if want_q else None), st[inv], U

@@ -18,7 +18,7 @@ def shard_range(n_total, rank, world_size):
 
 
 def reduce_stats(stats):
-    """Sum a per-rank statistics vector (int64[133]) over all ranks, in place."""
+    """Sum a per-rank statistics vector (int64[GC_STATS_LEN]) over all ranks, in place."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     return stats
@@ -27,5 +27,6 @@ def reduce_stats(stats):
 def stats_dict(stats):
     v = stats.tolist() if isinstance(stats, torch.Tensor) else list(stats)
     out = dict(zip(STATS_FIELDS, v[:5]))
-    out["t_histogram"] = v[5:]
+    out["t_histogram"] = v[5:133]
+    out["completed_subtasks"] = v[133] if len(v) > 133 else 0
     return out

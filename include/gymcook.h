@@ -228,8 +228,12 @@ int gc_state_hash(const uint32_t* state /*device*/, uint64_t* hash /*device*/, i
 
 /* ---- episode statistics (the Bag fields that survive batching; misc/metrics/metrics_bag.py:5-72)
  * stats[0] episodes  [1] successes  [2] sum of t over done envs  [3] sum collisions
- * [4] envs still running  [5..5+128) histogram of t over done envs */
-#define GC_STATS_LEN 133
+ * [4] envs still running  [5..5+128) histogram of t over done envs
+ * [133] sum over envs of completed subtasks, read off the state with the levels' subtask tables
+ *       (gc_level_set_subtasks): Chop(X) once X is chopped in some live object, Merge(a, b) once an
+ *       object contains a | b, Deliver(m) once m lies on a Delivery square - the batched form of the
+ *       Bag's num_completed_subtasks (metrics_bag.py:55-61) */
+#define GC_STATS_LEN 134
 int gc_stats_reduce(const uint32_t* state /*device*/, const uint32_t* collisions /*device, nullable*/,
                     const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
                     uint64_t* stats /*device uint64[GC_STATS_LEN], accumulated into*/,

@@ -246,6 +246,19 @@ def test_stats_reduce():
     assert s[2] == int(t[done == 1].sum())
     assert s[3] == int(kb.collisions.sum())
     assert (s[5:5 + 128] == np.bincount(t[done == 1], minlength=128)).all()
+    # [133]: completed subtasks read off the states (random walks chop and plate now and then)
+    slots = O.slots_of(st)
+    mask, holder, cell = slots & 0x7F, slots >> 13, (slots >> 7) & 63
+    want = 0
+    for sub in kb.subtasks[0]:
+        kind, _, _, goal = gcb.recipe_planner.subtask_masks(sub)
+        live = holder != 7
+        if kind == 3:  # Deliver: the goal object lies on the Delivery square (3, 0) -> cell 24
+            hit = live & (holder == 0) & (mask == goal) & (cell == 3 * 8 + 0)
+        else:
+            hit = live & ((mask & goal) == goal)
+        want += int(hit.any(axis=1).sum())
+    assert s[133] == want and want > 0
 
 
 def test_empty_and_ragged_sizes():

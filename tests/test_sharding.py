@@ -22,10 +22,10 @@ def _stats(lo, hi):
     rd, coll, _ = O.rollout_batch(lv, st, N_AGENTS, STEPS, env0=lo, seed=99)
     t = (st[:, 0] >> 24) & 127
     done = st[:, 0] >> 31
-    out = np.zeros(133, dtype=np.int64)
+    out = np.zeros(134, dtype=np.int64)
     out[0], out[1], out[2] = hi - lo, int(((done == 1) & (t < MAX_T)).sum()), int(t[done == 1].sum())
     out[3], out[4] = int(coll.sum()), int((done == 0).sum())
-    out[5:] = np.bincount(t[done == 1], minlength=128)
+    out[5:133] = np.bincount(t[done == 1], minlength=128)
     return out
 
 
