@@ -325,8 +325,10 @@ def run_ours(args):
         achieved = BYTES_PER_ENV_STEP * N_ENVS / launch_s / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        traffic_note = None
+        if os.path.exists(tpath):  # from the committed ncu capture of this kernel, not measured in this run
+            tj = json.load(open(tpath))
+            traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note")
         cpu_value, cpu_dt = cpu_port_rate(1 << 18, HORIZON, 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -350,9 +352,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "step2_kernel<NA=2,NOBJ=4,EXTRAS=0,BITS=0,MULTI=0> (gc_env_step, plain step)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "bytes_per_launch": BYTES_PER_ENV_STEP * N_ENVS, "launch_us": launch_s * 1e6,
-                         "traffic": traffic},
+                         "traffic": traffic, "traffic_source": traffic_note},
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": "2^18 envs x 100 steps of the same action stream, %.1f s" % cpu_dt},
+                             "sample": "2^18 envs x 100 steps of the same action stream, %.1f s" % cpu_dt,
+                             "python_reference": python_reference_numbers()},
             "secondary": secondary,
             "episode_stats": {"episodes": stats[0], "successes": stats[1], "sum_t_done": stats[2],
                               "running": stats[4], "reduced_with": "nccl all_reduce" if world > 1 else "single rank"},
@@ -372,6 +375,27 @@ def graph_upload(g, stream):
         return rt.cudaGraphUpload(g.raw_cuda_graph_exec(), stream.cuda_stream) == 0
     except Exception:
         return False
+
+
+def python_reference_numbers():
+    """Timings of the unmodified Python reference (main.py single process and a multiprocessing pool, env.step
+    alone, bayes_update alone) taken by oracle/time_reference.py in the build container - the reference cannot
+    travel to the GPU box, so these are attached from profiles/, not measured in this run."""
+    path = os.path.join(ROOT, "profiles", "r02_python_reference_cpu.json")
+    if not os.path.exists(path):
+        return None
+    d = json.load(open(path))
+    pick = lambda k, *f: {x: d[k][x] for x in f if x in d.get(k, {})}
+    return {"kind": "python-reference", "where": d.get("where"), "cores": d.get("cores"),
+            "env_step_1core": pick("C3_env_step_1core", "agent_steps_per_sec"),
+            "env_step_pool8": pick("C3_env_step_pool8", "agent_steps_per_sec"),
+            "main_py_cfg1_single_process": pick("C1_main_loop_cfg1", "agent_steps_per_sec", "posterior_updates_per_sec",
+                                                "env_steps", "seconds", "finished"),
+            "main_py_tomato_episode": pick("C1_finished_episode_tomato", "agent_steps_per_sec", "env_steps", "seconds",
+                                           "finished"),
+            "main_py_cfg1_pool8": pick("C2_main_loop_pool8", "agent_steps_per_sec", "posterior_updates_per_sec",
+                                       "wall_seconds"),
+            "bayes_update_per_core": pick("C5_bayes_update", "posterior_updates_per_sec_per_core")}
 
 
 def hbm_peak_gbs():
@@ -433,7 +457,8 @@ def secondary_metrics(gcb, torch, dev):
                 "config": "cfg-4: 2-agent open-divider_salad, bd/bd, 2^18 envs, horizon %d, from reset with a cold planner "
                           "memo; finished envs leave the working batch" % loop_steps,
                 "posterior_updates_per_sec": loop.posterior_updates / dt, "seconds": dt, "loop_steps": done_steps,
-                "delivered": st[1], "mean_steps_of_delivered": st[2] / max(st[1], 1),
+                "delivered": st[1],
+                "mean_steps_of_delivered": sum(t_ * c for t_, c in enumerate(st[5:5 + loop_steps])) / max(st[1], 1),
                 "completed_subtasks": st[133], "planning_states_solved": loop.cache.solved_states,
                 "planner_lookups": loop.cache.lookups})
     del loop
