@@ -6,9 +6,12 @@
 // (114,93,51) border; delivery (96,96,96) + sprite; cutboard = counter + sprite; lying objects at
 // tile size (plated contents 56 px at +12); agents at tile size; the held object 40 px at +40
 // (its plated contents 28 px at +46).  Sprites come from a caller-supplied RGBA atlas
-// uint8[GC_N_SPRITES][80][80][4] (gym_cooking_b200.render builds one procedurally, or from the
-// reference's PNG files when they are available); smaller sizes are nearest-neighbour samples
-// of the 80 px sprite, blits are "over" alpha compositing like pygame's per-pixel-alpha blit.
+// uint8[GC_N_SPRITES][4][80][80][4]: every sprite pre-scaled to the four sizes the reference draws
+// at (80, 56, 40, 28 px, each in the top-left corner of its own 80 x 80 frame) - game.py:105-108
+// scales the ORIGINAL image to the blit size every time, so sampling an 80 px copy again would pick
+// different source pixels (gym_cooking_b200.render builds the atlas procedurally, or from the
+// reference's PNG files when they are available); blits are "over" alpha compositing like pygame's
+// per-pixel-alpha blit.
 // Output is RGB (the reference's get_image_obs writes (g, b, r) of a mapped pixel value,
 // gameimage.py:48-50, which depends on the surface format - image parity is unpinned).
 //
@@ -42,8 +45,8 @@ __device__ __forceinline__ void blit(const uint8_t* __restrict__ atlas, int sp, 
                                      float (&rgb)[3]) {
   const int lx = px - off, ly = py - off;
   if (lx < 0 || ly < 0 || lx >= size || ly >= size) return;
-  const int sx = lx * kTile / size, sy = ly * kTile / size;  // nearest-neighbour scale
-  const uchar4 t = *reinterpret_cast<const uchar4*>(atlas + (size_t)sp * kSpriteBytes + (sy * kTile + sx) * 4);
+  const int level = size == kTile ? 0 : size == 56 ? 1 : size == 40 ? 2 : 3;  // the frame pre-scaled to `size`
+  const uchar4 t = *reinterpret_cast<const uchar4*>(atlas + ((size_t)sp * 4 + level) * kSpriteBytes + (ly * kTile + lx) * 4);
   const float a = t.w * (1.0f / 255.0f);
   rgb[0] = t.x * a + rgb[0] * (1.0f - a);
   rgb[1] = t.y * a + rgb[1] * (1.0f - a);
@@ -155,7 +158,7 @@ int gc_render(const gc_level* levels, int n_levels, const uint8_t* level_id, con
   if (n_agents < 1 || n_agents > GC_MAX_AGENTS) return gc_fail(GC_E_ARG, "n_agents must be 1..4");
   if (int rc = gc_nav_levels_to_dev(levels, n_levels, &lv)) return rc;
   if (!state || !img || m < 0) return gc_fail(GC_E_ARG, "gc_render: null state/img or m < 0");
-  if (!sprites) return gc_fail(GC_E_ARG, "gc_render: a sprite atlas uint8[%d][80][80][4] is required", 7 + 64);
+  if (!sprites) return gc_fail(GC_E_ARG, "gc_render: a sprite atlas uint8[%d][4][80][80][4] is required", 7 + 64);
   if (n_levels > 1 && !level_id) return gc_fail(GC_E_ARG, "gc_render: n_levels > 1 needs level_id");
   for (int l = 1; l < n_levels; l++)
     if (levels[l].width != levels[0].width || levels[l].height != levels[0].height)

@@ -333,7 +333,11 @@ int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id /*d
                void* stream);
 
 /* ---- (A') optional image_obs renderer -------------------------------------------------
- * misc/game/game.py:56-185 geometry (80 px tiles) -> uint8[m][H*80][W*80][3], RGB. */
+ * misc/game/game.py:56-185 geometry (80 px tiles) -> uint8[m][H*80][W*80][3], RGB.
+ * `sprites`: device uint8[71][4][80][80][4] RGBA atlas - sprite 0 delivery, 1 cutboard, 2 plate, 3-6 agents
+ * (blue, magenta, yellow, green), 7 + code food sprites with code = (mask & 7) | ((mask >> 4) & 7) << 3;
+ * every sprite pre-scaled to the four sizes the reference draws at (frame 0: 80 px, 1: 56, 2: 40, 3: 28, in
+ * the top-left corner of an 80 x 80 frame). */
 int gc_render(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
               const uint32_t* state /*device*/, const uint8_t* sprites /*device, nullable*/,
               uint8_t* img /*device*/, int64_t m, int n_agents, void* stream);

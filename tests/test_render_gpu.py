@@ -12,8 +12,7 @@ T = 80
 
 
 def _over(dst, spr, size, off_x, off_y):
-    idx = (np.arange(size) * T) // size
-    s = spr[idx][:, idx].astype(np.float32)
+    s = spr[R.SIZES.index(size), :size, :size].astype(np.float32)  # the frame pre-scaled to `size`
     a = s[..., 3:4] / 255.0
     box = dst[off_y:off_y + size, off_x:off_x + size]
     box[...] = s[..., :3] * a + box * (1 - a)
@@ -98,3 +97,24 @@ def test_facade_image_obs():
     env2 = gcb.OvercookedEnvironment(ns)
     env2.reset()
     assert env2.step({"agent-1": (0, 0), "agent-2": (0, 0)})[3]["image_obs"] is None
+
+
+def test_render_matches_the_reference_drawing_code(golden_dir):
+    """tests/golden/render.npz: eight reference env states drawn by the reference's own Game.on_render
+    (misc/game/game.py:56-185, unmodified) over a PIL-backed pygame stand-in (oracle/gen_golden_render.py), and
+    the sprite atlas built from the reference's PNG files.  gc_render must reproduce every image within +-1
+    (rounding of the alpha blend): squares, objects, agents, held and plated items, sizes, offsets, colours,
+    draw order."""
+    import os
+    g = np.load(os.path.join(golden_dir, "render.npz"))
+    atlas = g["atlas"]
+    assert atlas.shape == (R.N_SPRITES, len(R.SIZES), T, T, 4)
+    for r in range(g["state"].shape[0]):
+        level, n_agents = str(g["levels"][g["level"][r]]), int(g["n_agents"][r])
+        kb = gcb.KitchenBatch(level, n_agents, 1, 100)
+        kb.state.copy_(torch.from_numpy(g["state"][r:r + 1].view(np.int32)).to(kb.device))
+        img = R.render(kb, atlas).cpu().numpy()[0]
+        want = g["image"][r]
+        assert img.shape == want.shape
+        diff = np.abs(img.astype(np.int32) - want.astype(np.int32))
+        assert diff.max() <= 1, (r, level, int(diff.max()), int((diff > 1).sum()))
