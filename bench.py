@@ -334,12 +334,14 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": dict(workload_config(world), launch=(
-                "CUDA graphs of up to %d consecutive steps (captured and uploaded before the timed region)" % GRAPH_STEPS
-                if use_graphs else "one gc_env_step call per step from a Python loop"),
-                launch_ab={"mode": "python loop, one gc_env_step call per step" if use_graphs else "CUDA graphs",
-                           "steps": ab_steps, "us_per_step": ab_ms * 1e3 / ab_steps,
-                           "value": world * ab_steps * N_ENVS * N_AGENTS / (ab_ms * 1e-3)}), "clocks": clocks,
+            # `config` is the workload only (identical in both arms); how the steps were launched is its own key
+            "config": workload_config(world),
+            "launch": {"mode": ("CUDA graphs of up to %d consecutive steps (captured and uploaded before the timed region)"
+                                % GRAPH_STEPS if use_graphs else "one gc_env_step call per step from a Python loop"),
+                       "ab": {"mode": "python loop, one gc_env_step call per step" if use_graphs else "CUDA graphs",
+                              "steps": ab_steps, "us_per_step": ab_ms * 1e3 / ab_steps,
+                              "value": world * ab_steps * N_ENVS * N_AGENTS / (ab_ms * 1e-3)}},
+            "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_ENVS,
                     "d2h_bytes_per_step": (N_ENVS + 31) // 32 * 8,
                     "results": "done / reward bit planes (2 bits per env)",
