@@ -51,6 +51,9 @@ constexpr uint32_t kSlots2 = 1u << 17;
 #ifndef GC_JOINT_MAX_SLACK
 #define GC_JOINT_MAX_SLACK 48
 #endif
+#ifndef GC_JOINT_CTAS_PER_SM_DEFAULT
+#define GC_JOINT_CTAS_PER_SM_DEFAULT 16
+#endif
 constexpr uint32_t kMaxStates2 = GC_JOINT_MAX_STATES;
 constexpr int64_t kWideProblems = 32 * 1024;
 // one search per CTA: large batches run 4 CTAs of 128 threads per SM (throughput); small ones
@@ -878,7 +881,29 @@ static void joint_ctas(int64_t n, int n_pairs, int* tree_ctas, int* act_ctas, bo
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
-  const int64_t cap = (int64_t)sms * 4, problems = n * n_pairs;
+  // resident searches per SM: the searches are latency-bound on their global-memory arenas (3.5 % issue
+  // utilisation at 4 CTAs of 128 threads per SM, profiles/r02_planner_kernels_ncu.csv), so more of them in
+  // flight per SM hide more of that latency: 16 CTAs of 64 threads (64 registers each) solve cfg-3's states
+  // 2.0x faster than 4 x 128 (6.4 -> 3.2 s for 2^18 envs, scripts/joint_ctas_probe.sh).  Each search owns an
+  // 18 MB arena: 43 GB of the 180 GB at full width, capped at a quarter of the device memory.
+  // GC_JOINT_CTAS_PER_SM=k overrides.
+  static const int per_sm = [] {
+    const char* e = getenv("GC_JOINT_CTAS_PER_SM");
+    const int v = e ? atoi(e) : GC_JOINT_CTAS_PER_SM_DEFAULT;
+    return v >= 1 && v <= 16 ? v : GC_JOINT_CTAS_PER_SM_DEFAULT;
+  }();
+  static const int64_t arena_cap = [] {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+      cudaGetLastError();
+      total_b = (size_t)64 << 30;
+    }
+    const int64_t k = (int64_t)(total_b / 4 / sizeof(Arena2));
+    return k < 64 ? (int64_t)64 : k;
+  }();
+  int64_t cap = (int64_t)sms * per_sm;
+  if (cap > arena_cap) cap = arena_cap;
+  const int64_t problems = n * n_pairs;
   *tree_ctas = (int)(problems < cap ? (problems > 0 ? problems : 1) : cap);
   *act_ctas = (int)(problems * 25 < cap ? (problems > 0 ? problems * 25 : 1) : cap);
   if (wide) *wide = false;
@@ -932,7 +957,11 @@ int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, co
     // states it has not seen yet): 2 CTAs of 512 threads per SM, so that more hash / edge atomics are in
     // flight per search (a 96 K-state search is latency bound: 1.6x faster on the wide CTA)
     static const int64_t wide_limit = getenv("GC_JOINT_WIDE_PROBLEMS") ? atoll(getenv("GC_JOINT_WIDE_PROBLEMS")) : kWideProblems;
-    if (probs > wide_limit) {
+    static const bool narrow = !(getenv("GC_JOINT_THREADS") && atoi(getenv("GC_JOINT_THREADS")) == 128);  // 128: the round-1 shape
+    if (probs > wide_limit && narrow) {
+      joint_tree_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(
+          lv, pr, lid, s4, reinterpret_cast<Arena2*>(base), q, flags, todo, n, n_agents, kMaxStates2);
+    } else if (probs > wide_limit) {
       joint_tree_kernel<kThreads><<<(unsigned)tree_ctas, kThreads, 0, st>>>(
           lv, pr, lid, s4, reinterpret_cast<Arena2*>(base), q, flags, todo, n, n_agents, kMaxStates2);
     } else {

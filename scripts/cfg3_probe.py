@@ -16,7 +16,7 @@ def diversified(n, seed=1235):
     return kb
 
 
-for logn in (12, 16, 18, 20):
+for logn in (12, 16, 18, 20) if not os.environ.get("GC_JOINT_CTAS_PER_SM") else (16, 18):
     n = 1 << logn
     kb = diversified(n)
     ns = len(kb.subtasks[0])
