@@ -216,8 +216,8 @@ GC_HD uint32_t step(Env<NOBJ>& e, uint32_t aw, const StaticTables& S, const Leve
       const bool same = nxt[i] == nxt[j];
       const bool swap = (cell[i] == nxt[j]) & (cell[j] == nxt[i]);
       const bool bi = k8[i] != 0u, bj = k8[j] != 0u;
-      cancel[i] |= (same & !bi) | (!same & swap);
-      cancel[j] |= (same & (bi | !bj)) | (!same & swap);
+      cancel[i] |= same ? !bi : swap;
+      cancel[j] |= same ? (bi | !bj) : swap;
       if (WANT_EXEC) ncoll += (same | swap) ? 1u : 0u;
     }
   }
