@@ -305,3 +305,25 @@ def test_tree_search_equals_per_action_search(tmp_path):
         assert (np.isnan(qa) == np.isnan(qb)).all() and (qa[~np.isnan(qa)] == qb[~np.isnan(qb)]).all(), lv
         compared += int(both.sum())
     assert compared >= 2000, compared
+
+
+def test_subtask_q_unique_equals_subtask_q():
+    """planning.subtask_q_unique (each distinct planning state of the batch solved once) returns, env by env,
+    what subtask_q returns - t and the done bit do not enter a (subtask, agents) value."""
+    n = 6000
+    kb = gcb.KitchenBatch("partial-divider_salad", 2, n, 100)
+    acts = kb.random_actions(30, seed=8)
+    idx = torch.arange(n, device=kb.device) % 31
+    for s in range(30):
+        a = acts[s].clone()
+        a[idx <= s] = 4
+        kb.step(a)
+    ns = len(kb.subtasks[0])
+    pairs = [(s, i, j) for s in range(ns) for (i, j) in ((0, None), (1, None), (0, 1))]
+    v, q, st = gcb.subtask_q(kb, pairs)
+    v2, q2, st2, n_unique = gcb.subtask_q_unique(kb, pairs)
+    assert 1 < n_unique < n
+    assert torch.equal(st, st2)
+    ok = st == 0  # budget-limited searches (status 3) may prove different subsets of Q
+    assert torch.equal(torch.nan_to_num(v[ok], posinf=1e9), torch.nan_to_num(v2[ok], posinf=1e9))
+    assert torch.equal(torch.nan_to_num(q[ok], nan=-1.0, posinf=1e9), torch.nan_to_num(q2[ok], nan=-1.0, posinf=1e9))
