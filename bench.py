@@ -443,6 +443,31 @@ def secondary_metrics(gcb, torch, dev):
                 "bytes_per_update": bytes_per, "achieved_gbs": n * bytes_per / t / 1e9,
                 "roofline_frac": n * bytes_per / t / 1e9 / hbm_peak_gbs()[0]})
     del probs, hyp, w, qd, nv, ai
+    # cfg-5, env half: 4 agents, per-env level id uniform over the nine levels, 2^20 envs, philox actions
+    # (seed 1236) - step2_kernel<4,4,EXTRAS=0,MULTI=1>; ring of 4 batches (80 MB of state + actions per step)
+    n5, ring5 = 1 << 20, 4
+    g5 = torch.Generator(device="cpu").manual_seed(1236)
+    kbs = []
+    for r in range(ring5):
+        lid = torch.randint(0, 9, (n5,), generator=g5, dtype=torch.uint8)
+        kbs.append(gcb.KitchenBatch(list(gcb.levels.LEVEL_NAMES), 4, n5, HORIZON, device=dev, level_id=lid))
+    acts5 = [kb.random_actions(24, seed=1236 + r) for r, kb in enumerate(kbs)]
+    k5 = [0]
+
+    def step5():
+        r, t_ = k5[0] % ring5, (k5[0] // ring5) % 24
+        kbs[r].step(acts5[r][t_])
+        k5[0] += 1
+
+    t = timed(step5, 60, warm=8)
+    b5 = n5 * (33 + 4 + 1)  # 16 + 16 + 4 action bytes + 1 reward/done byte + 1 level id byte
+    out.append({"metric": "agent_steps_per_sec_cfg5_env", "value": n5 * 4 / t, "unit": "agent-steps/s",
+                "config": "cfg-5 env half: 4 agents, nine-level mix (per-env level id), 2^20 envs per launch, plain Python loop",
+                "us_per_step": t * 1e6,
+                "roofline": {"bound": "hbm", "kernel": "step2_kernel<NA=4,NOBJ=4,EXTRAS=0,BITS=0,MULTI=1>", "bytes_per_unit": 38,
+                             "achieved": b5 / t / 1e9, "peak": hbm_peak_gbs()[0], "unit": "GB/s",
+                             "frac": b5 / t / 1e9 / hbm_peak_gbs()[0]}})
+    del kbs, acts5
     # cfg-4: the device-resident Bayesian-Delegation loop (2-agent open-divider_salad, bd/bd): lower bounds +
     # exact Q through the planning-state memo + posterior + action selection + env step, 2^18 envs x 100
     # loop steps as SURVEY 8d states it, wall clock with a sync on both sides

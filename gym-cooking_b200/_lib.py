@@ -48,6 +48,7 @@ _SIGNATURES = {
     "gc_level_parse": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(Level)]),
     "gc_level_set_subtasks": (C.c_int, [C.POINTER(Level), C.POINTER(Subtask), C.c_int]),
     "gc_env_reset": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, C.c_int64, C.c_int, _VOIDP]),
+    "gc_env_prepare": (C.c_int, [C.POINTER(Level), C.c_int, C.c_int]),
     "gc_env_step": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP,
                               _VOIDP, C.c_int64, C.c_int, _VOIDP]),
     "gc_env_step_host": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP,

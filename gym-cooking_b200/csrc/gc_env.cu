@@ -7,6 +7,7 @@
 #include "gc_host.h"
 #include "gc_step2.cuh"
 
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -329,12 +330,20 @@ constexpr size_t kTablesHead = sizeof(gcs2::StaticTables);
 __host__ __device__ constexpr size_t tables_bytes(int n_levels) { return kTablesHead + (size_t)n_levels * sizeof(gcs2::LevelTables); }
 static_assert(kTablesHead % 16 == 0 && sizeof(gcs2::LevelTables) % 16 == 0, "tables are copied as uint4");
 
+// the tables depend on the map, the objects, the goals and the horizon - not on the subtask list that
+// gc_level_set_subtasks rewrites: the key is the part of gc_level in front of it
+constexpr size_t kLevelKeyBytes = offsetof(gc_level, subtask);
 struct TableCacheEntry {
   int device, n_levels, n_agents;
   uint64_t stamp;
-  gc_level levels[GC_MAX_LEVELS];
+  uint8_t key[GC_MAX_LEVELS][kLevelKeyBytes];
   DeviceTables* dev_ptr;
 };
+inline bool same_levels(const TableCacheEntry& e, const gc_level* levels, int n_levels) {
+  for (int l = 0; l < n_levels; l++)
+    if (memcmp(e.key[l], &levels[l], kLevelKeyBytes) != 0) return false;
+  return true;
+}
 // Every CTA of a launch copies the tables into its shared memory at the same moment: kTableCopies copies at
 // different addresses spread those reads over the L2 slices instead of queueing ~900 CTAs on the same 59
 // lines (GC_STEP_TABLE_COPIES=1 restores the single copy for A/B timing).
@@ -358,8 +367,7 @@ const DeviceTables* tables_for(const gc_level* levels, int n_levels, int n_agent
   std::lock_guard<std::mutex> lock(g_table_mutex);
   for (int k = 0; k < g_table_cache_used; k++) {
     TableCacheEntry& e = g_table_cache[k];
-    if (e.device == dev && e.n_levels == n_levels && e.n_agents == n_agents &&
-        memcmp(e.levels, levels, sizeof(gc_level) * (size_t)n_levels) == 0) {
+    if (e.device == dev && e.n_levels == n_levels && e.n_agents == n_agents && same_levels(e, levels, n_levels)) {
       e.stamp = ++g_table_stamp;
       return e.dev_ptr;
     }
@@ -397,7 +405,7 @@ const DeviceTables* tables_for(const gc_level* levels, int n_levels, int n_agent
   e.n_levels = n_levels;
   e.n_agents = n_agents;
   e.stamp = ++g_table_stamp;
-  memcpy(e.levels, levels, sizeof(gc_level) * (size_t)n_levels);
+  for (int l = 0; l < n_levels; l++) memcpy(e.key[l], &levels[l], kLevelKeyBytes);
   e.dev_ptr = d;
   if (slot == g_table_cache_used) g_table_cache_used++;
   return d;
@@ -485,6 +493,37 @@ __device__ __forceinline__ void step2_one(const gcs2::StaticTables& S, const gcs
   }
 }
 
+// Two envs of one thread, branch-free (ILP variant of the plain step): both transitions are computed in one
+// basic block so that the compiler can interleave their instruction streams; a finished (or out-of-range:
+// frozen) env computes a transition that is thrown away - its stores are predicated off.
+template <int NA, int NOBJ>
+__device__ __forceinline__ void step2_pair(const gcs2::StaticTables& S, const gcs2::LevelTables& L, const Step2Args& A,
+                                           uint4 (&s)[2], const uint32_t (&aw)[2], const uint32_t (&idx)[2],
+                                           const bool (&valid)[2]) {
+  bool done[2], success[2], live[2];
+  uint32_t exec;
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    live[u] = !(s[u].x >> 31);
+    const bool old_success = !(L.max_t24 != 0u && (s[u].x & 0x7F000000u) >= L.max_t24);
+    gcs2::Env<NOBJ> e;
+    gcs2::unpack<NOBJ>(s[u].x, s[u].y, s[u].z, s[u].w, e);
+    e.x &= 0x7FFFFFFFu;  // the transition assumes the done bit clear
+    gcs2::step<NA, NOBJ, false>(e, aw[u], S, L, done[u], success[u], exec);
+    gcs2::pack<NOBJ>(e, s[u].x, s[u].y, s[u].z, s[u].w);
+    done[u] = live[u] ? done[u] : true;
+    success[u] = live[u] ? success[u] : old_success;
+  }
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    if (live[u]) gc::st_stream(A.state + idx[u], s[u]);
+    if (valid[u]) A.reward_done[idx[u]] = (uint8_t)((done[u] ? GC_RD_DONE : 0) | (success[u] ? GC_RD_REWARD : 0));
+  }
+}
+
+#ifndef GC_STEP2_ILP
+#define GC_STEP2_ILP 1  // 2: two envs per thread and iteration (plain single-level step only)
+#endif
 #ifndef GC_STEP2_L2_AHEAD
 #define GC_STEP2_L2_AHEAD 1  // pull the tile after next into L2 while the next one loads into registers (-0.3 us per 2^20-env launch)
 #endif
@@ -569,6 +608,41 @@ step2_kernel(const __grid_constant__ Step2Args A) {
   // first version of this loop) the first use of the current state also waited for the loads just issued -
   // a prefetch distance of zero, 7.3 warps per issue slot parked on the long scoreboard
   // (profiles/r02_step2_v1_ncu.csv).
+#if GC_STEP2_ILP == 2
+  if constexpr (!EXTRAS && !BITS && !MULTI) {
+    // two tiles per iteration: envs i and i + stride; the pair after that prefetched into registers
+    uint4 t_next = frozen;
+    uint32_t b_next = 0;
+    if (i + stride < n) {
+      t_next = gc::ld_stream(A.state + i + stride);
+      b_next = JOINT ? load_joint_raw<NA>(A.actions, i + stride) : load_actions_raw<NA>(A.actions, i + stride);
+    }
+#pragma unroll 1
+    for (; i < n; i += 2u * stride) {
+      uint4 s[2] = {s_next, t_next};
+      const uint32_t aw[2] = {JOINT ? joint_to_bytes<NA>(a_next) : a_next, JOINT ? joint_to_bytes<NA>(b_next) : b_next};
+      const uint32_t idx[2] = {i, i + stride};
+      const bool valid[2] = {true, i + stride < n};
+      const uint32_t n0 = i + 2u * stride, n1 = i + 3u * stride;
+      s_next = frozen;
+      t_next = frozen;
+      if (n0 < n) {
+        s_next = gc::ld_stream(A.state + n0);
+        a_next = JOINT ? load_joint_raw<NA>(A.actions, n0) : load_actions_raw<NA>(A.actions, n0);
+      }
+      if (n1 < n) {
+        t_next = gc::ld_stream(A.state + n1);
+        b_next = JOINT ? load_joint_raw<NA>(A.actions, n1) : load_actions_raw<NA>(A.actions, n1);
+      }
+#if GC_STEP2_L2_AHEAD
+      l2_prefetch<JOINT ? (NA == 4 ? 2 : 1) : NA>(A, n0 + 2u * stride, n);
+      l2_prefetch<JOINT ? (NA == 4 ? 2 : 1) : NA>(A, n1 + 2u * stride, n);
+#endif
+      step2_pair<NA, NOBJ>(S, LV[0], A, s, aw, idx, valid);
+    }
+    return;
+  }
+#endif
 #pragma unroll 1
   for (; BITS ? (i - lane < n) : (i < n); i += stride) {
     const uint4 s = s_next;
@@ -822,6 +896,14 @@ int gc_env_reset(const gc_level* levels, int n_levels, const uint8_t* level_id, 
   reset_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(lv, n_levels > 1 ? level_id : nullptr,
                                                                   reinterpret_cast<uint4*>(state), n);
   return gc_check_launch("gc_env_reset");
+}
+
+int gc_env_prepare(const gc_level* levels, int n_levels, int n_agents) {
+  GcLevelsDev lv;
+  int max_objs = 0;
+  if (int rc = gc_levels_to_dev(levels, n_levels, n_agents, &lv, &max_objs)) return rc;
+  if (int rc = gc_require_device()) return rc;
+  return tables_for(levels, n_levels, n_agents) ? GC_OK : GC_E_CUDA;
 }
 
 // gc_env_step plus the optional bit planes of the results (internal: gc_env_step_host)

@@ -53,6 +53,8 @@ class KitchenBatch:
         else:
             self.level_id = None
         self._plans = {}  # prepared steps (gc_step_plan), by action format
+        with torch.cuda.device(self.device):  # device tables now, so that a first step inside a graph capture works
+            _lib.check(self.lib.gc_env_prepare(self._lv(), self.n_levels, self.num_agents))
         self.reset()
 
     def __del__(self):

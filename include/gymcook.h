@@ -159,6 +159,11 @@ int gc_level_set_subtasks(gc_level* lvl, const gc_subtask* subtasks, int n);
 int gc_env_reset(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
                  uint32_t* state /*device uint32[n][4]*/, int64_t n, int n_agents, void* stream);
 
+/* Builds and caches the device tables of a level set on the current device (what the first gc_env_step /
+ * gc_env_rollout of that level set does implicitly: an allocation and a synchronous copy).  Call it before a
+ * stream capture whose first captured operation would be that first step. */
+int gc_env_prepare(const gc_level* levels, int n_levels, int n_agents);
+
 /* step(): one joint transition for n envs, in place (env.step :255-306: t+=1,
  * check_collisions :724-762, execute_navigation :767-770 -> interact, done/reward :316-376).
  * Envs whose done bit is set are left untouched (sticky done) and report their old outcome.

@@ -9,15 +9,15 @@ build() {  # name, extra nvcc flags
   GC_LIBGYMCOOK=$PWD/build/variants/libgymcook_$name.so GC_NVCC_EXTRA="$*" python gym-cooking_b200/build.py > /dev/null
   echo built $name: "$@"
 }
-build c7 -DGC_STEP2_MIN_CTAS_ALL=7 &
-
-build t128 -DGC_STEP2_THREADS=128 -DGC_STEP2_MIN_CTAS_ALL=12 &
-
-
-wait
-build l2a -DGC_STEP2_L2_AHEAD=1 &
-build c7l2a -DGC_STEP2_L2_AHEAD=1 -DGC_STEP2_MIN_CTAS_ALL=7 &
-wait
-build c8 -DGC_STEP2_MIN_CTAS_ALL=8 &
-build c8l2a -DGC_STEP2_L2_AHEAD=1 -DGC_STEP2_MIN_CTAS_ALL=8 &
+for v in "$@"; do
+  case $v in
+    c7) build c7 -DGC_STEP2_MIN_CTAS_ALL=7 & ;;
+    c8) build c8 -DGC_STEP2_MIN_CTAS_ALL=8 & ;;
+    t128) build t128 -DGC_STEP2_THREADS=128 -DGC_STEP2_MIN_CTAS_ALL=12 & ;;
+    nol2a) build nol2a -DGC_STEP2_L2_AHEAD=0 & ;;
+    ilp2c4) build ilp2c4 -DGC_STEP2_ILP=2 -DGC_STEP2_MIN_CTAS_ALL=4 & ;;
+    ilp2c5) build ilp2c5 -DGC_STEP2_ILP=2 -DGC_STEP2_MIN_CTAS_ALL=5 & ;;
+    ilp2t128) build ilp2t128 -DGC_STEP2_ILP=2 -DGC_STEP2_THREADS=128 -DGC_STEP2_MIN_CTAS_ALL=8 & ;;
+  esac
+done
 wait
