@@ -257,8 +257,9 @@ def run_ours(args):
         ms, timed_launches = timed(lambda: run_loop(k, k + args.steps))
     clocks = sampler.stop()
     k += args.steps
-    # the other launch mode over the next `steps` steps (bounded), for the A/B line
-    ab_steps = min(args.steps, 2000)
+    # the other launch mode, for the A/B line: at least 400 steps (the first dozens of launches of a host loop
+    # are not pipelined yet; 20 steps would measure that ramp), at most 2000
+    ab_steps = min(max(args.steps, 400), 2000)
     if use_graphs:
         ab_ms, _ = timed(lambda: run_loop(k, k + ab_steps))
     else:
