@@ -1,8 +1,8 @@
 // gc_env.cu - path A kernels: reset, step, fused rollout, action stream, hash, statistics.
 // One thread per env; a warp is a tile of 32 envs whose 128-bit states are read and written
-// with one fully coalesced 512-byte transaction each way.  Static level tables arrive as
-// kernel parameters (constant bank, warp-uniform) when the batch has one level, and are
-// staged through shared memory when envs carry a per-env level id.
+// with one fully coalesced 512-byte transaction each way.  The default step (step2_kernel, on the byte planes
+// of gc_step2.cuh) stages cached device tables in shared memory; the generic kernels (step_kernel /
+// rollout_kernel on gc::step, the plain-ALU reference form) take the level bitboards as kernel parameters.
 #include "gc_device.cuh"
 #include "gc_host.h"
 #include "gc_step2.cuh"
