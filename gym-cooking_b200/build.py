@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("GC_LIBGYMCOOK") or os.path.join(PKG_DIR, "libgymcook.
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--use_fast_math", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    "--use_fast_math", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "--threads", "0",
 ]
 
 

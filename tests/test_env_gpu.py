@@ -377,3 +377,28 @@ def test_prepared_plans_and_joint_actions(level, n_agents, n):
         assert torch.equal(a.reward_done, ref.reward_done) and torch.equal(b.reward_done, ref.reward_done)
         assert np.array_equal(bits.numpy().view(np.uint32), _planes(ref.reward_done.cpu().numpy(), n)), "step %d" % s
     assert bool(ref.done.all())  # the horizon was reached: done / timeout bits were part of the comparison
+
+
+def test_table_cache_survives_more_level_sets_than_it_holds(tmp_path):
+    """The device-table cache holds 16 level sets and evicts the least recently used one: 20 distinct kitchens
+    (an extra counter on a different floor square each), stepped in turn and then again from the first, all
+    match the oracle."""
+    base = gcb.levels.level_text("open-divider_tomato").split("\n")
+    batches = []
+    for k in range(20):
+        rows = list(base)
+        y, x = 2 + k // 5, 1 + k % 5          # a floor square that is not an agent start ((2,1), (4,1) are in row 1)
+        rows[y] = rows[y][:x] + "-" + rows[y][x + 1:]
+        text = "\n".join(rows)
+        path = tmp_path / ("variant%d.txt" % k)
+        path.write_text(text)
+        kb = gcb.KitchenBatch(str(path), 2, 513, 100)
+        lv = O.parse_level(text, 100)
+        batches.append((kb, lv, O.reset_state(lv, 2, 513)))
+    for rnd in range(2):
+        for k, (kb, lv, ost) in enumerate(batches):
+            acts = kb.random_actions(6, seed=100 * rnd + k)
+            for s in range(6):
+                kb.step(acts[s])
+                O.step_batch(lv, ost, acts[s].cpu().numpy(), 2, want_collisions=False)
+            assert (_u32(kb.state) == ost).all(), (rnd, k)
