@@ -348,7 +348,7 @@ inline bool same_levels(const TableCacheEntry& e, const gc_level* levels, int n_
 // different addresses spread those reads over the L2 slices instead of queueing ~900 CTAs on the same 59
 // lines (GC_STEP_TABLE_COPIES=1 restores the single copy for A/B timing).
 constexpr int kTableCopies = 32;
-constexpr int kTableCache = 16;
+constexpr int kTableCache = 64;
 TableCacheEntry g_table_cache[kTableCache];
 int g_table_cache_used = 0;
 uint64_t g_table_stamp = 0;
@@ -356,8 +356,10 @@ std::mutex g_table_mutex;
 const gcs2::StaticTables g_static_tables_host = gcs2::make_static_tables();
 
 // device tables for this level set (nullptr + gc_last_error on failure).  The first call for a level set
-// allocates and copies (synchronously: do it outside a stream capture - KitchenBatch's constructor does,
-// through gc_env_reset); later calls are a memcmp.
+// allocates and copies (synchronously: do it outside a stream capture - gc_env_prepare, which KitchenBatch's
+// constructor calls); later calls are a memcmp.  The cache holds kTableCache level sets per process and evicts
+// the least recently used one; a CUDA graph captured with a level set's tables stays valid while the set is
+// cached.
 const DeviceTables* tables_for(const gc_level* levels, int n_levels, int n_agents) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) {
@@ -857,6 +859,7 @@ int launch_rollout(const gc_level* levels, int n_levels, const GcLevelsDev& lv, 
 // Everything gc_env_step derives per call (level validation, table lookup, argument block, launch
 // configuration) fixed once; a step is then one cudaLaunchKernelEx.
 struct gc_step_plan {
+  gc_level level;  // looked up in the table cache at every run: an evicted level set is rebuilt, never dangling
   int device, n_agents, flags;
   int64_t n;
   Step2Args args;
@@ -973,6 +976,7 @@ int gc_step_plan_create(const gc_level* level, uint32_t* state, uint8_t* reward_
   const DeviceTables* tables = tables_for(level, 1, n_agents);
   if (!tables) return GC_E_CUDA;
   gc_step_plan* p = new gc_step_plan();
+  p->level = *level;
   cudaGetDevice(&p->device);
   p->n_agents = n_agents;
   p->flags = flags;
@@ -1000,6 +1004,8 @@ int gc_step_plan_create(const gc_level* level, uint32_t* state, uint8_t* reward_
 int gc_step_plan_run(const gc_step_plan* p, const uint8_t* actions, void* stream) {
   if (!p || !actions) return gc_fail(GC_E_ARG, "gc_step_plan_run: null plan / actions");
   Step2Args A = p->args;
+  A.tables = tables_for(&p->level, 1, p->n_agents);  // a memcmp against the cached level sets
+  if (!A.tables) return GC_E_CUDA;
   A.actions = actions;
   const cudaError_t err = p->launch(A, (cudaStream_t)stream);
   if (err != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_step_plan_run: launch failed: %s", cudaGetErrorString(err));
@@ -1035,6 +1041,8 @@ int gc_step_plan_run_host(gc_step_plan* p, const uint8_t* actions_host, uint32_t
     cudaGetLastError();
   }
   Step2Args A = p->args;
+  A.tables = tables_for(&p->level, 1, p->n_agents);
+  if (!A.tables) return GC_E_CUDA;
   A.actions = p->actions_dev;
   A.rd_bits = p->zc_dev ? p->zc_dev : p->bits_dev;
   e = p->launch_bits(A, st);

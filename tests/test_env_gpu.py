@@ -380,15 +380,18 @@ def test_prepared_plans_and_joint_actions(level, n_agents, n):
 
 
 def test_table_cache_survives_more_level_sets_than_it_holds(tmp_path):
-    """The device-table cache holds 16 level sets and evicts the least recently used one: 20 distinct kitchens
-    (an extra counter on a different floor square each), stepped in turn and then again from the first, all
-    match the oracle."""
+    """The device-table cache holds 64 level sets and evicts the least recently used one: 72 distinct kitchens
+    (one or two extra counters on different floor squares), stepped in turn and then again from the first, all
+    match the oracle - prepared plans look their tables up again at every run, so an evicted set is rebuilt."""
     base = gcb.levels.level_text("open-divider_tomato").split("\n")
     batches = []
-    for k in range(20):
+    import itertools
+    combos = list(itertools.combinations(range(20), 2))[:72]
+    for k in range(72):
         rows = list(base)
-        y, x = 2 + k // 5, 1 + k % 5          # a floor square that is not an agent start ((2,1), (4,1) are in row 1)
-        rows[y] = rows[y][:x] + "-" + rows[y][x + 1:]
+        for sq in combos[k]:
+            y, x = 2 + sq // 5, 1 + sq % 5    # a floor square that is not an agent start ((2,1), (4,1) are in row 1)
+            rows[y] = rows[y][:x] + "-" + rows[y][x + 1:]
         text = "\n".join(rows)
         path = tmp_path / ("variant%d.txt" % k)
         path.write_text(text)
