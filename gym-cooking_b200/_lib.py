@@ -56,6 +56,7 @@ _SIGNATURES = {
     "gc_step_plan_create": (C.c_int, [C.POINTER(Level), _VOIDP, _VOIDP, C.c_int64, C.c_int, C.c_int, C.POINTER(_VOIDP)]),
     "gc_step_plan_run": (C.c_int, [_VOIDP, _VOIDP, _VOIDP]),
     "gc_step_plan_run_host": (C.c_int, [_VOIDP, _VOIDP, _VOIDP, _VOIDP]),
+    "gc_step_plan_enqueue_host": (C.c_int, [_VOIDP, _VOIDP, _VOIDP, _VOIDP]),
     "gc_step_plan_destroy": (None, [_VOIDP]),
     "gc_env_rollout": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP,
                                  C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_uint64, _VOIDP]),

@@ -1012,7 +1012,17 @@ int gc_step_plan_run(const gc_step_plan* p, const uint8_t* actions, void* stream
   return GC_OK;
 }
 
+static int plan_run_host(gc_step_plan* p, const uint8_t* actions_host, uint32_t* rd_bits_host, void* stream, bool wait);
+
 int gc_step_plan_run_host(gc_step_plan* p, const uint8_t* actions_host, uint32_t* rd_bits_host, void* stream) {
+  return plan_run_host(p, actions_host, rd_bits_host, stream, true);
+}
+
+int gc_step_plan_enqueue_host(gc_step_plan* p, const uint8_t* actions_host, uint32_t* rd_bits_host, void* stream) {
+  return plan_run_host(p, actions_host, rd_bits_host, stream, false);
+}
+
+static int plan_run_host(gc_step_plan* p, const uint8_t* actions_host, uint32_t* rd_bits_host, void* stream, bool wait) {
   if (!p || !actions_host || !rd_bits_host) return gc_fail(GC_E_ARG, "gc_step_plan_run_host: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t bits_bytes = (size_t)((p->n + 31) / 32) * 8;
@@ -1048,7 +1058,7 @@ int gc_step_plan_run_host(gc_step_plan* p, const uint8_t* actions_host, uint32_t
   e = p->launch_bits(A, st);
   if (e == cudaSuccess && !p->zc_dev)
     e = cudaMemcpyAsync(rd_bits_host, p->bits_dev, bits_bytes, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess && wait) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_step_plan_run_host: %s", cudaGetErrorString(e));
   return GC_OK;
 }

@@ -176,10 +176,12 @@ class KitchenBatch:
             _lib.check(rc)
         return self.reward_done
 
-    def step_host_bits(self, actions_host, bits_host):
+    def step_host_bits(self, actions_host, bits_host, stream=None):
         """gc_step_plan_run_host: actions from a (pinned) host tensor - bytes [N][num_agents] or joint indices
         [N] - results as the done / reward bit planes in `bits_host` (pinned int32[(N+31)//32][2]); returns
-        when the copies and the step are done.  None when the batch is outside the plans' envelope."""
+        when the copies and the step are done.  None when the batch is outside the plans' envelope.
+        With `stream` (a torch.cuda.Stream) the three operations are only enqueued on it
+        (gc_step_plan_enqueue_host): synchronise the stream before reading `bits_host`."""
         joint = self._check_actions(actions_host, False)
         if bits_host.is_cuda or not bits_host.is_contiguous() or bits_host.numel() * bits_host.element_size() < (self.num_envs + 31) // 32 * 8:
             raise ValueError("bits_host must be a contiguous host tensor of (N+31)//32 x 2 32-bit words")
@@ -187,8 +189,12 @@ class KitchenBatch:
         if plan is None:
             return None
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.gc_step_plan_run_host(plan, actions_host.data_ptr(), bits_host.data_ptr(),
-                                                      _lib.stream_ptr(self.device)))
+            if stream is not None:
+                _lib.check(self.lib.gc_step_plan_enqueue_host(plan, actions_host.data_ptr(), bits_host.data_ptr(),
+                                                              stream.cuda_stream))
+            else:
+                _lib.check(self.lib.gc_step_plan_run_host(plan, actions_host.data_ptr(), bits_host.data_ptr(),
+                                                          _lib.stream_ptr(self.device)))
         return bits_host
 
     def step_host(self, actions_host, actions_dev, reward_done_host=None, bits_dev=None, bits_host=None):

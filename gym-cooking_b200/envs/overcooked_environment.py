@@ -217,6 +217,7 @@ class OvercookedEnvironment(_ReferenceSurface):
         self._pinned_rd = None
         self._dev_actions = None
         self._streams = None
+        self._async_stream, self._async_pending = None, False
         self._pinned_bits = self._dev_bits = None
         # image_obs only when the reference would have a GameImage (env:240-246)
         self._atlas = None
@@ -330,6 +331,37 @@ class OvercookedEnvironment(_ReferenceSurface):
     PACKED_RESULTS = os.environ.get("GC_E2E_BYTE_RESULTS") is None
     PIPELINE_CHUNKS = 1
     PIPELINE_MIN_ENVS = 1 << 16
+
+    # -- vector-env style asynchronous step (gym.vector.VectorEnv.step_async / step_wait) ---------------
+    def step_async(self, actions):
+        """Enqueue one step of a batched env with HOST actions (pinned uint8[N][n_agents], or joint indices
+        uint8[N] / int16[N]) on this env's own stream and return at once; `step_wait()` delivers the result.
+        Two envs stepped alternately overlap one's PCIe copies with the other's kernel."""
+        kb = self._kb
+        if self.num_envs == 1 or actions.is_cuda:
+            raise ValueError("step_async is the batched, host-actions form; use step()")
+        if self._async_stream is None:
+            self._async_stream = torch.cuda.Stream(device=kb.device)
+            self._async_stream.wait_stream(torch.cuda.current_stream(kb.device))
+        if self._pinned_bits is None:
+            words = (self.num_envs + 31) // 32
+            self._pinned_bits = torch.zeros((words, 2), dtype=torch.int32).pin_memory()
+            self._dev_bits = torch.zeros((words, 2), dtype=torch.int32, device=kb.device)
+        if kb.step_host_bits(actions, self._pinned_bits, stream=self._async_stream) is None:
+            raise _lib.GcError("step_async needs a single-level batch without collision counters")
+        self.t += 1
+        self._async_pending = True
+
+    def step_wait(self):
+        """-> (obs, reward, done, info) of the step enqueued by step_async"""
+        if not self._async_pending:
+            raise RuntimeError("step_wait without step_async")
+        self._async_stream.synchronize()
+        self._async_pending = False
+        n = self.num_envs
+        obs = self._obs()
+        done, reward = BitFlag(self._pinned_bits, 0, n, True), BitFlag(self._pinned_bits, 1, n, False)
+        return obs, reward, done, {"t": self.t, "obs": obs, "image_obs": None, "done": done, "termination_info": ""}
 
     def _step_batched(self, acts):
         kb = self._kb

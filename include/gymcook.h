@@ -211,6 +211,11 @@ int gc_step_plan_create(const gc_level* level, uint32_t* state /*device*/, uint8
                         int64_t n, int n_agents, int flags, gc_step_plan** out);
 int gc_step_plan_run(const gc_step_plan* plan, const uint8_t* actions /*device*/, void* stream);
 int gc_step_plan_run_host(gc_step_plan* plan, const uint8_t* actions_host, uint32_t* rd_bits_host, void* stream);
+/* The same three stream operations without the final wait (the asynchronous half of a vector-env style
+ * step_async / step_wait pair): the caller synchronises `stream` before reading `rd_bits_host`, and must not
+ * touch `actions_host` until then.  Two batches on two streams overlap one batch's copies with the other's
+ * kernel (PCIe is full duplex). */
+int gc_step_plan_enqueue_host(gc_step_plan* plan, const uint8_t* actions_host, uint32_t* rd_bits_host, void* stream);
 void gc_step_plan_destroy(gc_step_plan* plan);
 
 /* rollout(): `n_steps` fused transitions with uniform-random actions generated in-kernel:

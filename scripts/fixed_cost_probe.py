@@ -36,15 +36,21 @@ def per_launch_us(n, ring=16, reps=20):  # 3 + 5 x 20 = 103 steps < horizon 127:
     return e0.elapsed_time(e1) * 1e3 / (4 * reps * ring)
 
 
-rows = []
-for k in (1, 2, 4, 5, 8, 32):
-    n = TILE * k
-    ring = 16 if k <= 8 else 4
-    us = per_launch_us(n, ring=ring)
-    rows.append((k, n, us))
-    print("tiles/CTA %2d  n=%8d  %.2f us per launch  (%.2f us per tile)" % (k, n, us, us / k))
-for n in (1 << 20,):
-    print("n=%8d (%.2f tiles/CTA)  %.2f us per launch" % (n, n / TILE, per_launch_us(n)))
-(k0, _, u0), (k1, _, u1) = rows[3], rows[-1]
-slope = (u1 - u0) / (k1 - k0)
-print("slope %.3f us per tile-iteration, intercept (fixed cost per launch) %.2f us" % (slope, u0 - slope * k0))
+def main():
+    rows = []
+    for k in (1, 2, 4, 5, 8, 32):
+        n = TILE * k
+        ring = 16 if k <= 8 else 4
+        us = per_launch_us(n, ring=ring)
+        rows.append((k, n, us))
+        print("tiles/CTA %2d  n=%8d  %.2f us per launch  (%.2f us per tile)" % (k, n, us, us / k))
+    for n in (1 << 20,):
+        print("n=%8d (%.2f tiles/CTA)  %.2f us per launch" % (n, n / TILE, per_launch_us(n)))
+    (k0, _, u0), (k1, _, u1) = rows[3], rows[-1]
+    slope = (u1 - u0) / (k1 - k0)
+    print("slope %.3f us per tile-iteration, intercept (fixed cost per launch) %.2f us" % (slope, u0 - slope * k0))
+
+
+
+if __name__ == "__main__":
+    main()

@@ -119,3 +119,30 @@ def test_reference_named_helpers():
     assert [str(s) for s in agent.get_subtasks(obs.world)] == [str(s) for s in env.all_subtasks]
     agent.setup_subtasks(env=obs)
     assert agent.delegator.add_subtasks() and str(agent) == "1"
+
+
+def test_step_async_wait_equals_step():
+    """Vector-env style step_async / step_wait on two alternating batches (own streams) returns what the
+    synchronous step returns, step by step."""
+    import argparse
+    n = 40000
+    ns = argparse.Namespace(level="partial-divider_tl", num_agents=2, max_num_timesteps=12, max_num_subtasks=14, seed=1,
+                            model1=None, model2=None, model3=None, model4=None)
+    envs = [gcb.OvercookedEnvironment(ns, num_envs=n, track_collisions=False) for _ in range(3)]
+    for e in envs:
+        e.reset()
+    a, b, ref = envs
+    acts = ref._kb.random_actions(14, seed=4)
+    joint = [(acts[s][:, 0] * 5 + acts[s][:, 1]).to(torch.uint8).cpu().pin_memory() for s in range(14)]
+    for s in range(14):
+        a.step_async(joint[s])
+        b.step_async(joint[s])
+        _, r_ref, d_ref, _ = ref.step(joint[s])
+        _, r_a, d_a, info = a.step_wait()
+        _, r_b, d_b, _ = b.step_wait()
+        assert torch.equal(a.state, ref.state) and torch.equal(b.state, ref.state), s
+        for got in ((r_a, d_a), (r_b, d_b)):
+            assert torch.equal(got[0].tensor().bool(), r_ref.tensor().bool()), s
+            assert torch.equal(got[1].tensor().bool(), d_ref.tensor().bool()), s
+        assert info["t"] == s + 1
+    assert bool(d_ref.tensor().all())
