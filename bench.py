@@ -281,7 +281,8 @@ def run_ours(args):
     env = gcb.OvercookedEnvironment(ns, num_envs=N_ENVS, device=dev, track_collisions=False)
     byte_actions = [actions[0][s].cpu().pin_memory() for s in range(8)]
     joint_actions = [(actions[0][s][:, 0] * 5 + actions[0][s][:, 1]).to(torch.uint8).cpu().pin_memory() for s in range(8)]
-    e2e_steps = max(1, min(args.steps, 400))
+    # at least 400 timed steps whatever --steps is (28 ms): a 20-step e2e leg would sit inside that ramp
+    e2e_steps = min(max(args.steps, 400), 2000)
     # warm-up: one untimed block of the same length.  The first few hundred host-driven steps run up to
     # 30-45 % slower than the steady state (PCIe link / copy-engine / host ramp; scripts/e2e_numa_probe.py:
     # blocks of 400 steps measure 1.3-1.8e10, then 2.4e10 for every later block), so 3 steps are not enough
