@@ -707,7 +707,13 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
       // widen: the forward pass resumes where it stopped; cost-to-go values are rebuilt from the goals
       slack += kSlackStep;
       limit = min(kMaxCost, result + slack);
-      for (uint32_t k = threadIdx.x; k < kSlots2; k += kTreeThreads) A->val[k] = kInfCost;
+      // only the slots this search inserted can hold a value (a 512 KB sweep of the whole table per widening
+      // round was a good part of the kernel's 27 GB of DRAM traffic per 2^12-env launch)
+      if (n_states <= kTouchedCap) {
+        for (uint32_t i = threadIdx.x; i < n_states; i += kTreeThreads) A->val[A->touched[i]] = kInfCost;
+      } else {
+        for (uint32_t k = threadIdx.x; k < kSlots2; k += kTreeThreads) A->val[k] = kInfCost;
+      }
       __syncthreads();
       for (uint32_t i = threadIdx.x; i < min(n_goals, kGoalCap); i += kTreeThreads) A->val[A->goals[i]] = 0u;
       __syncthreads();

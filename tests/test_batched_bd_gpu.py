@@ -98,3 +98,26 @@ def test_likelihood_row_kernel_equals_the_torch_restatement(level, models):
             assert bool((nv >= 1).all()) and bool((ai < nv).all())
             compared += int(nv.numel())
     assert compared > 100000
+
+
+@pytest.mark.parametrize("level,optimum,min_success", [("open-divider_tomato", 15, 0.99), ("partial-divider_tomato", 17, 0.9),
+                                                       ("open-divider_salad", 24, 0.5)])
+def test_episode_lengths_against_the_reference_yardsticks(level, optimum, min_success):
+    """Distributional sanity of whole bd/bd episodes: no delivered episode is shorter than the
+    optimal length the reference's plots use as yardstick (misc/metrics/make_graphs.py:48-52: open tomato 15,
+    partial tomato 17, open salad 24 steps for two agents), the mean stays within 2x of it, and the reference's
+    own open-divider_tomato bd/bd run (seed 1: delivered at t = 23, profiles/r02_python_reference_cpu.json) lies
+    inside the batch's distribution."""
+    n = 4096
+    loop = batched_agents.BatchedDelegation(level, n, ("bd", "bd"), seed=11)
+    loop.run()
+    t = ((loop.kb.state[:, 0].to(torch.int64) >> 24) & 127)
+    ok = loop.kb.reward.bool()
+    assert float(ok.float().mean()) >= min_success
+    lengths = t[ok]
+    assert int(lengths.min()) >= optimum, (int(lengths.min()), optimum)
+    assert float(lengths.float().mean()) <= 2.0 * optimum
+    if level == "open-divider_tomato":
+        assert int(lengths.min()) <= 23 <= int(lengths.max())
+    print("%s: %.1f %% delivered, steps min %d mean %.1f max %d (reference yardstick %d)" % (
+        level, 100 * float(ok.float().mean()), int(lengths.min()), float(lengths.float().mean()), int(lengths.max()), optimum))
