@@ -870,6 +870,9 @@ struct gc_step_plan {
   size_t action_bytes;
   const void* zc_host;   // last rd_bits_host seen and its device alias (pinned, mapped memory), or null
   uint32_t* zc_dev;
+  cudaStream_t side[4];  // chunked gc_step_plan_run_host: one stream per chunk (created on first use)
+  cudaEvent_t ev_start, ev_done[4];
+  int n_side;
 };
 
 namespace {
@@ -1032,8 +1035,6 @@ static int plan_run_host(gc_step_plan* p, const uint8_t* actions_host, uint32_t*
     if (e == cudaSuccess) e = cudaMalloc(&p->bits_dev, bits_bytes);
     if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_step_plan_run_host: staging: %s", cudaGetErrorString(e));
   }
-  e = cudaMemcpyAsync(p->actions_dev, actions_host, p->action_bytes, cudaMemcpyHostToDevice, st);
-  if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_step_plan_run_host: copy in failed: %s", cudaGetErrorString(e));
   // Results: when `rd_bits_host` is pinned, mapped host memory (any cudaHostAlloc / torch pin_memory buffer
   // under unified addressing) the kernel stores the bit planes straight into it - posted writes over PCIe,
   // visible to the host once the stream has drained - and the device-to-host copy with its ~10 us of
@@ -1053,6 +1054,53 @@ static int plan_run_host(gc_step_plan* p, const uint8_t* actions_host, uint32_t*
   Step2Args A = p->args;
   A.tables = tables_for(&p->level, 1, p->n_agents);
   if (!A.tables) return GC_E_CUDA;
+  // Synchronous call on a large batch: the batch goes in `chunks` pieces, each on its own stream (copy in, step,
+  // copy out), so that piece k+1's host-to-device copy overlaps piece k's kernel and device-to-host copy - the
+  // two copy directions have their own engines.  (The first copy of this call, issued above for the whole batch
+  // in the single-chunk form, is issued per piece here.)  GC_E2E_CHUNKS=1..4, default 2 from 2^18 envs.
+  static const int want_chunks = [] {
+    const char* c = getenv("GC_E2E_CHUNKS");
+    const int v = c ? atoi(c) : 2;
+    return v >= 1 && v <= 4 ? v : 2;
+  }();
+  const int chunks = (wait && !p->zc_dev && p->n >= ((int64_t)1 << 18)) ? want_chunks : 1;
+  if (chunks > 1) {
+    if (p->n_side < chunks) {
+      if (!p->ev_start && cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming) != cudaSuccess)
+        return gc_fail(GC_E_CUDA, "gc_step_plan_run_host: event");
+      for (int c = p->n_side; c < chunks; c++) {
+        if (cudaStreamCreateWithFlags(&p->side[c], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ev_done[c], cudaEventDisableTiming) != cudaSuccess)
+          return gc_fail(GC_E_CUDA, "gc_step_plan_run_host: side stream");
+        p->n_side = c + 1;
+      }
+    }
+    const size_t ab = p->action_bytes / (size_t)p->n;  // action bytes per env
+    e = cudaEventRecord(p->ev_start, st);
+    for (int c = 0; c < chunks && e == cudaSuccess; c++) {
+      const int64_t lo = (p->n * c / chunks) & ~(int64_t)1023, hi = c + 1 == chunks ? p->n : ((p->n * (c + 1) / chunks) & ~(int64_t)1023);
+      cudaStream_t s = p->side[c];
+      e = cudaStreamWaitEvent(s, p->ev_start, 0);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(p->actions_dev + lo * ab, actions_host + lo * ab, (size_t)(hi - lo) * ab, cudaMemcpyHostToDevice, s);
+      Step2Args B = A;
+      B.state = A.state + lo;
+      B.actions = p->actions_dev + lo * ab;
+      B.reward_done = A.reward_done + lo;
+      B.rd_bits = p->bits_dev + lo / 16;
+      B.n = (uint32_t)(hi - lo);
+      if (e == cudaSuccess) e = p->launch_bits(B, s);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(rd_bits_host + lo / 16, p->bits_dev + lo / 16, (size_t)((hi - lo + 31) / 32) * 8, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaEventRecord(p->ev_done[c], s);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(st, p->ev_done[c], 0);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_step_plan_run_host: %s", cudaGetErrorString(e));
+    return GC_OK;
+  }
+  e = cudaMemcpyAsync(p->actions_dev, actions_host, p->action_bytes, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return gc_fail(GC_E_CUDA, "gc_step_plan_run_host: copy in failed: %s", cudaGetErrorString(e));
   A.actions = p->actions_dev;
   A.rd_bits = p->zc_dev ? p->zc_dev : p->bits_dev;
   e = p->launch_bits(A, st);
@@ -1067,6 +1115,11 @@ void gc_step_plan_destroy(gc_step_plan* p) {
   if (!p) return;
   if (p->actions_dev) cudaFree(p->actions_dev);
   if (p->bits_dev) cudaFree(p->bits_dev);
+  for (int c = 0; c < p->n_side; c++) {
+    cudaStreamDestroy(p->side[c]);
+    cudaEventDestroy(p->ev_done[c]);
+  }
+  if (p->ev_start) cudaEventDestroy(p->ev_start);
   delete p;
 }
 

@@ -343,13 +343,15 @@ def test_step_host_bit_planes(n, kind):
     assert seen_done > 0
 
 
-@pytest.mark.parametrize("level,n_agents,n", [("partial-divider_tl", 2, 70001), ("full-divider_salad", 3, 4099),
+@pytest.mark.parametrize("level,n_agents,n", [("partial-divider_tl", 2, 70001), ("partial-divider_tl", 2, (1 << 18) + 777),
+                                              ("full-divider_salad", 3, 4099),
                                               ("open-divider_salad", 4, 33333), ("onion-8x8", 1, 1000)])
 def test_prepared_plans_and_joint_actions(level, n_agents, n):
     """The prepared-step path (gc_step_plan_run / _run_host) and the joint-index action format
     (j = sum_i a_i * 5^(NA-1-i); uint8, int16 for 4 agents) against gc_env_step on action bytes - which the
     tests above hold against the oracle: same states, reward/done bytes and bit planes at every step; an
-    out-of-range joint index means "everybody stays"."""
+    out-of-range joint index means "everybody stays".  From 2^18 envs the synchronous host call goes in two
+    pipelined chunks on side streams (second parameter set)."""
     text, src = level_source(level)
     max_t = 14
     a = gcb.KitchenBatch(src, n_agents, n, max_t)                           # plan, bytes
