@@ -121,6 +121,11 @@ class _ObserverTables:
         fallback = np.zeros(H, dtype=bool)
         sel_sub = np.full(H, S, dtype=np.int64)
         sel_joint = np.zeros(H, dtype=bool)
+        sel_first = np.ones(H, dtype=bool)             # the observer is the first agent of its (sorted) pair
+        plan_pid = np.zeros(H, dtype=np.int64)          # planner pair RealAgent.plan asks for (agent.py:244-263)
+        # planning level of `plan` (e2e:360-406): greedy passes no other planners (level 0); otherwise level 1
+        # as soon as somebody is outside the subtask's agent set
+        plan_level = lambda ag: 0 if model == "greedy" else (1 if len(ag) < owner.NA else 0)
         rows, row_index = [], {}
         keys = []
         for h, alloc in enumerate(allocs):
@@ -137,6 +142,9 @@ class _ObserverTables:
                     static_ok[h] = False  # nobody does None together (bd:243-246)
                 if me in ag:
                     sel_sub[h], sel_joint[h] = s, len(ag) > 1
+                    sel_first[h] = ag[0] == me
+                    if s < S:
+                        plan_pid[h] = owner.pid[(s, ag, plan_level(ag))]
                 if model == "greedy" and me not in ag:
                     continue
                 if s == S and len(ag) > 1:
@@ -166,23 +174,19 @@ class _ObserverTables:
         self.hyp_pair = t(hyp_pair)
         self.static_ok, self.fallback, self.rank = t(static_ok), t(fallback), t(rank)
         self.sel_sub, self.sel_joint = t(sel_sub), t(sel_joint)
-        # likelihood rows (bd:461-689): None rows, single-agent rows (level 1 when somebody else is
-        # around, :650-654), joint rows (level 0)
-        kind = np.array([0 if s == S else (1 if len(ag) == 1 else 2) for s, ag in rows], dtype=np.int64)
+        self.sel_first, self.plan_pid = t(sel_first), t(plan_pid)
+        # likelihood rows (bd:461-689): None rows (kind 0), single-agent rows (1), joint rows with the observer in
+        # the pair (2: partner filter, five entries) or outside it (3: all 25 joint actions); the planning world
+        # is level 1 as soon as somebody is outside the row's agent set (:650-654), else level 0
+        kind = np.array([0 if s == S else (1 if len(ag) == 1 else (2 if me in ag else 3)) for s, ag in rows], dtype=np.int64)
         agent = np.array([ag[0] for s, ag in rows], dtype=np.int64)
-        lvl1 = 1 if owner.NA > 1 else 0
-        pid = np.array([0 if s == S else owner.pid[(s, ag, lvl1 if len(ag) == 1 else 0)] for s, ag in rows],
+        pid = np.array([0 if s == S else owner.pid[(s, ag, 1 if len(ag) < owner.NA else 0)] for s, ag in rows],
                        dtype=np.int64)
         w = np.array([1 if model == "greedy" else len(ag) for s, ag in rows], dtype=np.uint8)
         self.row_kind, self.row_agent, self.row_pid, self.pair_w = t(kind), t(agent), t(pid), t(w)
         self.row_kind_host, self.row_agent_host, self.row_pid_host = kind, agent, pid
         self.row_agent2_host = np.array([ag[1] if len(ag) > 1 else ag[0] for s, ag in rows], dtype=np.int64)
-        plan_lvl = 0 if model == "greedy" else lvl1  # RealAgent.plan :252-257
-        self.plan_single = t(np.array([owner.pid[(s, (me,), plan_lvl)] for s in range(S)], dtype=np.int64))
-        if owner.NA > 1:
-            self.plan_joint = t(np.array([owner.pid[(s, (0, 1), 0)] for s in range(S)], dtype=np.int64))
-        else:
-            self.plan_joint = self.plan_single
+        self.A = 25 if bool((kind == 3).any()) else 5
 
 
 class BatchedDelegation:
@@ -191,8 +195,8 @@ class BatchedDelegation:
     def __init__(self, level, num_envs, models=("bd", "bd"), max_num_timesteps=100, beta=1.3, none_action_prob=0.5,
                  seed=1, deterministic=False, device=None):
         self.NA = len(models)
-        if self.NA not in (1, 2):
-            raise NotImplementedError("the batched delegation loop covers 1 or 2 agents")
+        if not 1 <= self.NA <= 4:
+            raise ValueError("1 to 4 agents")
         for m in models:
             if m not in ("bd", "up", "fb", "dc", "greedy"):
                 raise ValueError("unknown model type %r" % (m,))
@@ -206,18 +210,28 @@ class BatchedDelegation:
         self.S = S = len(self.subtasks)
         lv = self.kb.levels[0]
         self.perimeter = float(2 * (lv.width + lv.height))  # world.perimeter, env:198
-        agsets = [(i,) for i in range(self.NA)] + ([(0, 1)] if self.NA == 2 else [])
+        import itertools
+        agsets = [(i,) for i in range(self.NA)] + list(itertools.combinations(range(self.NA), 2))
         self.lpairs, self.lid, self.cpairs, self.pid = [], {}, [], {}
         for s in range(S):
             for ag in agsets:
                 self.lid[(s, ag)] = len(self.lpairs)
                 self.lpairs.append((s, ag[0], ag[1] if len(ag) > 1 else None))
-                for lvl in ((0, 1) if len(ag) == 1 and self.NA > 1 else (0,)):
+                # level 0 (priors, greedy planning; everybody inside the set) and, when somebody is outside the
+                # agent set, level 1 (likelihoods and non-greedy planning)
+                for lvl in ((0, 1) if len(ag) < self.NA else (0,)):
                     self.pid[(s, ag, lvl)] = len(self.cpairs)
                     self.cpairs.append((s, ag[0], ag[1] if len(ag) > 1 else None, bool(lvl)))
         self.lpair_sub = torch.tensor([p[0] for p in self.lpairs], dtype=torch.int64, device=self.device)
         self.cache = PlanCache(self.kb, self.cpairs)
         self.tables = [_ObserverTables(self, i, models[i]) for i in range(self.NA)]
+        # the hypothesis space is tabulated over the level's full subtask list (H rows per observer) and every env
+        # keeps a dense probability row: fine for two agents (H <= 100) and for three (H <= 2 457), out of
+        # reach for four bd agents at scale (H = 39 906)
+        dense = sum(T.H for T in self.tables) * num_envs * 9
+        if dense > (24 << 30):
+            raise MemoryError("%d envs x %s hypotheses need %.0f GB of dense tables: use fewer envs (the pruned "
+                              "per-env representation is not built yet)" % (num_envs, [T.H for T in self.tables], dense / 2 ** 30))
         masks = [recipe_planner.subtask_masks(s) for s in self.subtasks]
         dev = self.device
         self.goal_mask = torch.tensor([m[3] for m in masks], dtype=torch.int64, device=dev)
@@ -430,14 +444,13 @@ class BatchedDelegation:
         new_sub = torch.where(nothing, S, T.sel_sub[best])
         new_joint = T.sel_joint[best] & ~nothing
         # plan :218-281
-        subc = new_sub.clamp(max=S - 1)
-        pid = torch.where(new_joint, T.plan_joint[subc], T.plan_single[subc])
+        pid = T.plan_pid[best]
         q = self.cache.q[ci, pid]  # [N][25]
         q = torch.where(new_joint[:, None] | (torch.arange(25, device=dev)[None, :] < 5), q, float("nan"))
         valid = ~torch.isnan(q)
         qv = torch.where(valid, q.clamp(max=1e30), float("inf"))
         a = self._pick(valid & (qv == qv.min(1, keepdim=True).values))  # argmin, random ties (e2e:27-30)
-        own = torch.where(new_joint, (a // 5) if i == 0 else (a % 5), a)
+        own = torch.where(new_joint, torch.where(T.sel_first[best], a // 5, a % 5), a)  # agent.py:270-272
         own = torch.where(valid.any(1), own, 4)
         # doing nothing: stay with none_action_prob, else a uniformly random offered move (:235-243)
         off = offered[:, i]

@@ -489,7 +489,7 @@ struct RowTable {
   uint8_t kind[128], agent[128], agent2[128];
 };
 
-template <typename T>
+template <typename T, int A>
 __global__ void __launch_bounds__(kThreads)
 bd_rows_kernel(const float* __restrict__ q_table, const int64_t* __restrict__ q_row, int n_pairs,
                const __grid_constant__ RowTable rows, const uint8_t* __restrict__ executed,
@@ -500,14 +500,32 @@ bd_rows_kernel(const float* __restrict__ q_table, const int64_t* __restrict__ q_
   const int64_t env = idx / P;
   const int p = (int)(idx - env * P);
   const int kind = rows.kind[p], ag = rows.agent[p];
-  T out[5] = {T(0), T(0), T(0), T(0), T(0)};
+  T* out = qdiff + idx * A;
   int nv = 0, taken_rank = 0;
   if (kind == 0) {  // doing nothing (bd:618-641)
     const int k = min((int)n_moves[env], 4);
     nv = k + 1;
     out[0] = none_p;
     for (int a = 1; a <= k; a++) out[a] = (T(1) - none_p) / T(k);
+    for (int a = k + 1; a < A; a++) out[a] = T(0);
     taken_rank = executed[env * n_agents + ag] == 4 ? 0 : min(1, nv - 1);
+  } else if (kind == 3) {
+    // a joint row the observer is not part of (three or more agents): every offered joint action is valid
+    // (no partner filter, bd:677 is false), taken = 5 * a_i + a_j
+    if constexpr (A >= 25) {
+      const float* base = q_table + (q_row[env] * n_pairs + rows.pair[p]) * 25;
+      const int taken = 5 * min((int)executed[env * n_agents + ag], 4) + min((int)executed[env * n_agents + rows.agent2[p]], 4);
+      const float qt = base[taken];
+      const T old = (isnan(qt) || isinf(qt)) ? q_cap : min((T)qt, q_cap);
+      for (int a = 0; a < 25; a++) {
+        const float q = base[a];
+        if (!isnan(q) || a == taken) {
+          if (a == taken) taken_rank = nv;
+          out[nv++] = old - ((isnan(q) || isinf(q)) ? q_cap : min((T)q, q_cap));
+        }
+      }
+      for (int a = nv; a < A; a++) out[a] = T(0);
+    }
   } else {
     const float* base = q_table + (q_row[env] * n_pairs + rows.pair[p]) * 25;
     int taken = executed[env * n_agents + ag];
@@ -516,14 +534,14 @@ bd_rows_kernel(const float* __restrict__ q_table, const int64_t* __restrict__ q_
       const int ag2 = rows.agent2[p];
       if (observer == ag) {
         stride = 5;
-        offset = executed[env * n_agents + ag2];
+        offset = min((int)executed[env * n_agents + ag2], 4);
       } else {
-        offset = 5 * taken;
+        offset = 5 * min(taken, 4);
         taken = executed[env * n_agents + ag2];
       }
     }
     taken = min(taken, 4);
-    T qc[5];
+    T qc[5], res[5] = {T(0), T(0), T(0), T(0), T(0)};
     bool valid[5];
 #pragma unroll
     for (int a = 0; a < 5; a++) {
@@ -540,13 +558,14 @@ bd_rows_kernel(const float* __restrict__ q_table, const int64_t* __restrict__ q_
         if (a == taken) taken_rank = nv;
 #pragma unroll
         for (int o = 0; o < 5; o++)
-          if (o == nv) out[o] = old - qc[a];
+          if (o == nv) res[o] = old - qc[a];
         nv++;
       }
     }
-  }
 #pragma unroll
-  for (int a = 0; a < 5; a++) qdiff[idx * 5 + a] = out[a];
+    for (int a = 0; a < 5; a++) out[a] = res[a];
+    for (int a = 5; a < A; a++) out[a] = T(0);
+  }
   n_valid[idx] = (uint8_t)nv;
   act_idx[idx] = (uint8_t)taken_rank;
 }
@@ -555,7 +574,7 @@ template <typename T>
 int launch_rows(const float* q_table, const int64_t* q_row, int n_pairs, const int32_t* row_pair,
                 const uint8_t* row_kind, const uint8_t* row_agent, const uint8_t* row_agent2, const uint8_t* executed,
                 const uint8_t* n_moves, int observer, T none_p, T q_cap, T* qdiff, uint8_t* n_valid, uint8_t* act_idx,
-                int64_t n, int P, int n_agents, void* stream) {
+                int64_t n, int P, int n_agents, int A, void* stream) {
   if (!q_table || !q_row || !row_pair || !row_kind || !row_agent || !row_agent2 || !executed || !n_moves || !qdiff ||
       !n_valid || !act_idx)
     return gc_fail(GC_E_ARG, "gc_bd_likelihood_rows: null array");
@@ -563,15 +582,18 @@ int launch_rows(const float* q_table, const int64_t* q_row, int n_pairs, const i
       observer >= n_agents)
     return gc_fail(GC_E_ARG, "gc_bd_likelihood_rows: bad sizes (n=%lld P=%d pairs=%d agents=%d observer=%d)",
                    (long long)n, P, n_pairs, n_agents, observer);
+  if (A != 5 && A != 25) return gc_fail(GC_E_ARG, "gc_bd_likelihood_rows: A must be 5 or 25");
   RowTable rt;
   memset(&rt, 0, sizeof(rt));
   for (int p = 0; p < P; p++) {
     const int kind = row_kind[p];
-    if (kind > 2 || row_agent[p] >= n_agents || (kind == 2 && row_agent2[p] >= n_agents) ||
+    if (kind > 3 || row_agent[p] >= n_agents || (kind >= 2 && row_agent2[p] >= n_agents) ||
         (kind != 0 && (row_pair[p] < 0 || row_pair[p] >= n_pairs)))
       return gc_fail(GC_E_ARG, "gc_bd_likelihood_rows: row %d is malformed", p);
     if (kind == 2 && observer != row_agent[p] && observer != row_agent2[p])
-      return gc_fail(GC_E_LIMIT, "gc_bd_likelihood_rows: joint row %d does not contain the observer", p);
+      return gc_fail(GC_E_ARG, "gc_bd_likelihood_rows: joint row %d does not contain the observer (that is kind 3)", p);
+    if (kind == 3 && (A != 25 || observer == row_agent[p] || observer == row_agent2[p]))
+      return gc_fail(GC_E_ARG, "gc_bd_likelihood_rows: row %d: kind 3 is a joint row WITHOUT the observer and needs A = 25", p);
     rt.pair[p] = row_pair[p];
     rt.kind[p] = (uint8_t)kind;
     rt.agent[p] = row_agent[p];
@@ -580,8 +602,13 @@ int launch_rows(const float* q_table, const int64_t* q_row, int n_pairs, const i
   if (n == 0) return GC_OK;
   if (int rc = gc_require_device()) return rc;
   const int64_t total = n * P;
-  bd_rows_kernel<T><<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      q_table, q_row, n_pairs, rt, executed, n_moves, observer, none_p, q_cap, qdiff, n_valid, act_idx, n, P, n_agents);
+  const unsigned grid = (unsigned)((total + kThreads - 1) / kThreads);
+  if (A == 25)
+    bd_rows_kernel<T, 25><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        q_table, q_row, n_pairs, rt, executed, n_moves, observer, none_p, q_cap, qdiff, n_valid, act_idx, n, P, n_agents);
+  else
+    bd_rows_kernel<T, 5><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        q_table, q_row, n_pairs, rt, executed, n_moves, observer, none_p, q_cap, qdiff, n_valid, act_idx, n, P, n_agents);
   return gc_check_launch("gc_bd_likelihood_rows");
 }
 
@@ -605,18 +632,18 @@ int gc_bd_likelihood_rows_f32(const float* q_table, const int64_t* q_row, int n_
                               const uint8_t* row_kind, const uint8_t* row_agent, const uint8_t* row_agent2,
                               const uint8_t* executed, const uint8_t* n_moves, int observer, float none_action_prob,
                               float q_cap, float* qdiff, uint8_t* n_valid, uint8_t* act_idx, int64_t n, int P,
-                              int n_agents, void* stream) {
+                              int n_agents, int A, void* stream) {
   return launch_rows<float>(q_table, q_row, n_pairs, row_pair, row_kind, row_agent, row_agent2, executed, n_moves,
-                            observer, none_action_prob, q_cap, qdiff, n_valid, act_idx, n, P, n_agents, stream);
+                         observer, none_action_prob, q_cap, qdiff, n_valid, act_idx, n, P, n_agents, A, stream);
 }
 
 int gc_bd_likelihood_rows_f64(const float* q_table, const int64_t* q_row, int n_pairs, const int32_t* row_pair,
                               const uint8_t* row_kind, const uint8_t* row_agent, const uint8_t* row_agent2,
                               const uint8_t* executed, const uint8_t* n_moves, int observer, double none_action_prob,
                               double q_cap, double* qdiff, uint8_t* n_valid, uint8_t* act_idx, int64_t n, int P,
-                              int n_agents, void* stream) {
+                              int n_agents, int A, void* stream) {
   return launch_rows<double>(q_table, q_row, n_pairs, row_pair, row_kind, row_agent, row_agent2, executed, n_moves,
-                             observer, none_action_prob, q_cap, qdiff, n_valid, act_idx, n, P, n_agents, stream);
+                         observer, none_action_prob, q_cap, qdiff, n_valid, act_idx, n, P, n_agents, A, stream);
 }
 
 }  // extern "C"

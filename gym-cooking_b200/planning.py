@@ -32,7 +32,8 @@ def bd_posterior(probs, alive, hyp_pair, pair_w, qdiff, n_valid, act_idx, beta):
 def bd_likelihood_rows(q_table, q_row, row_pair, row_kind, row_agent, row_agent2, executed, n_moves, observer,
                        none_action_prob, q_cap=100.0, dtype=torch.float64):
     """prob_nav_actions' softmax inputs (bd:461-689) for every (env, likelihood row): returns
-    (qdiff [n][P][5], n_valid [n][P], act_idx [n][P]) ready for bd_posterior - see gymcook.h."""
+    (qdiff [n][P][A], n_valid [n][P], act_idx [n][P]) ready for bd_posterior - see gymcook.h.  A = 5, or 25
+    when the table holds joint rows the observer is not part of (kind 3: three or more agents)."""
     lib = _lib.load()
     n, P = q_row.shape[0], len(row_pair)
     dev = q_table.device
@@ -40,14 +41,15 @@ def bd_likelihood_rows(q_table, q_row, row_pair, row_kind, row_agent, row_agent2
     rk, ra, ra2 = (np.ascontiguousarray(np.asarray(a, dtype=np.uint8)) for a in (row_kind, row_agent, row_agent2))
     fn = {torch.float32: lib.gc_bd_likelihood_rows_f32, torch.float64: lib.gc_bd_likelihood_rows_f64}[dtype]
     with torch.cuda.device(dev):
-        qdiff = torch.empty((n, P, 5), dtype=dtype, device=dev)
+        A = 25 if bool((rk == 3).any()) else 5
+        qdiff = torch.empty((n, P, A), dtype=dtype, device=dev)
         n_valid = torch.empty((n, P), dtype=torch.uint8, device=dev)
         act_idx = torch.empty((n, P), dtype=torch.uint8, device=dev)
         _lib.check(fn(_lib.ptr(q_table, torch.float32), _lib.ptr(q_row, torch.int64), q_table.shape[1],
                       rp.ctypes.data_as(C.c_void_p), rk.ctypes.data_as(C.c_void_p), ra.ctypes.data_as(C.c_void_p),
                       ra2.ctypes.data_as(C.c_void_p), _lib.ptr(executed, torch.uint8), _lib.ptr(n_moves, torch.uint8),
                       int(observer), float(none_action_prob), float(q_cap), _lib.ptr(qdiff), _lib.ptr(n_valid),
-                      _lib.ptr(act_idx), n, P, executed.shape[1], _lib.stream_ptr(dev)))
+                      _lib.ptr(act_idx), n, P, executed.shape[1], A, _lib.stream_ptr(dev)))
     return qdiff, n_valid, act_idx
 
 

@@ -280,6 +280,8 @@ int gc_bd_posterior_f64(double* probs, const uint8_t* alive, const uint8_t* hyp_
  *   single row (kind 1)              Q of row_agent's five actions
  *   joint row  (kind 2, bd:677-679)  the observer is row_agent or row_agent2: only joint actions
  *                                    that match the partner's executed move (five entries)
+ *   joint row  (kind 3)              the observer is neither (three or more agents): all 25 joint actions
+ *                                    a = 5 * a_i + a_j, no partner filter; needs A = 25
  * Valid = offered (Q not NaN) or taken; Q is capped at q_cap (+inf = goal out of reach); the valid
  * entries are compacted to the front in action order as  Q(taken) - Q(a).
  *   q_table  device float[..][n_pairs][25]  gc_subtask_q / gc_joint_q rows (any number of states)
@@ -287,17 +289,18 @@ int gc_bd_posterior_f64(double* probs, const uint8_t* alive, const uint8_t* hyp_
  *   row_pair/row_kind/row_agent/row_agent2  HOST arrays [P] (pair index into n_pairs; agents 0-based)
  *   executed device uint8[n][n_agents]      env.agent_actions of the step that left obs_tm1
  *   n_moves  device uint8[n]
- * Outputs: qdiff [n][P][5], n_valid [n][P], act_idx [n][P] as gc_bd_posterior_* reads them. */
+ * Outputs: qdiff [n][P][A] (A = 5, or 25 when the table has kind-3 rows), n_valid [n][P], act_idx [n][P] as
+ * gc_bd_posterior_* reads them. */
 int gc_bd_likelihood_rows_f32(const float* q_table, const int64_t* q_row, int n_pairs, const int32_t* row_pair,
                               const uint8_t* row_kind, const uint8_t* row_agent, const uint8_t* row_agent2,
                               const uint8_t* executed, const uint8_t* n_moves, int observer, float none_action_prob,
                               float q_cap, float* qdiff, uint8_t* n_valid, uint8_t* act_idx, int64_t n, int P,
-                              int n_agents, void* stream);
+                              int n_agents, int A, void* stream);
 int gc_bd_likelihood_rows_f64(const float* q_table, const int64_t* q_row, int n_pairs, const int32_t* row_pair,
                               const uint8_t* row_kind, const uint8_t* row_agent, const uint8_t* row_agent2,
                               const uint8_t* executed, const uint8_t* n_moves, int observer, double none_action_prob,
                               double q_cap, double* qdiff, uint8_t* n_valid, uint8_t* act_idx, int64_t n, int P,
-                              int n_agents, void* stream);
+                              int n_agents, int A, void* stream);
 
 /* ---- (B) navigation planner ------------------------------------------------------------
  * Distance lower bound of env.get_lower_bound_for_subtask_given_objs (env:594-664) =

@@ -44,7 +44,13 @@ def deterministic_facade(monkeypatch):
                                           ("partial-divider_tomato", ("bd", "up")),
                                           ("open-divider_tl", ("bd", "bd")),
                                           ("partial-divider_tl", ("greedy", "bd")),
-                                          ("open-divider_tomato", ("dc", "fb"))])
+                                          ("open-divider_tomato", ("dc", "fb")),
+                                          # three and four agents: joint rows the observer is not part of (25-entry
+                                          # likelihood rows), level-1 joint planning, every pair of agents
+                                          ("open-divider_tomato", ("bd", "bd", "bd")),
+                                          ("partial-divider_tomato", ("bd", "up", "dc")),
+                                          ("open-divider_tl", ("greedy", "bd", "fb")),
+                                          ("open-divider_tomato", ("bd", "up", "dc", "greedy"))])
 def test_batched_loop_equals_facade_loop(level, models, deterministic_facade):
     loop = batched_agents.BatchedDelegation(level, 8, models, deterministic=True)
     deterministic_facade["list"] = loop.subtasks
