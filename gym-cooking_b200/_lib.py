@@ -72,6 +72,12 @@ _SIGNATURES = {
     "gc_bd_likelihood_rows_f64": (C.c_int, [_VOIDP, _VOIDP, C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, C.c_int,
                                             C.c_double, C.c_double, _VOIDP, _VOIDP, _VOIDP, C.c_int64, C.c_int, C.c_int,
                                             C.c_int, _VOIDP]),
+    "gc_bd_update_lists_f32": (C.c_int, [_VOIDP, _VOIDP, _VOIDP, C.c_int, _VOIDP, C.c_int, C.c_int, _VOIDP, _VOIDP, _VOIDP,
+                                         C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, C.c_int, C.c_float,
+                                         C.c_float, C.c_float, C.c_int64, C.c_int, C.c_int, _VOIDP]),
+    "gc_bd_update_lists_f64": (C.c_int, [_VOIDP, _VOIDP, _VOIDP, C.c_int, _VOIDP, C.c_int, C.c_int, _VOIDP, _VOIDP, _VOIDP,
+                                         C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, C.c_int, C.c_double,
+                                         C.c_double, C.c_double, C.c_int64, C.c_int, C.c_int, _VOIDP]),
     "gc_lower_bound": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, C.c_int, _VOIDP,
                                  C.c_int64, C.c_int, _VOIDP]),
     "gc_subtask_q": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, C.c_int, _VOIDP, _VOIDP,

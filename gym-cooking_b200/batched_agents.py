@@ -21,6 +21,8 @@ of operations is RealAgent.select_action :82-104: update_subtasks (reset / set_p
 cache, gc_bd_posterior_f64, gc_env_step); the masks, gathers and arg-max/min around them are torch
 tensor ops on the same device - nothing leaves HBM during an episode.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -28,6 +30,8 @@ from . import engine, planning, recipe_planner
 from .delegation_planner import UNREACHABLE_Q, SubtaskAllocation, hypothesis_space
 
 _T_MASK = ~0xFF000000  # clears t and done of w[0] inside the low int64 of a packed state
+DENSE_MAX_H = 128       # hypothesis tables up to this size stay dense per env (gc_bd_posterior's limit)
+_FORCE_LISTS = bool(os.environ.get("GC_BD_LISTS"))  # tests: run small tables through the list form too
 
 
 class _StateView:
@@ -187,6 +191,17 @@ class _ObserverTables:
         self.row_kind_host, self.row_agent_host, self.row_pid_host = kind, agent, pid
         self.row_agent2_host = np.array([ag[1] if len(ag) > 1 else ag[0] for s, ag in rows], dtype=np.int64)
         self.A = 25 if bool((kind == 3).any()) else 5
+        # list form (three / four agents): an env keeps the table rows that survive pruning as a list `rid`; row H is
+        # the padding row (no entries, never alive)
+        self.lists = H > DENSE_MAX_H or _FORCE_LISTS
+        pad = lambda a, fill: t(np.concatenate([a, np.full((1,) + a.shape[1:], fill, dtype=a.dtype)]))
+        self.ent_lidx_pad = pad(np.where(has, lid, len(owner.lpairs)), len(owner.lpairs))
+        self.ent_pidx_pad = pad(np.where(has, pid0, len(owner.cpairs)), len(owner.cpairs))
+        self.rank_pad = pad(rank, H)
+        self.sel_sub_pad, self.sel_joint_pad = pad(sel_sub, S), pad(sel_joint, False)
+        self.sel_first_pad, self.plan_pid_pad = pad(sel_first, True), pad(plan_pid, 0)
+        self.hyp_pair_dev = self.hyp_pair.contiguous()
+        self.pair_w_host = w
 
 
 class BatchedDelegation:
@@ -225,13 +240,9 @@ class BatchedDelegation:
         self.lpair_sub = torch.tensor([p[0] for p in self.lpairs], dtype=torch.int64, device=self.device)
         self.cache = PlanCache(self.kb, self.cpairs)
         self.tables = [_ObserverTables(self, i, models[i]) for i in range(self.NA)]
-        # the hypothesis space is tabulated over the level's full subtask list (H rows per observer) and every env
-        # keeps a dense probability row: fine for two agents (H <= 100) and for three (H <= 2 457), out of
-        # reach for four bd agents at scale (H = 39 906)
-        dense = sum(T.H for T in self.tables) * num_envs * 9
-        if dense > (24 << 30):
-            raise MemoryError("%d envs x %s hypotheses need %.0f GB of dense tables: use fewer envs (the pruned "
-                              "per-env representation is not built yet)" % (num_envs, [T.H for T in self.tables], dense / 2 ** 30))
+        # the hypothesis space is tabulated over the level's full subtask list (H rows per observer); an env keeps a
+        # dense probability row over it for two agents (H <= 100) and a list of the surviving rows beyond that
+        # (H = 2 457 for three, 39 906 for four bd agents on a salad level, of which a few hundred survive pruning)
         masks = [recipe_planner.subtask_masks(s) for s in self.subtasks]
         dev = self.device
         self.goal_mask = torch.tensor([m[3] for m in masks], dtype=torch.int64, device=dev)
@@ -258,8 +269,9 @@ class BatchedDelegation:
         self.cur_sub = torch.full((N, NA), self.S, dtype=torch.int64, device=dev)
         self.cur_joint = torch.zeros((N, NA), dtype=torch.bool, device=dev)
         self.has_probs = torch.zeros((N, NA), dtype=torch.bool, device=dev)
-        self.probs = [torch.zeros((N, T.H), dtype=torch.float64, device=dev) for T in self.tables]
-        self.alive = [torch.zeros((N, T.H), dtype=torch.bool, device=dev) for T in self.tables]
+        self.probs = [torch.zeros((N, 1 if T.lists else T.H), dtype=torch.float64, device=dev) for T in self.tables]
+        self.alive = [torch.zeros((N, 1 if T.lists else T.H), dtype=torch.bool, device=dev) for T in self.tables]
+        self.rid = [torch.full((N, 1), T.H, dtype=torch.int64, device=dev) if T.lists else None for T in self.tables]
         self.executed = torch.full((N, NA), 4, dtype=torch.uint8, device=dev)
         self.prev = None
         self.posterior_updates = 0
@@ -330,7 +342,7 @@ class BatchedDelegation:
         """index of one True per row of `cand`: uniformly random, or lowest rank when deterministic"""
         if self.deterministic:
             r = rank if rank is not None else torch.arange(cand.shape[1], device=cand.device)
-            return torch.where(cand, r.expand_as(cand), cand.shape[1] + 1).argmin(1)
+            return torch.where(cand, r.expand_as(cand), 1 << 40).argmin(1)
         noise = torch.rand(cand.shape, device=cand.device, generator=self.gen) + 1e-6
         return (noise * cand).argmax(1)
 
@@ -410,7 +422,9 @@ class BatchedDelegation:
         return out
 
     def _select_action(self, i, ci, doable, offered):
-        T, S, N, dev = self.tables[i], self.S, self.N, self.device
+        T, S = self.tables[i], self.S
+        if T.lists:
+            return self._select_action_lists(i, ci, doable, offered)
         inc, cur = self.incomplete[:, i], self.cur_sub[:, i]
         alive_new = self._entries_ok(T, doable, inc) & T.static_ok
         alive_cur, has = self.alive[i], self.has_probs[:, i]
@@ -440,17 +454,140 @@ class BatchedDelegation:
         best_p = masked.max(1, keepdim=True).values
         tol = 1e-12 if self.deterministic else 0.0
         best = self._pick(alive & (masked >= best_p - tol), T.rank)
+        return self._plan(i, best, ~alive.any(1), ci, offered)
+
+    # -- the list form: three and four agents ----------------------------------------------------
+    def _alive_rows(self, T, ok):
+        """Rows of T's hypothesis table whose every entry names an `ok` (subtask, agent set) pair, per env, as a
+        front-packed list: (rows int64[N][Wn] padded with H, count int64[N]).  The surviving set depends on the env
+        only through its `ok` bits, so it is evaluated once per DISTINCT bit pattern of the batch (bd:792-886
+        regenerates and bd:200-256 prunes the space per agent and step)."""
+        N, L = ok.shape
+        dev = ok.device
+        words = []
+        for lo in range(0, L, 62):
+            bits = ok[:, lo:lo + 62].long()
+            words.append((bits << torch.arange(bits.shape[1], device=dev)[None, :]).sum(1))
+        uk, inv = torch.unique(torch.stack(words, dim=1), dim=0, return_inverse=True)
+        U = uk.shape[0]
+        first = torch.zeros(U, dtype=torch.int64, device=dev)
+        first.scatter_(0, inv, torch.arange(N, device=dev))  # any env of each pattern
+        ok_u = torch.cat([ok[first], torch.ones((U, 1), dtype=torch.bool, device=dev)], dim=1)  # [U][L + 1]
+        parts, counts = [], []
+        chunk = max(1, (1 << 26) // T.H)
+        for lo in range(0, U, chunk):
+            o = ok_u[lo:lo + chunk]
+            alive_u = T.static_ok[None, :] & o[:, T.ent_lidx[:, 0]]
+            for e in range(1, T.E):
+                alive_u &= o[:, T.ent_lidx[:, e]]
+            k_u = alive_u.sum(1)
+            nz = alive_u.nonzero()  # row-major: grouped by pattern, rows ascending
+            parts.append((nz, k_u))
+            counts.append(k_u)
+        k_u = torch.cat(counts)
+        Wn = max(int(k_u.max()), 1)
+        rows_u = torch.full((U, Wn), T.H, dtype=torch.int64, device=dev)
+        lo = 0
+        for nz, k in parts:
+            off = torch.cumsum(k, 0) - k
+            j = torch.arange(nz.shape[0], device=dev) - off[nz[:, 0]]
+            rows_u[lo + nz[:, 0], j] = nz[:, 1]
+            lo += k.shape[0]
+        return rows_u[inv], k_u[inv]
+
+    @staticmethod
+    def _widen(x, W, fill):
+        if x.shape[1] >= W:
+            return x
+        return torch.cat([x, torch.full((x.shape[0], W - x.shape[1]), fill, dtype=x.dtype, device=x.device)], dim=1)
+
+    def _select_action_lists(self, i, ci, doable, offered):
+        """_select_action with the observer's distribution kept as a list of table rows per env"""
+        T, S, N, dev = self.tables[i], self.S, self.N, self.device
+        H = T.H
+        inc, cur = self.incomplete[:, i], self.cur_sub[:, i]
+        ok = doable & (((inc[:, None] >> self.lpair_sub[None, :]) & 1) != 0)
+        rows_new, k_new = self._alive_rows(T, ok)
+        alive_cur, rid_cur, has = self.alive[i], self.rid[i], self.has_probs[:, i]
+        stale = (cur < S) & (((inc >> cur.clamp(max=S - 1)) & 1) == 0)
+        reset = stale | ~has | (k_new != alive_cur.sum(1))  # should_reset_priors bd:54-79
+        do_prior = reset | (cur >= S)
+        has_fallback = bool(T.fallback.any())
+        if has_fallback:  # dc: an empty distribution becomes {None: me} (bd:1019-1024); the fallback is row H - 1
+            empty = k_new == 0
+            rows_new[:, 0] = torch.where(empty, H - 1, rows_new[:, 0])
+            k_new = torch.where(empty, 1, k_new)
+        alive_new = torch.arange(rows_new.shape[1], device=dev)[None, :] < k_new[:, None]
+        # priors (set_priors bd:262-290, get_spatial_priors :296-369)
+        cnt = k_new.clamp(min=1)[:, None]
+        prior = alive_new.double() / cnt
+        if T.spatial:
+            inv_v = 1.0 / self.cache.v[ci].double().clamp(min=1e-9)
+            inv_v = torch.cat([inv_v, torch.zeros((N, 1), dtype=torch.float64, device=dev)], dim=1)
+            w = inv_v.gather(1, T.ent_pidx_pad[:, 0][rows_new])
+            for e in range(1, T.E):
+                w = w + inv_v.gather(1, T.ent_pidx_pad[:, e][rows_new])
+            p = prior * (w * 4.0)
+            tot = p.sum(1, keepdim=True)
+            prior = torch.where(tot == 0, prior, p / tot.clamp(min=1e-300))
+        if self.prev is not None and not bool(do_prior.all()):
+            okprev = torch.cat([self.prev["doable"], torch.ones((N, 1), dtype=torch.bool, device=dev)], dim=1)
+            alive_upd = alive_cur.clone()
+            for e in range(T.E):
+                alive_upd &= okprev.gather(1, T.ent_lidx_pad[:, e][rid_cur])
+            probs_cur = self.probs[i]
+            if has_fallback:
+                empty = ~alive_upd.any(1)
+                in_list = ((rid_cur == H - 1) & empty[:, None])
+                slot = torch.where(in_list.any(1), in_list.int().argmax(1), 0)  # its own slot if listed, else slot 0
+                at = torch.arange(rid_cur.shape[1], device=dev)[None, :] == slot[:, None]
+                put = empty[:, None] & at
+                probs_cur = torch.where(put & ~in_list, 0.0, probs_cur)
+                rid_cur = torch.where(put, H - 1, rid_cur)
+                alive_upd = alive_upd | put
+            if T.model == "fb":
+                upd = probs_cur * alive_upd
+            else:
+                pv = self.prev
+                upd = probs_cur.contiguous().clone()
+                planning.bd_update_lists(upd, alive_upd.contiguous().view(torch.uint8), rid_cur.contiguous(), T.hyp_pair_dev,
+                                         T.pair_w_host, self.cache.q, pv["ci"].contiguous(), T.row_pid_host,
+                                         T.row_kind_host, T.row_agent_host, T.row_agent2_host, self.executed,
+                                         pv["offered"][:, T.me].sum(-1).to(torch.uint8), T.me, self.none_action_prob,
+                                         self.beta, UNREACHABLE_Q)
+                self.posterior_updates += N
+            W = max(rows_new.shape[1], rid_cur.shape[1])
+            sel = do_prior[:, None]
+            probs = torch.where(sel, self._widen(prior, W, 0.0), self._widen(upd, W, 0.0))
+            alive = torch.where(sel, self._widen(alive_new, W, False), self._widen(alive_upd, W, False))
+            rid = torch.where(sel, self._widen(rows_new, W, H), self._widen(rid_cur, W, H))
+            used = alive.any(0).nonzero()
+            Wt = int(used.max()) + 1 if used.numel() else 1  # drop the columns nobody uses any more
+            probs, alive, rid = probs[:, :Wt].contiguous(), alive[:, :Wt].contiguous(), rid[:, :Wt].contiguous()
+        else:
+            probs, alive, rid = prior, alive_new, rows_new
+        self.probs[i], self.alive[i], self.rid[i] = probs, alive, rid
+        self.has_probs[:, i] = True
+        masked = torch.where(alive, probs, -1.0)
+        best_p = masked.max(1, keepdim=True).values
+        tol = 1e-12 if self.deterministic else 0.0
+        best = self._pick(alive & (masked >= best_p - tol), T.rank_pad[rid] if self.deterministic else None)
         nothing = ~alive.any(1)
-        new_sub = torch.where(nothing, S, T.sel_sub[best])
-        new_joint = T.sel_joint[best] & ~nothing
-        # plan :218-281
-        pid = T.plan_pid[best]
+        hbest = torch.where(nothing, H, rid.gather(1, best[:, None])[:, 0])
+        return self._plan(i, hbest, nothing, ci, offered)
+
+    def _plan(self, i, best, nothing, ci, offered):
+        """select_subtask's result (table row `best`, H = the padding row) -> RealAgent.plan :218-281"""
+        T, S, N, dev = self.tables[i], self.S, self.N, self.device
+        new_sub = torch.where(nothing, S, T.sel_sub_pad[best])
+        new_joint = T.sel_joint_pad[best] & ~nothing
+        pid = T.plan_pid_pad[best]
         q = self.cache.q[ci, pid]  # [N][25]
         q = torch.where(new_joint[:, None] | (torch.arange(25, device=dev)[None, :] < 5), q, float("nan"))
         valid = ~torch.isnan(q)
         qv = torch.where(valid, q.clamp(max=1e30), float("inf"))
         a = self._pick(valid & (qv == qv.min(1, keepdim=True).values))  # argmin, random ties (e2e:27-30)
-        own = torch.where(new_joint, torch.where(T.sel_first[best], a // 5, a % 5), a)  # agent.py:270-272
+        own = torch.where(new_joint, torch.where(T.sel_first_pad[best], a // 5, a % 5), a)  # agent.py:270-272
         own = torch.where(valid.any(1), own, 4)
         # doing nothing: stay with none_action_prob, else a uniformly random offered move (:235-243)
         off = offered[:, i]
@@ -506,6 +643,7 @@ class BatchedDelegation:
             setattr(self, name, getattr(self, name)[live].contiguous())
         self.probs = [p[live].contiguous() for p in self.probs]
         self.alive = [a[live].contiguous() for a in self.alive]
+        self.rid = [None if r is None else r[live].contiguous() for r in self.rid]
         if self.prev is not None:
             self.prev = {k: v[live].contiguous() for k, v in self.prev.items()}
 

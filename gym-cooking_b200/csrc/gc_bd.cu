@@ -612,9 +612,181 @@ int launch_rows(const float* q_table, const int64_t* q_row, int n_pairs, const i
   return gc_check_launch("gc_bd_likelihood_rows");
 }
 
+
+// ---- fused update over per-env hypothesis lists (three / four agents) ----------------------------------
+// With three or four agents the hypothesis table of a level has 10^2..4*10^4 rows (add_subtasks, bd:792-886)
+// of which an env keeps the few that survive pruning (bd:200-256), so each env carries a LIST of table rows
+// (`rid`) next to its probabilities instead of a dense [H] vector, and the table (`hyp_pair [H][E]`) is shared
+// by all envs.  One warp per env: lanes build the env's likelihood values straight from the planner's Q rows
+// (the arithmetic of bd_rows_kernel followed by the softmax of bd_posterior_kernel, same order of operations),
+// park them in shared memory, then walk the list.
+struct RowTableW {
+  RowTable t;
+  uint8_t w[128];
+};
+
+constexpr int kListWarps = 8;
+
+template <typename T>
+__device__ T row_likelihood(const RowTable& rows, int p, const float* __restrict__ q_table, int64_t qrow, int n_pairs,
+                            const uint8_t* __restrict__ ex, int n_moves, int observer, T none_p, T q_cap, T beta) {
+  const int kind = rows.kind[p], ag = rows.agent[p];
+  if (kind == 0) {  // doing nothing (bd:618-641)
+    const int k = min(n_moves, 4);
+    const int nv = k + 1;
+    const int taken_rank = ex[ag] == 4 ? 0 : min(1, nv - 1);
+    const T other = (T(1) - none_p) / T(k);
+    T mx = beta * none_p;
+    if (k > 0) mx = max(mx, beta * other);
+    T sum = exp_t<T>(beta * none_p - mx);
+    for (int a = 1; a <= k; a++) sum += exp_t<T>(beta * other - mx);
+    return exp_t<T>(beta * (taken_rank == 0 ? none_p : other) - mx) / sum;
+  }
+  const float* base = q_table + (qrow * n_pairs + rows.pair[p]) * 25;
+  int taken = min((int)ex[ag], 4), stride = 1, offset = 0, count = 5;
+  if (kind == 3) {  // joint row without the observer: all 25 joint actions, taken = 5 a_i + a_j
+    taken = 5 * taken + min((int)ex[rows.agent2[p]], 4);
+    count = 25;
+  } else if (kind == 2) {  // only joint actions matching the partner's executed move (bd:677-679)
+    const int ag2 = rows.agent2[p];
+    if (observer == ag) {
+      stride = 5;
+      offset = min((int)ex[ag2], 4);
+    } else {
+      offset = 5 * taken;
+      taken = min((int)ex[ag2], 4);
+    }
+  }
+  const float qt = base[offset + taken * stride];
+  const T old = (isnan(qt) || isinf(qt)) ? q_cap : min((T)qt, q_cap);
+  T mx = T(0);  // the taken action is always valid and its difference is 0
+  bool first = true;
+  for (int a = 0; a < count; a++) {
+    const float q = base[offset + a * stride];
+    if (!isnan(q) || a == taken) {
+      const T d = beta * (old - ((isnan(q) || isinf(q)) ? q_cap : min((T)q, q_cap)));
+      mx = first ? d : max(mx, d);
+      first = false;
+    }
+  }
+  T sum = T(0);
+  for (int a = 0; a < count; a++) {
+    const float q = base[offset + a * stride];
+    if (!isnan(q) || a == taken) sum += exp_t<T>(beta * (old - ((isnan(q) || isinf(q)) ? q_cap : min((T)q, q_cap))) - mx);
+  }
+  return exp_t<T>(beta * (old - old) - mx) / sum;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kListWarps * 32)
+bd_update_lists_kernel(T* __restrict__ probs, const uint8_t* __restrict__ alive, const int64_t* __restrict__ rid, int W,
+                       const uint8_t* __restrict__ hyp_pair, int H, int E, const float* __restrict__ q_table,
+                       const int64_t* __restrict__ q_row, int n_pairs, const __grid_constant__ RowTableW rows,
+                       const uint8_t* __restrict__ executed, const uint8_t* __restrict__ n_moves, int observer, T none_p,
+                       T q_cap, T beta, int64_t n, int P, int n_agents) {
+  __shared__ T s_l[kListWarps][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t env = (int64_t)blockIdx.x * kListWarps + warp;
+  if (env >= n) return;
+  const uint8_t* ex = executed + env * n_agents;
+  const int64_t qrow = q_row[env];
+  const int nm = n_moves[env];
+  for (int p = lane; p < P; p += 32)
+    s_l[warp][p] = T(rows.w[p]) * row_likelihood<T>(rows.t, p, q_table, qrow, n_pairs, ex, nm, observer, none_p, q_cap, beta);
+  __syncwarp();
+  T* pr = probs + env * W;
+  const uint8_t* al = alive + env * W;
+  const int64_t* rd = rid + env * W;
+  T total = T(0);
+  int n_alive = 0;
+  for (int k = lane; k < W; k += 32) {
+    const int64_t r = rd[k];
+    T v = T(0);
+    if (al[k] && r >= 0 && r < H) {
+      T update = T(0);
+      for (int e = 0; e < E; e++) {
+        const int p = hyp_pair[r * E + e];
+        if (p != 0xFF) update += s_l[warp][p];
+      }
+      v = pr[k] * update;
+      n_alive += 1;
+      total += v;
+    }
+    pr[k] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    total += __shfl_xor_sync(0xffffffffu, total, o);
+    n_alive += __shfl_xor_sync(0xffffffffu, n_alive, o);
+  }
+  __syncwarp();
+  for (int k = lane; k < W; k += 32) {
+    const int64_t r = rd[k];
+    if (al[k] && r >= 0 && r < H) pr[k] = (total == T(0)) ? T(1) / T(n_alive) : pr[k] * (T(1) / total);
+  }
+}
+
+template <typename T>
+int launch_lists(T* probs, const uint8_t* alive, const int64_t* rid, int W, const uint8_t* hyp_pair, int H, int E,
+                 const uint8_t* pair_w, const float* q_table, const int64_t* q_row, int n_pairs, const int32_t* row_pair,
+                 const uint8_t* row_kind, const uint8_t* row_agent, const uint8_t* row_agent2, const uint8_t* executed,
+                 const uint8_t* n_moves, int observer, T none_p, T q_cap, T beta, int64_t n, int P, int n_agents,
+                 void* stream) {
+  if (!probs || !alive || !rid || !hyp_pair || !pair_w || !q_table || !q_row || !row_pair || !row_kind || !row_agent ||
+      !row_agent2 || !executed || !n_moves)
+    return gc_fail(GC_E_ARG, "gc_bd_update_lists: null array");
+  if (n < 0 || W < 1 || H < 1 || E < 1 || E > GC_MAX_AGENTS || P < 1 || P > 128 || n_pairs < 1 || n_agents < 1 ||
+      n_agents > GC_MAX_AGENTS || observer < 0 || observer >= n_agents)
+    return gc_fail(GC_E_ARG, "gc_bd_update_lists: bad sizes (n=%lld W=%d H=%d E=%d P=%d pairs=%d agents=%d observer=%d)",
+                   (long long)n, W, H, E, P, n_pairs, n_agents, observer);
+  RowTableW rt;
+  memset(&rt, 0, sizeof(rt));
+  for (int p = 0; p < P; p++) {
+    const int kind = row_kind[p];
+    if (kind > 3 || row_agent[p] >= n_agents || (kind >= 2 && row_agent2[p] >= n_agents) ||
+        (kind != 0 && (row_pair[p] < 0 || row_pair[p] >= n_pairs)))
+      return gc_fail(GC_E_ARG, "gc_bd_update_lists: row %d is malformed", p);
+    const bool inside = observer == row_agent[p] || observer == row_agent2[p];
+    if ((kind == 2 && !inside) || (kind == 3 && inside))
+      return gc_fail(GC_E_ARG, "gc_bd_update_lists: row %d: kind 2 = joint row with the observer, kind 3 = without", p);
+    rt.t.pair[p] = row_pair[p];
+    rt.t.kind[p] = (uint8_t)kind;
+    rt.t.agent[p] = row_agent[p];
+    rt.t.agent2[p] = row_agent2[p];
+    rt.w[p] = pair_w[p];
+  }
+  if (n == 0) return GC_OK;
+  if (int rc = gc_require_device()) return rc;
+  bd_update_lists_kernel<T><<<(unsigned)((n + kListWarps - 1) / kListWarps), kListWarps * 32, 0, (cudaStream_t)stream>>>(
+      probs, alive, rid, W, hyp_pair, H, E, q_table, q_row, n_pairs, rt, executed, n_moves, observer, none_p, q_cap, beta,
+      n, P, n_agents);
+  return gc_check_launch("gc_bd_update_lists");
+}
+
 }  // namespace
 
 extern "C" {
+
+int gc_bd_update_lists_f32(float* probs, const uint8_t* alive, const int64_t* rid, int W, const uint8_t* hyp_pair, int H,
+                           int n_entries, const uint8_t* pair_w, const float* q_table, const int64_t* q_row, int n_pairs,
+                           const int32_t* row_pair, const uint8_t* row_kind, const uint8_t* row_agent,
+                           const uint8_t* row_agent2, const uint8_t* executed, const uint8_t* n_moves, int observer,
+                           float none_action_prob, float q_cap, float beta, int64_t n, int P, int n_agents, void* stream) {
+  return launch_lists<float>(probs, alive, rid, W, hyp_pair, H, n_entries, pair_w, q_table, q_row, n_pairs, row_pair,
+                             row_kind, row_agent, row_agent2, executed, n_moves, observer, none_action_prob, q_cap, beta,
+                             n, P, n_agents, stream);
+}
+
+int gc_bd_update_lists_f64(double* probs, const uint8_t* alive, const int64_t* rid, int W, const uint8_t* hyp_pair, int H,
+                           int n_entries, const uint8_t* pair_w, const float* q_table, const int64_t* q_row, int n_pairs,
+                           const int32_t* row_pair, const uint8_t* row_kind, const uint8_t* row_agent,
+                           const uint8_t* row_agent2, const uint8_t* executed, const uint8_t* n_moves, int observer,
+                           double none_action_prob, double q_cap, double beta, int64_t n, int P, int n_agents,
+                           void* stream) {
+  return launch_lists<double>(probs, alive, rid, W, hyp_pair, H, n_entries, pair_w, q_table, q_row, n_pairs, row_pair,
+                              row_kind, row_agent, row_agent2, executed, n_moves, observer, none_action_prob, q_cap, beta,
+                              n, P, n_agents, stream);
+}
 
 int gc_bd_posterior_f32(float* probs, const uint8_t* alive, const uint8_t* hyp_pair, const uint8_t* pair_w,
                         const float* qdiff, const uint8_t* n_valid, const uint8_t* act_idx, float beta, int64_t n,

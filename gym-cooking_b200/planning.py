@@ -53,6 +53,31 @@ def bd_likelihood_rows(q_table, q_row, row_pair, row_kind, row_agent, row_agent2
     return qdiff, n_valid, act_idx
 
 
+def bd_update_lists(probs, alive, rid, hyp_pair, pair_w, q_table, q_row, row_pair, row_kind, row_agent, row_agent2,
+                    executed, n_moves, observer, none_action_prob, beta, q_cap=100.0):
+    """bayes_update (bd:1026-1072) in place on per-env hypothesis LISTS: probs/alive/rid [n][W], rid naming rows of
+    the shared table hyp_pair [H][E]; the likelihood rows are built inside the kernel - see gymcook.h."""
+    lib = _lib.load()
+    n, W = probs.shape
+    H, E = hyp_pair.shape
+    P = len(row_pair)
+    dev = probs.device
+    rp = np.ascontiguousarray(np.asarray(row_pair, dtype=np.int32))
+    rk, ra, ra2, pw = (np.ascontiguousarray(np.asarray(a, dtype=np.uint8)) for a in (row_kind, row_agent, row_agent2, pair_w))
+    fn = {torch.float32: lib.gc_bd_update_lists_f32, torch.float64: lib.gc_bd_update_lists_f64}[probs.dtype]
+    u8 = torch.uint8
+    if alive.shape != probs.shape or rid.shape != probs.shape or len(pw) != P:
+        raise _lib.GcError("bd_update_lists: probs, alive and rid must share [n][W]; pair_w has one weight per row")
+    with torch.cuda.device(dev):
+        _lib.check(fn(_lib.ptr(probs), _lib.ptr(alive, u8), _lib.ptr(rid, torch.int64), W, _lib.ptr(hyp_pair, u8), H, E,
+                      pw.ctypes.data_as(C.c_void_p), _lib.ptr(q_table, torch.float32), _lib.ptr(q_row, torch.int64),
+                      q_table.shape[1], rp.ctypes.data_as(C.c_void_p), rk.ctypes.data_as(C.c_void_p),
+                      ra.ctypes.data_as(C.c_void_p), ra2.ctypes.data_as(C.c_void_p), _lib.ptr(executed, u8),
+                      _lib.ptr(n_moves, u8), int(observer), float(none_action_prob), float(q_cap), float(beta), n, P,
+                      executed.shape[1], _lib.stream_ptr(dev)))
+    return probs
+
+
 def _pairs_array(pairs):
     """[(subtask index, agent i, agent j or None[, level1])] -> host uint8[n_pairs][3]; a truthy
     fourth element selects the level-1 planning world (bit 7 of the subtask byte, gymcook.h)."""

@@ -302,6 +302,28 @@ int gc_bd_likelihood_rows_f64(const float* q_table, const int64_t* q_row, int n_
                               double q_cap, double* qdiff, uint8_t* n_valid, uint8_t* act_idx, int64_t n, int P,
                               int n_agents, int A, void* stream);
 
+/* bayes_update (bd:1026-1072) for envs that keep their hypotheses as a LIST of rows of a shared table - the form
+ * three and four agents need, where the table of a level has up to 4*10^4 rows (add_subtasks, bd:792-886) and an env
+ * only the few that survive pruning (bd:200-256).  Fuses gc_bd_likelihood_rows and gc_bd_posterior: the likelihood
+ * values are built from the planner's Q rows inside the kernel (one warp per env), no [n][P][A] array exists.
+ *   probs    device [n][W]            in place; entries that are not alive are set to 0
+ *   alive    device uint8 [n][W]
+ *   rid      device int64 [n][W]      row of the hypothesis table each list entry stands for (outside 0..H-1 = dead)
+ *   hyp_pair device uint8 [H][n_entries]  likelihood-row index of each entry of each table row, 0xFF = unused
+ *   pair_w   HOST uint8 [P]           weight of a likelihood row (bd:1066)
+ * Row tables, executed, n_moves, q_table, q_row: as gc_bd_likelihood_rows_*.  total == 0 -> uniform over the alive. */
+int gc_bd_update_lists_f32(float* probs, const uint8_t* alive, const int64_t* rid, int W, const uint8_t* hyp_pair, int H,
+                           int n_entries, const uint8_t* pair_w, const float* q_table, const int64_t* q_row, int n_pairs,
+                           const int32_t* row_pair, const uint8_t* row_kind, const uint8_t* row_agent,
+                           const uint8_t* row_agent2, const uint8_t* executed, const uint8_t* n_moves, int observer,
+                           float none_action_prob, float q_cap, float beta, int64_t n, int P, int n_agents, void* stream);
+int gc_bd_update_lists_f64(double* probs, const uint8_t* alive, const int64_t* rid, int W, const uint8_t* hyp_pair, int H,
+                           int n_entries, const uint8_t* pair_w, const float* q_table, const int64_t* q_row, int n_pairs,
+                           const int32_t* row_pair, const uint8_t* row_kind, const uint8_t* row_agent,
+                           const uint8_t* row_agent2, const uint8_t* executed, const uint8_t* n_moves, int observer,
+                           double none_action_prob, double q_cap, double beta, int64_t n, int P, int n_agents,
+                           void* stream);
+
 /* ---- (B) navigation planner ------------------------------------------------------------
  * Distance lower bound of env.get_lower_bound_for_subtask_given_objs (env:594-664) =
  * World.get_lower_bound_between (utils/world.py:115-264) + holding penalty, for every

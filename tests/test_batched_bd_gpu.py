@@ -52,7 +52,21 @@ def deterministic_facade(monkeypatch):
                                           ("open-divider_tl", ("greedy", "bd", "fb")),
                                           ("open-divider_tomato", ("bd", "up", "dc", "greedy"))])
 def test_batched_loop_equals_facade_loop(level, models, deterministic_facade):
+    _compare_with_facade(level, models, deterministic_facade)
+
+
+@pytest.mark.parametrize("level,models", [("open-divider_tl", ("bd", "bd")), ("partial-divider_tl", ("greedy", "bd")),
+                                          ("open-divider_tomato", ("dc", "fb")), ("partial-divider_tomato", ("bd", "up", "dc"))])
+def test_list_form_equals_facade_loop(level, models, deterministic_facade, monkeypatch):
+    """the same comparison with the small hypothesis tables forced through the per-env LIST form that large tables
+    (three agents on tl / salad levels, four agents) always take"""
+    monkeypatch.setattr(batched_agents, "_FORCE_LISTS", True)
+    _compare_with_facade(level, models, deterministic_facade)
+
+
+def _compare_with_facade(level, models, deterministic_facade):
     loop = batched_agents.BatchedDelegation(level, 8, models, deterministic=True)
+    assert all(T.lists == (T.H > batched_agents.DENSE_MAX_H or batched_agents._FORCE_LISTS) for T in loop.tables)
     deterministic_facade["list"] = loop.subtasks
     env, agents, history = gmain.main_loop(_arglist(level, models), max_steps=40)
     for step, action_dict in enumerate(history):
