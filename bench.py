@@ -356,7 +356,32 @@ def run_ours(args):
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)  # NCCL over NVLink, 1064 bytes
     stats = stats.cpu().tolist()
 
+    # ---- cfg-5: four agents, mixed bd/up/dc/fb/greedy, all nine levels; every rank runs its own shard of episodes
+    # (no data-path collective), the totals are reduced like the episode statistics ----
+    cfg5 = None
+    if not args.no_secondary and args.cfg5_envs > 0:
+        from gym_cooking_b200 import batched_agents
+        r5 = batched_agents.run_mixed(args.cfg5_envs, 4, shard=rank, device=dev)
+        tot = torch.tensor([r5["envs"], r5["agent_steps"], r5["posterior_updates"], r5["delivered"],
+                            r5["planning_states_solved"], r5["planner_lookups"], r5["completed_subtasks"]],
+                           dtype=torch.int64, device=dev)
+        tmax = torch.tensor([r5["seconds"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tot, tmax = tot.cpu().tolist(), float(tmax.item())
+        cfg5 = {"metric": "cfg5_agent_steps_per_sec", "value": tot[1] / tmax, "unit": "agent-steps/s",
+                "config": "cfg-5: 4 agents, model types bd/up/dc/fb/greedy rotated over seats and levels, all nine levels, "
+                          "%d envs per level per GPU x %d GPU(s), horizon 100, full delegation loop from reset with a cold "
+                          "planner memo (max over ranks of the summed per-level wall time)" % (args.cfg5_envs, world),
+                "posterior_updates_per_sec": tot[2] / tmax, "seconds": tmax, "envs": tot[0], "delivered": tot[3],
+                "planning_states_solved": tot[4], "planner_lookups": tot[5], "completed_subtasks": tot[6],
+                "note": "planner-bound: with four agents nearly every env-step reaches a planning state nobody has seen, "
+                        "and each such state costs 20 x n_subtasks exact searches (DESIGN.md section 7)",
+                "per_level_rank0": [{k_: v_ for k_, v_ in rec.items()} for rec in r5["per_level"]]}
     secondary = secondary_metrics(gcb, torch, dev) if (rank == 0 and not args.no_secondary) else None
+    if secondary is not None and cfg5 is not None:
+        secondary.append(cfg5)
     if rank == 0:
         peak, peak_src = hbm_peak_gbs()
         launch_s = ms * 1e-3 / args.steps  # average gc_env_step launch, launch gaps included
@@ -587,6 +612,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cfg5-envs", type=int, default=128,
+                    help="envs per level (x 9 levels) per GPU of the cfg-5 leg (4 agents, mixed models); 0 skips it")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the planner / posterior side metrics (used for short ncu passes)")
     args = ap.parse_args()

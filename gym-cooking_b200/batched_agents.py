@@ -666,3 +666,40 @@ class BatchedDelegation:
                 done = 0  # the working batch now holds running envs only
         self._write_back()
         return steps
+
+
+# -- cfg-5 of the north star: four agents, mixed model types, all nine levels ---------------------------
+MIXED_MODELS = ("bd", "up", "dc", "fb", "greedy")
+MIXED_LEVELS = tuple("%s-divider_%s" % (d, r) for r in ("tomato", "tl", "salad") for d in ("open", "partial", "full"))
+
+
+def run_mixed(envs_per_level, n_agents=4, levels=MIXED_LEVELS, shard=0, horizon=100, device=None, seed=1, max_steps=None):
+    """The reference's experiment grid (run_experiments.sh: every level x every model type) as batches: for level
+    k of `levels`, `envs_per_level` episodes of `n_agents` RealAgents whose model types are MIXED_MODELS rotated by
+    k + shard (so every type meets every level and every seat).  Episodes are independent: `shard` (a rank) only
+    changes seeds and the rotation.  Returns the totals and one record per level; wall-clock seconds are measured
+    with a device synchronisation on both sides."""
+    import time
+    total = dict(envs=0, agent_steps=0, posterior_updates=0, delivered=0, seconds=0.0, planning_states_solved=0,
+                 planner_lookups=0, completed_subtasks=0, per_level=[])
+    for k, level in enumerate(levels):
+        models = tuple(MIXED_MODELS[(k + shard + j) % len(MIXED_MODELS)] for j in range(n_agents))
+        loop = BatchedDelegation(level, envs_per_level, models, max_num_timesteps=horizon,
+                                 seed=seed + 1000 * shard + k, device=device)
+        torch.cuda.synchronize(loop.device)
+        t0 = time.perf_counter()
+        steps = loop.run(max_steps=max_steps)
+        torch.cuda.synchronize(loop.device)
+        dt = time.perf_counter() - t0
+        st = loop.kb.stats().cpu().tolist()
+        rec = dict(level=level, models="/".join(models), hypotheses=[T.H for T in loop.tables], loop_steps=steps,
+                   seconds=dt, agent_steps=loop.agent_steps, posterior_updates=loop.posterior_updates, delivered=st[1],
+                   completed_subtasks=st[133], planning_states_solved=loop.cache.solved_states,
+                   planner_lookups=loop.cache.lookups)
+        total["per_level"].append(rec)
+        total["envs"] += envs_per_level
+        for key in ("agent_steps", "posterior_updates", "delivered", "seconds", "planning_states_solved", "planner_lookups",
+                    "completed_subtasks"):
+            total[key] += rec[key]
+        del loop
+    return total
