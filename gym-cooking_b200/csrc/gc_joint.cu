@@ -477,8 +477,11 @@ __device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* 
         atomicExch(over, 1);
       }
     }
+    // strictly cheaper only: `prev == 2g + 1` is this state already SETTLED at the same cost - re-opening it would
+    // expand it a second time and record every one of its edges twice.  (The min has cleared its settled bit by
+    // then, which is harmless: the one open-list entry that carried this cost has been consumed.)
     const uint32_t prev = atomicMin(&A->gcost[h], 2u * g);
-    if (prev > 2u * g) {
+    if (prev > 2u * g + 1u) {
       const uint32_t est = is_goal(w, p) ? 0u : heuristic(w, T, p);
       if (est == kInfCost) return;  // dead end: recorded (it has a slot and its edge) but never expanded
       const uint32_t f = max(fmin, g + est);
@@ -497,13 +500,17 @@ __device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* 
   atomicExch(over, 1);
 }
 
-// Forward pass, one open-list entry (slot | g << 17) popped at key `cur`: settle it (stale entries
-// and states expanded already fail the CAS), absorb goal states, relax every joint successor.
-__device__ __forceinline__ void expand_entry(const World& w, const Tables* T, Arena2* A, uint32_t* bcount,
-                                             uint32_t* n_states, uint32_t* n_pool, uint32_t* n_goals, int* over,
-                                             int* result, uint32_t entry, uint32_t cur, uint32_t max_states) {
+// Forward pass over the open-list entries (slot | g << 17) popped at key `cur`, in two phases so that the
+// parallelism is (entry x joint action) and not just entries: a frontier of this search has a handful of states
+// far more often than a CTA's worth, and a thread that relaxes all 24 successors of one state itself pays 24
+// dependent chains of global atomics (hash CAS, edge node, cost min, bucket push) one after the other - the
+// kernel sat at 8 of 32 lanes and 3.5 % issue utilisation (profiles/r02_planner_kernels_ncu.csv).
+// settle_entry: claim the state (stale entries and states expanded already fail the CAS), absorb goal states;
+// returns false when there is nothing to expand.
+__device__ __forceinline__ bool settle_entry(const World& w, Arena2* A, uint32_t* n_goals, int* over, int* result,
+                                             uint32_t entry) {
   const uint32_t h = entry & (kSlots2 - 1u), g = entry >> 17;
-  if (atomicCAS(&A->gcost[h], 2u * g, 2u * g + 1u) != 2u * g) return;
+  if (atomicCAS(&A->gcost[h], 2u * g, 2u * g + 1u) != 2u * g) return false;
   const PState p = unpack_state(A->states[h]);
   if (is_goal(w, p)) {
     atomicMin(result, (int)g);
@@ -511,20 +518,24 @@ __device__ __forceinline__ void expand_entry(const World& w, const Tables* T, Ar
     const uint32_t gi = atomicAdd(n_goals, 1u);
     if (gi < kGoalCap) A->goals[gi] = h;
     else atomicExch(over, 1);
-    return;
+    return false;
   }
-  const uint32_t v1 = single_actions(w, p, 0), v2 = single_actions(w, p, 1);
-  for (uint32_t b1 = 0; b1 < 5; b1++) {
-    if (!((v1 >> b1) & 1u)) continue;
-    for (uint32_t b2 = 0; b2 < 5; b2++) {
-      if (!((v2 >> b2) & 1u) || (b1 == 4u && b2 == 4u) || !joint_ok(w, p, b1, b2)) continue;
-      PState nx = p;
-      interact(w, nx, 0, b1);
-      interact(w, nx, 1, b2);
-      const uint32_t code = (b1 != 4u) + (b2 != 4u);
-      relax2(w, T, A, bcount, n_states, n_pool, over, nx, g + 10u + code, cur, h, code, max_states);
-    }
-  }
+  return true;
+}
+
+// expand_action: relax the successor of a settled entry under joint action `act` (0..23; stay-stay is a self loop)
+__device__ __forceinline__ void expand_action(const World& w, const Tables* T, Arena2* A, uint32_t* bcount,
+                                              uint32_t* n_states, uint32_t* n_pool, int* over, uint32_t entry,
+                                              uint32_t act, uint32_t cur, uint32_t max_states) {
+  const uint32_t h = entry & (kSlots2 - 1u), g = entry >> 17;
+  const uint32_t b1 = act / 5u, b2 = act % 5u;
+  const PState p = unpack_state(A->states[h]);
+  if (!((single_actions(w, p, 0) >> b1) & 1u) || !((single_actions(w, p, 1) >> b2) & 1u) || !joint_ok(w, p, b1, b2)) return;
+  PState nx = p;
+  interact(w, nx, 0, b1);
+  interact(w, nx, 1, b2);
+  const uint32_t code = (b1 != 4u) + (b2 != 4u);
+  relax2(w, T, A, bcount, n_states, n_pool, over, nx, g + 10u + code, cur, h, code, max_states);
 }
 
 template <int kTreeThreads>
@@ -612,9 +623,22 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
           __syncthreads();
           const uint32_t cnt = s_cnt;
           if (cnt == done) break;
+#ifdef GC_JOINT_PER_ENTRY  // the earlier shape, kept for A/B builds: one thread settles AND expands an entry
           for (uint32_t e = done + threadIdx.x; e < cnt; e += kTreeThreads)
-            expand_entry(w, &T, A, bcount, &n_states, &n_pool, &n_goals, &over, &result, A->bucket[b][e], (uint32_t)cur,
-                         max_states);
+            if (settle_entry(w, A, &n_goals, &over, &result, A->bucket[b][e]))
+              for (uint32_t act = 0; act < 24u; act++)
+                expand_action(w, &T, A, bcount, &n_states, &n_pool, &over, A->bucket[b][e], act, (uint32_t)cur, max_states);
+          done = cnt;
+          if (cnt == kRingCap) break;
+          continue;
+#endif
+          for (uint32_t e = done + threadIdx.x; e < cnt; e += kTreeThreads)
+            if (!settle_entry(w, A, &n_goals, &over, &result, A->bucket[b][e])) A->bucket[b][e] = kNil;
+          __syncthreads();
+          for (uint32_t item = threadIdx.x; item < (cnt - done) * 24u; item += kTreeThreads) {
+            const uint32_t entry = A->bucket[b][done + item / 24u];
+            if (entry != kNil) expand_action(w, &T, A, bcount, &n_states, &n_pool, &over, entry, item % 24u, (uint32_t)cur, max_states);
+          }
           done = cnt;
           if (cnt == kRingCap) break;
         }

@@ -18,6 +18,7 @@ for v in "$@"; do
     ilp2c4) build ilp2c4 -DGC_STEP2_ILP=2 -DGC_STEP2_MIN_CTAS_ALL=4 & ;;
     ilp2c5) build ilp2c5 -DGC_STEP2_ILP=2 -DGC_STEP2_MIN_CTAS_ALL=5 & ;;
     ilp2t128) build ilp2t128 -DGC_STEP2_ILP=2 -DGC_STEP2_THREADS=128 -DGC_STEP2_MIN_CTAS_ALL=8 & ;;
+    jpe) build jpe -DGC_JOINT_PER_ENTRY & ;;
   esac
 done
 wait

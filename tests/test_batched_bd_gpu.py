@@ -141,3 +141,16 @@ def test_episode_lengths_against_the_reference_yardsticks(level, optimum, min_su
         assert int(lengths.min()) <= 23 <= int(lengths.max())
     print("%s: %.1f %% delivered, steps min %d mean %.1f max %d (reference yardstick %d)" % (
         level, 100 * float(ok.float().mean()), int(lengths.min()), float(lengths.float().mean()), int(lengths.max()), optimum))
+
+
+def test_mixed_four_agent_grid_runs():
+    """cfg-5 in miniature: four agents, rotated model types, three levels - every episode ends (delivery or
+    horizon), most deliver, and the totals add up"""
+    levels = ("open-divider_tomato", "partial-divider_tl", "full-divider_salad")
+    r = batched_agents.run_mixed(24, 4, levels=levels, horizon=60, seed=3)
+    assert r["envs"] == 72 and len(r["per_level"]) == 3
+    assert [rec["models"] for rec in r["per_level"]] == ["bd/up/dc/fb", "up/dc/fb/greedy", "dc/fb/greedy/bd"]
+    assert r["agent_steps"] == sum(rec["agent_steps"] for rec in r["per_level"]) and r["agent_steps"] <= 72 * 4 * 61
+    assert r["delivered"] >= 36 and r["posterior_updates"] > 0
+    assert r["per_level"][2]["hypotheses"][2] == 10 and max(r["per_level"][2]["hypotheses"]) == 39906  # greedy / bd tables
+    assert all(rec["loop_steps"] <= 61 for rec in r["per_level"])
