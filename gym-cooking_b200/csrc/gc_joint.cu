@@ -468,11 +468,14 @@ __device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* 
     } else if (old != k) {
       continue;
     }
+    // (the cost min and the list-head exchange do not depend on each other: both are issued before either
+    // result is used, one global round trip instead of two)
+    const uint32_t prev = atomicMin(&A->gcost[h], 2u * g);
     if (pred != kNil) {
       const uint32_t node = atomicAdd(n_pool, 1u);
       if (node < kPool) {
-        A->pool[node].x = pred | (code << 30);
-        A->pool[node].y = atomicExch(&A->head[h], node);
+        const uint32_t next = atomicExch(&A->head[h], node);
+        A->pool[node] = make_uint2(pred | (code << 30), next);
       } else {
         atomicExch(over, 1);
       }
@@ -480,7 +483,6 @@ __device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* 
     // strictly cheaper only: `prev == 2g + 1` is this state already SETTLED at the same cost - re-opening it would
     // expand it a second time and record every one of its edges twice.  (The min has cleared its settled bit by
     // then, which is harmless: the one open-list entry that carried this cost has been consumed.)
-    const uint32_t prev = atomicMin(&A->gcost[h], 2u * g);
     if (prev > 2u * g + 1u) {
       const uint32_t est = is_goal(w, p) ? 0u : heuristic(w, T, p);
       if (est == kInfCost) return;  // dead end: recorded (it has a slot and its edge) but never expanded
@@ -506,31 +508,35 @@ __device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* 
 // dependent chains of global atomics (hash CAS, edge node, cost min, bucket push) one after the other - the
 // kernel sat at 8 of 32 lanes and 3.5 % issue utilisation (profiles/r02_planner_kernels_ncu.csv).
 // settle_entry: claim the state (stale entries and states expanded already fail the CAS), absorb goal states;
-// returns false when there is nothing to expand.
-__device__ __forceinline__ bool settle_entry(const World& w, Arena2* A, uint32_t* n_goals, int* over, int* result,
-                                             uint32_t entry) {
+// returns 0 when there is nothing to expand, else bit 10 | the two agents' offered single actions (5 bits each)
+// and the state itself in `packed`.
+__device__ __forceinline__ uint32_t settle_entry(const World& w, Arena2* A, uint32_t* n_goals, int* over, int* result,
+                                                 uint32_t entry, uint4& packed) {
   const uint32_t h = entry & (kSlots2 - 1u), g = entry >> 17;
-  if (atomicCAS(&A->gcost[h], 2u * g, 2u * g + 1u) != 2u * g) return false;
-  const PState p = unpack_state(A->states[h]);
+  if (atomicCAS(&A->gcost[h], 2u * g, 2u * g + 1u) != 2u * g) return 0u;
+  packed = A->states[h];
+  const PState p = unpack_state(packed);
   if (is_goal(w, p)) {
     atomicMin(result, (int)g);
     A->val[h] = 0u;
     const uint32_t gi = atomicAdd(n_goals, 1u);
     if (gi < kGoalCap) A->goals[gi] = h;
     else atomicExch(over, 1);
-    return false;
+    return 0u;
   }
-  return true;
+  return (1u << 10) | single_actions(w, p, 0) | (single_actions(w, p, 1) << 5);
 }
 
 // expand_action: relax the successor of a settled entry under joint action `act` (0..23; stay-stay is a self loop)
 __device__ __forceinline__ void expand_action(const World& w, const Tables* T, Arena2* A, uint32_t* bcount,
                                               uint32_t* n_states, uint32_t* n_pool, int* over, uint32_t entry,
-                                              uint32_t act, uint32_t cur, uint32_t max_states) {
+                                              const uint4& packed, uint32_t masks, uint32_t act, uint32_t cur,
+                                              uint32_t max_states) {
   const uint32_t h = entry & (kSlots2 - 1u), g = entry >> 17;
   const uint32_t b1 = act / 5u, b2 = act % 5u;
-  const PState p = unpack_state(A->states[h]);
-  if (!((single_actions(w, p, 0) >> b1) & 1u) || !((single_actions(w, p, 1) >> b2) & 1u) || !joint_ok(w, p, b1, b2)) return;
+  if (!((masks >> b1) & 1u) || !((masks >> (5u + b2)) & 1u)) return;
+  const PState p = unpack_state(packed);
+  if (!joint_ok(w, p, b1, b2)) return;
   PState nx = p;
   interact(w, nx, 0, b1);
   interact(w, nx, 1, b2);
@@ -550,6 +556,8 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
   __shared__ PState start;
   __shared__ World w;
   __shared__ __align__(16) Tables T;
+  __shared__ __align__(16) uint4 s_state[kTreeThreads];  // the chunk of open-list entries being expanded
+  __shared__ uint32_t s_ent[kTreeThreads], s_msk[kTreeThreads];
   Arena2* A = arenas + blockIdx.x;
   const int64_t n_prob = n * pairs.n;
   auto clear_all = [&]() {
@@ -624,21 +632,34 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
           const uint32_t cnt = s_cnt;
           if (cnt == done) break;
 #ifdef GC_JOINT_PER_ENTRY  // the earlier shape, kept for A/B builds: one thread settles AND expands an entry
-          for (uint32_t e = done + threadIdx.x; e < cnt; e += kTreeThreads)
-            if (settle_entry(w, A, &n_goals, &over, &result, A->bucket[b][e]))
+          for (uint32_t e = done + threadIdx.x; e < cnt; e += kTreeThreads) {
+            uint4 packed;
+            const uint32_t entry = A->bucket[b][e];
+            const uint32_t masks = settle_entry(w, A, &n_goals, &over, &result, entry, packed);
+            if (masks)
               for (uint32_t act = 0; act < 24u; act++)
-                expand_action(w, &T, A, bcount, &n_states, &n_pool, &over, A->bucket[b][e], act, (uint32_t)cur, max_states);
-          done = cnt;
-          if (cnt == kRingCap) break;
-          continue;
-#endif
-          for (uint32_t e = done + threadIdx.x; e < cnt; e += kTreeThreads)
-            if (!settle_entry(w, A, &n_goals, &over, &result, A->bucket[b][e])) A->bucket[b][e] = kNil;
-          __syncthreads();
-          for (uint32_t item = threadIdx.x; item < (cnt - done) * 24u; item += kTreeThreads) {
-            const uint32_t entry = A->bucket[b][done + item / 24u];
-            if (entry != kNil) expand_action(w, &T, A, bcount, &n_states, &n_pool, &over, entry, item % 24u, (uint32_t)cur, max_states);
+                expand_action(w, &T, A, bcount, &n_states, &n_pool, &over, entry, packed, masks, act, (uint32_t)cur, max_states);
           }
+#else
+          // chunks of one entry per thread: settle (phase A, state and action masks parked in shared memory), then
+          // all (entry, action) pairs of the chunk (phase B)
+          for (uint32_t base = done; base < cnt; base += kTreeThreads) {
+            const uint32_t m = min(cnt - base, (uint32_t)kTreeThreads);
+            if (threadIdx.x < m) {
+              uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+              const uint32_t entry = A->bucket[b][base + threadIdx.x];
+              s_msk[threadIdx.x] = settle_entry(w, A, &n_goals, &over, &result, entry, packed);
+              s_ent[threadIdx.x] = entry;
+              s_state[threadIdx.x] = packed;
+            }
+            __syncthreads();
+            for (uint32_t item = threadIdx.x; item < m * 24u; item += kTreeThreads) {
+              const uint32_t i = item / 24u, masks = s_msk[i];
+              if (masks) expand_action(w, &T, A, bcount, &n_states, &n_pool, &over, s_ent[i], s_state[i], masks, item % 24u, (uint32_t)cur, max_states);
+            }
+            __syncthreads();
+          }
+#endif
           done = cnt;
           if (cnt == kRingCap) break;
         }
@@ -685,10 +706,16 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
         for (uint32_t e = threadIdx.x; e < cnt; e += kTreeThreads) {
           const uint32_t h = A->bbucket[b][e];
           if (A->val[h] != (uint32_t)bc) continue;  // improved since it was pushed
-          for (uint32_t node = A->head[h]; node != kNil; node = A->pool[node].y) {
-            const uint32_t x = A->pool[node].x & 0x3FFFFFFFu;
-            const uint32_t nv = (uint32_t)bc + 10u + (A->pool[node].x >> 30);
-            if (atomicMin(&A->val[x], nv) > nv) {
+          // predecessor list: the next node is fetched while this node's atomic is in flight
+          uint32_t node = A->head[h];
+          uint2 pn = node != kNil ? A->pool[node] : make_uint2(0u, kNil);
+          while (node != kNil) {
+            const uint32_t x = pn.x & 0x3FFFFFFFu;
+            const uint32_t nv = (uint32_t)bc + 10u + (pn.x >> 30);
+            const uint32_t old = atomicMin(&A->val[x], nv);
+            node = pn.y;
+            if (node != kNil) pn = A->pool[node];
+            if (old > nv) {
               const uint32_t pos = atomicAdd(&bbcount[nv & (kBuckets - 1)], 1u);
               if (pos < kRingCap) A->bbucket[nv & (kBuckets - 1)][pos] = x;
               else atomicExch(&over, 2);

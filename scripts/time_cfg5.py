@@ -41,6 +41,14 @@ def main():
                   level, "/".join(models), [T.H for T in loop.tables], t1 - t0, steps, dt, loop.agent_steps / dt, st[1], n,
                   loop.cache.solved_states, loop.cache.lookups,
                   [int(a.shape[1]) for a in loop.alive], torch.cuda.max_memory_allocated() / 2 ** 30), flush=True)
+        if os.environ.get("GC_STATUS"):
+            stt = loop.cache.status  # [states][pairs]
+            kinds = {}
+            for k_, pr in enumerate(loop.cache.pairs):
+                kinds.setdefault(("joint" if pr[2] is not None else "single", "L1" if pr[3] else "L0"), []).append(k_)
+            for key, cols in kinds.items():
+                h = torch.bincount(stt[:, cols].flatten().long(), minlength=5).tolist()
+                print("   %s %s: status histogram %s (0 ok, 1 goal met, 2 unreachable, 3 budget, 4 unsupported)" % (key[0], key[1], h))
         del loop
         torch.cuda.empty_cache()
 
