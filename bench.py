@@ -612,7 +612,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cfg5-envs", type=int, default=128,
+    ap.add_argument("--cfg5-envs", type=int, default=256,
                     help="envs per level (x 9 levels) per GPU of the cfg-5 leg (4 agents, mixed models); 0 skips it")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the planner / posterior side metrics (used for short ncu passes)")
