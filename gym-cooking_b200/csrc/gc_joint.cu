@@ -54,7 +54,15 @@ constexpr uint32_t kSlots2 = 1u << 17;
 #ifndef GC_JOINT_CTAS_PER_SM_DEFAULT
 #define GC_JOINT_CTAS_PER_SM_DEFAULT 16
 #endif
-constexpr uint32_t kMaxStates2 = GC_JOINT_MAX_STATES;
+constexpr uint32_t kMaxStates2 = GC_JOINT_MAX_STATES;   // budget of a per-action A* (and the arenas' capacity)
+#ifndef GC_JOINT_TREE_STATES
+#define GC_JOINT_TREE_STATES (32 * 1024)
+#endif
+#ifndef GC_JOINT_WIDEN_STATES
+#define GC_JOINT_WIDEN_STATES (8 * 1024)
+#endif
+constexpr uint32_t kTreeStates = GC_JOINT_TREE_STATES;    // the tree search's budget BEYOND its first goal: what it cannot prove inside it
+constexpr uint32_t kWidenStates = GC_JOINT_WIDEN_STATES;  // is cheaper to prove action by action; no widening beyond this
 constexpr int64_t kWideProblems = 32 * 1024;
 // one search per CTA: large batches run 4 CTAs of 128 threads per SM (throughput); small ones
 // (the delegation loop solving the few states it has not seen yet) run 2 CTAs of 512 threads so
@@ -453,6 +461,7 @@ __device__ uint32_t heuristic(const World& w, const Tables* T, const PState& p) 
 // insert / relax successor `p` of state slot `pred` (kNil for the start) reached with total cost g
 // over an edge of cost 10 + code; records the edge in p's predecessor list.  fmin = the parent's
 // f, so that keys never decrease along a path (pathmax).  Bucket entries carry (slot, g).
+template <bool kRecord = true>
 __device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* A, uint32_t* bcount, uint32_t* n_states,
                                        uint32_t* n_pool, int* over, const PState& p, uint32_t g, uint32_t fmin,
                                        uint32_t pred, uint32_t code, uint32_t max_states) {
@@ -471,7 +480,7 @@ __device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* 
     // (the cost min and the list-head exchange do not depend on each other: both are issued before either
     // result is used, one global round trip instead of two)
     const uint32_t prev = atomicMin(&A->gcost[h], 2u * g);
-    if (pred != kNil) {
+    if (kRecord && pred != kNil) {  // (the per-action A* needs no backward pass: no edges)
       const uint32_t node = atomicAdd(n_pool, 1u);
       if (node < kPool) {
         const uint32_t next = atomicExch(&A->head[h], node);
@@ -528,6 +537,7 @@ __device__ __forceinline__ uint32_t settle_entry(const World& w, Arena2* A, uint
 }
 
 // expand_action: relax the successor of a settled entry under joint action `act` (0..23; stay-stay is a self loop)
+template <bool kRecord>
 __device__ __forceinline__ void expand_action(const World& w, const Tables* T, Arena2* A, uint32_t* bcount,
                                               uint32_t* n_states, uint32_t* n_pool, int* over, uint32_t entry,
                                               const uint4& packed, uint32_t masks, uint32_t act, uint32_t cur,
@@ -541,7 +551,60 @@ __device__ __forceinline__ void expand_action(const World& w, const Tables* T, A
   interact(w, nx, 0, b1);
   interact(w, nx, 1, b2);
   const uint32_t code = (b1 != 4u) + (b2 != 4u);
-  relax2(w, T, A, bcount, n_states, n_pool, over, nx, g + 10u + code, cur, h, code, max_states);
+  relax2<kRecord>(w, T, A, bcount, n_states, n_pool, over, nx, g + 10u + code, cur, h, code, max_states);
+}
+
+// One key bucket of the forward pass, swept until it stops growing (children on the same plateau - pathmax - land in
+// this very bucket), then emptied.  Shared by the tree search and the per-action A*; every thread of the CTA calls it.
+template <int kTreeThreads, bool kRecord>
+__device__ __forceinline__ void sweep_bucket(const World& w, const Tables& T, Arena2* A, uint32_t* bcount, uint32_t b,
+                                             uint32_t cur, uint32_t* n_states, uint32_t* n_pool, uint32_t* n_goals, int* over,
+                                             int* result, uint32_t* s_cnt, uint4* s_state, uint32_t* s_ent, uint32_t* s_msk,
+                                             uint32_t max_states) {
+  for (uint32_t done = 0;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) *s_cnt = min(bcount[b], kRingCap);
+    __syncthreads();
+    const uint32_t cnt = *s_cnt;
+    if (cnt == done) break;
+#ifdef GC_JOINT_PER_ENTRY  // the earlier shape, kept for A/B builds: one thread settles AND expands an entry
+    for (uint32_t e = done + threadIdx.x; e < cnt; e += kTreeThreads) {
+      uint4 packed;
+      const uint32_t entry = A->bucket[b][e];
+      const uint32_t masks = settle_entry(w, A, n_goals, over, result, entry, packed);
+      if (masks)
+        for (uint32_t act = 0; act < 24u; act++)
+          expand_action<kRecord>(w, &T, A, bcount, n_states, n_pool, over, entry, packed, masks, act, cur, max_states);
+    }
+#else
+    // chunks of one entry per thread: settle (phase A, state and action masks parked in shared memory), then
+    // all (entry, action) pairs of the chunk (phase B)
+    for (uint32_t base = done; base < cnt; base += kTreeThreads) {
+      const uint32_t m = min(cnt - base, (uint32_t)kTreeThreads);
+      if (threadIdx.x < m) {
+        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t entry = A->bucket[b][base + threadIdx.x];
+        s_msk[threadIdx.x] = settle_entry(w, A, n_goals, over, result, entry, packed);
+        s_ent[threadIdx.x] = entry;
+        s_state[threadIdx.x] = packed;
+      }
+      __syncthreads();
+      for (uint32_t item = threadIdx.x; item < m * 24u; item += kTreeThreads) {
+        const uint32_t i = item / 24u, masks = s_msk[i];
+        if (masks) expand_action<kRecord>(w, &T, A, bcount, n_states, n_pool, over, s_ent[i], s_state[i], masks, item % 24u, cur, max_states);
+      }
+      __syncthreads();
+    }
+#endif
+    done = cnt;
+    if (cnt == kRingCap) break;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (bcount[b] > kRingCap) *over = 1;
+    bcount[b] = 0;
+  }
+  __syncthreads();
 }
 
 template <int kTreeThreads>
@@ -613,6 +676,9 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
     // ---- forward A*: every state with key f <= V* + kSlack is expanded, every generated edge recorded ----
     int empty_run = 0, limit = kMaxCost, cur = (int)s_f0, slack = kSlack;
     bool complete = false;
+    // budget: until a goal comes into view this is plain A* and every state is needed (max_states, the arena's
+    // capacity); what follows - the ball of radius V* + slack that proves the other actions - gets kTreeStates more
+    uint32_t budget = max_states;
     for (;;) {  // widen the explored region until every offered action is proven (or kMaxSlack / the budget is hit)
       for (; cur <= limit; cur++) {
         const uint32_t b = (uint32_t)cur & (kRing - 1);
@@ -624,51 +690,9 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
           continue;
         }
         empty_run = 0;
-        // children on the same plateau (pathmax) land in this very bucket: sweep it until it stops growing
-        for (uint32_t done = 0;;) {
-          __syncthreads();
-          if (threadIdx.x == 0) s_cnt = min(bcount[b], kRingCap);
-          __syncthreads();
-          const uint32_t cnt = s_cnt;
-          if (cnt == done) break;
-#ifdef GC_JOINT_PER_ENTRY  // the earlier shape, kept for A/B builds: one thread settles AND expands an entry
-          for (uint32_t e = done + threadIdx.x; e < cnt; e += kTreeThreads) {
-            uint4 packed;
-            const uint32_t entry = A->bucket[b][e];
-            const uint32_t masks = settle_entry(w, A, &n_goals, &over, &result, entry, packed);
-            if (masks)
-              for (uint32_t act = 0; act < 24u; act++)
-                expand_action(w, &T, A, bcount, &n_states, &n_pool, &over, entry, packed, masks, act, (uint32_t)cur, max_states);
-          }
-#else
-          // chunks of one entry per thread: settle (phase A, state and action masks parked in shared memory), then
-          // all (entry, action) pairs of the chunk (phase B)
-          for (uint32_t base = done; base < cnt; base += kTreeThreads) {
-            const uint32_t m = min(cnt - base, (uint32_t)kTreeThreads);
-            if (threadIdx.x < m) {
-              uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-              const uint32_t entry = A->bucket[b][base + threadIdx.x];
-              s_msk[threadIdx.x] = settle_entry(w, A, &n_goals, &over, &result, entry, packed);
-              s_ent[threadIdx.x] = entry;
-              s_state[threadIdx.x] = packed;
-            }
-            __syncthreads();
-            for (uint32_t item = threadIdx.x; item < m * 24u; item += kTreeThreads) {
-              const uint32_t i = item / 24u, masks = s_msk[i];
-              if (masks) expand_action(w, &T, A, bcount, &n_states, &n_pool, &over, s_ent[i], s_state[i], masks, item % 24u, (uint32_t)cur, max_states);
-            }
-            __syncthreads();
-          }
-#endif
-          done = cnt;
-          if (cnt == kRingCap) break;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          if (bcount[b] > kRingCap) over = 1;
-          bcount[b] = 0;
-        }
-        __syncthreads();
+        sweep_bucket<kTreeThreads, true>(w, T, A, bcount, b, (uint32_t)cur, &n_states, &n_pool, &n_goals, &over, &result,
+                                         &s_cnt, s_state, s_ent, s_msk, budget);
+        if (result != 0x7fffffff && budget == max_states) budget = min(max_states, n_states + kTreeStates);  // uniform
         if (over) break;
         if (result != 0x7fffffff) limit = min(kMaxCost, result + slack);
       }
@@ -680,7 +704,9 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
       __syncthreads();
       if (result == 0x7fffffff) {  // no goal inside the explored region
         if (threadIdx.x == 0) {
-          if (!complete) atomicOr(&flags[prob], 1);  // budget: unknown.  complete: every offered Q is +inf, exactly
+          // complete: every offered Q is +inf, exactly.  Otherwise plain A* from the start ran out of budget: unknown
+          // (an A* from any successor would explore the same space)
+          if (!complete) atomicOr(&flags[prob], 1);
           todo[prob] = 0;
         }
         break;
@@ -746,13 +772,13 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
       }
       __syncthreads();
       const uint32_t open_actions = s_todo;
-      if (open_actions == 0u || complete || over || slack >= kMaxSlack || limit >= kMaxCost) {
-        if (threadIdx.x == 0) {
-          // a search that outgrew the budget keeps what it proved and reports the rest as unknown: the
-          // per-action searches explore the same region with half the budget and would burn it 24 times
-          if (over && open_actions) atomicOr(&flags[prob], 1);
-          todo[prob] = over ? 0u : open_actions;
-        }
+      // Widening pays while the region is small.  Once it is not (or the budget ran out) the actions still open go to
+      // the per-action A* (joint_astar_kernel): from T(start, a) with NO slack it only visits states on optimal plans,
+      // where this search - which needs the ball of radius V* + slack around the start to prove an action whose Q is
+      // that far above V* - explodes with every step of slack (a partner's idle move costs 0.1).  over == 2 (the
+      // backward pass overflowed a bucket) leaves nothing proven beyond doubt: the open actions go the same way.
+      if (open_actions == 0u || complete || over || slack >= kMaxSlack || limit >= kMaxCost || n_states > kWidenStates) {
+        if (threadIdx.x == 0) todo[prob] = open_actions;
         break;
       }
       // widen: the forward pass resumes where it stopped; cost-to-go values are rebuilt from the goals
@@ -781,6 +807,105 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
     } else {
       clear_all();
     }
+  }
+}
+
+// Per-action A*: Q(start, a) = cost(a) + V*(T(start, a)) for the actions the tree search left open (todo mask),
+// each by its own forward A* from the successor with the same keys, heuristic and pathmax rule as the tree search
+// but NO slack and NO edge recording: the first goal state settled ends the search (keys are monotone, a strictly
+// cheaper path re-opens a state, so that cost is V*), and an exhausted open list proves +inf.
+template <int kTreeThreads>
+__global__ void __launch_bounds__(kTreeThreads)
+joint_astar_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant__ GcPairs pairs,
+                   const uint8_t* __restrict__ level_id, const uint4* __restrict__ state, Arena2* __restrict__ arenas,
+                   float* __restrict__ q_out, int* __restrict__ flags, const uint32_t* __restrict__ todo, int64_t n,
+                   int n_agents, uint32_t max_states) {
+  __shared__ uint32_t bcount[kRing];
+  __shared__ uint32_t n_states, n_pool, n_goals, s_f0, s_cnt;
+  __shared__ int over, result;
+  __shared__ PState start;
+  __shared__ World w;
+  __shared__ __align__(16) Tables T;
+  __shared__ __align__(16) uint4 s_state[kTreeThreads];
+  __shared__ uint32_t s_ent[kTreeThreads], s_msk[kTreeThreads];
+  Arena2* A = arenas + blockIdx.x;  // left clean by the tree kernel; every search cleans up after itself
+  const int64_t n_prob = n * pairs.n;
+  for (int64_t prob = blockIdx.x; prob < n_prob; prob += gridDim.x) {
+    uint32_t open = todo[prob];  // uniform; nearly always 0
+    if (open == 0u) continue;
+    const int64_t env = prob / pairs.n;
+    const int pi = (int)(prob - env * pairs.n);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      PState p;
+      gc_subtask st;
+      setup_problem(levels, pairs, level_id, state, env, pi, n_agents, w, p, st);
+      start = p;
+    }
+    __syncthreads();
+    fill_tables(w, &T);
+    while (open) {
+      const uint32_t act = (uint32_t)__ffs((int)open) - 1u;
+      open &= open - 1u;
+      const uint32_t a1 = act / 5u, a2 = act % 5u;
+      const uint32_t code = (a1 != 4u) + (a2 != 4u);
+      __syncthreads();
+      if (threadIdx.x < kRing) bcount[threadIdx.x] = 0;
+      if (threadIdx.x == 0) {
+        n_states = n_pool = n_goals = 0;
+        over = 0;
+        result = 0x7fffffff;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        PState nx = start;
+        interact(w, nx, 0, a1);
+        interact(w, nx, 1, a2);
+        relax2<false>(w, &T, A, bcount, &n_states, &n_pool, &over, nx, 0u, 0u, kNil, 0u, max_states);
+        s_f0 = n_pool;  // the root's key (relax2 leaves it there for the start)
+        n_pool = 0;
+      }
+      __syncthreads();
+      int empty_run = 0;
+      bool complete = false;
+      for (int cur = (int)s_f0; cur <= kMaxCost; cur++) {
+        const uint32_t b = (uint32_t)cur & (kRing - 1);
+        if (bcount[b] == 0) {
+          if (++empty_run >= kRing) {
+            complete = true;
+            break;
+          }
+          continue;
+        }
+        empty_run = 0;
+        sweep_bucket<kTreeThreads, false>(w, T, A, bcount, b, (uint32_t)cur, &n_states, &n_pool, &n_goals, &over, &result,
+                                          &s_cnt, s_state, s_ent, s_msk, max_states);
+        if (over || result != 0x7fffffff) break;
+      }
+      if (threadIdx.x == 0) {
+        if (result != 0x7fffffff) q_out[prob * 25 + act] = 1.0f + 0.1f * (float)code + 0.1f * (float)result;
+        else if (!complete) atomicOr(&flags[prob], 1);  // budget (or the cost ceiling): this Q stays unknown
+      }
+      // the pair is reported as status 3 from here on: its other open actions would most likely burn the budget too
+      if (result == 0x7fffffff && !complete) open = 0u;
+      __syncthreads();
+      if (n_states <= kTouchedCap) {
+        for (uint32_t i = threadIdx.x; i < n_states; i += kTreeThreads) {
+          const uint32_t h = A->touched[i];
+          A->keys[h] = kEmpty;
+          A->gcost[h] = kInfCost;
+          A->val[h] = kInfCost;
+          A->head[h] = kNil;
+        }
+      } else {
+        for (uint32_t k = threadIdx.x; k < kSlots2; k += kTreeThreads) {
+          A->keys[k] = kEmpty;
+          A->gcost[k] = kInfCost;
+          A->val[k] = kInfCost;
+          A->head[k] = kNil;
+        }
+      }
+    }  // open actions
   }
 }
 
@@ -1015,19 +1140,30 @@ int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, co
     // flight per search (a 96 K-state search is latency bound: 1.6x faster on the wide CTA)
     static const int64_t wide_limit = getenv("GC_JOINT_WIDE_PROBLEMS") ? atoll(getenv("GC_JOINT_WIDE_PROBLEMS")) : kWideProblems;
     static const bool narrow = !(getenv("GC_JOINT_THREADS") && atoi(getenv("GC_JOINT_THREADS")) == 128);  // 128: the round-1 shape
+    // GC_JOINT_UCS_FALLBACK=1: the open actions go to the first-generation uniform-cost search instead (A/B runs)
+    static const bool ucs_fallback = getenv("GC_JOINT_UCS_FALLBACK") != nullptr;
+    Arena2* a2 = reinterpret_cast<Arena2*>(base);
     if (probs > wide_limit && narrow) {
-      joint_tree_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(
-          lv, pr, lid, s4, reinterpret_cast<Arena2*>(base), q, flags, todo, n, n_agents, kMaxStates2);
+      joint_tree_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n, n_agents, kMaxStates2);
+      if (!ucs_fallback)
+        joint_astar_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n, n_agents, kMaxStates2);
     } else if (probs > wide_limit) {
-      joint_tree_kernel<kThreads><<<(unsigned)tree_ctas, kThreads, 0, st>>>(
-          lv, pr, lid, s4, reinterpret_cast<Arena2*>(base), q, flags, todo, n, n_agents, kMaxStates2);
+      joint_tree_kernel<kThreads><<<(unsigned)tree_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n, n_agents,
+                                                                          kMaxStates2);
+      if (!ucs_fallback)
+        joint_astar_kernel<kThreads><<<(unsigned)tree_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n,
+                                                                             n_agents, kMaxStates2);
     } else {
       const int wide_ctas = tree_ctas < 2 ? tree_ctas : (tree_ctas + 1) / 2;
-      joint_tree_kernel<kTreeThreadsWide><<<(unsigned)wide_ctas, kTreeThreadsWide, 0, st>>>(
-          lv, pr, lid, s4, reinterpret_cast<Arena2*>(base), q, flags, todo, n, n_agents, kMaxStates2);
+      joint_tree_kernel<kTreeThreadsWide><<<(unsigned)wide_ctas, kTreeThreadsWide, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo,
+                                                                                         n, n_agents, kMaxStates2);
+      if (!ucs_fallback)
+        joint_astar_kernel<kTreeThreadsWide><<<(unsigned)wide_ctas, kTreeThreadsWide, 0, st>>>(lv, pr, lid, s4, a2, q, flags,
+                                                                                              todo, n, n_agents, kMaxStates2);
     }
-    joint_q_kernel<<<(unsigned)act_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, reinterpret_cast<Arena*>(base), q, flags,
-                                                            todo, n, n_agents);
+    if (ucs_fallback)
+      joint_q_kernel<<<(unsigned)act_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, reinterpret_cast<Arena*>(base), q, flags, todo,
+                                                              n, n_agents);
   }
   joint_finalize_kernel<<<pgrid, 256, 0, st>>>(pr, v, q, status, flags, n);
   return gc_check_launch("gc_joint_q");

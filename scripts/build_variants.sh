@@ -19,6 +19,11 @@ for v in "$@"; do
     ilp2c5) build ilp2c5 -DGC_STEP2_ILP=2 -DGC_STEP2_MIN_CTAS_ALL=5 & ;;
     ilp2t128) build ilp2t128 -DGC_STEP2_ILP=2 -DGC_STEP2_THREADS=128 -DGC_STEP2_MIN_CTAS_ALL=8 & ;;
     jpe) build jpe -DGC_JOINT_PER_ENTRY & ;;
+    oldpol) build oldpol -DGC_JOINT_TREE_STATES=98304 -DGC_JOINT_WIDEN_STATES=98304 & ;;  # + GC_JOINT_UCS_FALLBACK=1 at run time
+    t32w32) build t32w32 -DGC_JOINT_TREE_STATES=32768 -DGC_JOINT_WIDEN_STATES=32768 & ;;
+    t64w16) build t64w16 -DGC_JOINT_TREE_STATES=65536 -DGC_JOINT_WIDEN_STATES=16384 & ;;
+    t16w8) build t16w8 -DGC_JOINT_TREE_STATES=16384 -DGC_JOINT_WIDEN_STATES=8192 & ;;
+    t16w2) build t16w2 -DGC_JOINT_TREE_STATES=16384 -DGC_JOINT_WIDEN_STATES=2048 & ;;
   esac
 done
 wait
