@@ -1142,24 +1142,30 @@ int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, co
     static const bool narrow = !(getenv("GC_JOINT_THREADS") && atoi(getenv("GC_JOINT_THREADS")) == 128);  // 128: the round-1 shape
     // GC_JOINT_UCS_FALLBACK=1: the open actions go to the first-generation uniform-cost search instead (A/B runs)
     static const bool ucs_fallback = getenv("GC_JOINT_UCS_FALLBACK") != nullptr;
+    // GC_JOINT_BUDGET=<states>: a smaller per-search state budget than the arenas' capacity (experiments)
+    static const uint32_t budget = [] {
+      const char* e = getenv("GC_JOINT_BUDGET");
+      const long v = e ? atol(e) : 0;
+      return v >= 1024 && v < (long)kMaxStates2 ? (uint32_t)v : kMaxStates2;
+    }();
     Arena2* a2 = reinterpret_cast<Arena2*>(base);
     if (probs > wide_limit && narrow) {
-      joint_tree_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n, n_agents, kMaxStates2);
+      joint_tree_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n, n_agents, budget);
       if (!ucs_fallback)
-        joint_astar_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n, n_agents, kMaxStates2);
+        joint_astar_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n, n_agents, budget);
     } else if (probs > wide_limit) {
       joint_tree_kernel<kThreads><<<(unsigned)tree_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n, n_agents,
-                                                                          kMaxStates2);
+                                                                          budget);
       if (!ucs_fallback)
         joint_astar_kernel<kThreads><<<(unsigned)tree_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n,
-                                                                             n_agents, kMaxStates2);
+                                                                             n_agents, budget);
     } else {
       const int wide_ctas = tree_ctas < 2 ? tree_ctas : (tree_ctas + 1) / 2;
       joint_tree_kernel<kTreeThreadsWide><<<(unsigned)wide_ctas, kTreeThreadsWide, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo,
-                                                                                         n, n_agents, kMaxStates2);
+                                                                                         n, n_agents, budget);
       if (!ucs_fallback)
         joint_astar_kernel<kTreeThreadsWide><<<(unsigned)wide_ctas, kTreeThreadsWide, 0, st>>>(lv, pr, lid, s4, a2, q, flags,
-                                                                                              todo, n, n_agents, kMaxStates2);
+                                                                                              todo, n, n_agents, budget);
     }
     if (ucs_fallback)
       joint_q_kernel<<<(unsigned)act_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, reinterpret_cast<Arena*>(base), q, flags, todo,

@@ -28,7 +28,14 @@ namespace {
 constexpr int kThreads = 64;
 constexpr int kMaxDepth = 7;          // interactions on one plan
 constexpr int kMaxSteps = 60;         // deepest bound tried before declaring the budget exceeded
-constexpr uint32_t kNodeBudget = 400000;
+#ifndef GC_SEARCH_NODE_BUDGET
+#define GC_SEARCH_NODE_BUDGET 32768
+#endif
+// search nodes per (env, pair), all of its solves together.  Round 1 allowed 400 000; on 4 096-env samples of four
+// levels (scripts/time_single.py) the SAME 52 problems fail at 25 000, 100 000 and 400 000 nodes with identical results
+// everywhere else - they are goals the deepening can never reach, not deep plans - and the launch waits for them:
+// 6.1 s at 400 000, 1.5 s at 100 000, 0.32 s at 25 000.
+constexpr uint32_t kNodeBudget = GC_SEARCH_NODE_BUDGET;
 constexpr int kInf = 1 << 20;
 
 enum { ST_OK = 0, ST_AT_GOAL = 1, ST_UNREACHABLE = 2, ST_BUDGET = 3, ST_JOINT_UNSUPPORTED = 4 };
@@ -257,13 +264,16 @@ __device__ bool dfs(Ctx& cx, const Plan& p, int g, int bound) {
   return false;
 }
 
-// minimal number of steps from plan state p to the goal; kInf = unreachable / over budget
-__device__ int solve(Ctx& cx, const Plan& p, int first_bound) {
+// minimal number of steps from plan state p to the goal; kInf = unreachable / over budget.  `known_max`: an upper
+// bound the caller can prove (kInf = none) - the deepening stops below it and returns it unsearched (the last
+// iteration of an iterative deepening costs more than all the earlier ones together).
+__device__ int solve(Ctx& cx, const Plan& p, int first_bound, int known_max = kInf) {
   uint8_t dist[64];
   bfs(cx, p.cell, dist);
   const int h0 = heuristic(cx, p, dist);
   if (h0 >= kInf) return kInf;
   for (int bound = max(h0, first_bound); bound <= kMaxSteps; bound++) {
+    if (bound >= known_max) return known_max;
     if (dfs<0>(cx, p, 0, bound)) return bound;
     if (cx.over) return kInf;
   }
@@ -347,6 +357,9 @@ subtask_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_consta
       if ((cx.blocked >> tgt) & 1ull) continue;  // another agent stands there (navigation_planner/utils.py:71)
       Plan nx = p;
       bool goal_now = false;
+      // A step that one more step undoes (a walk; a pick-up or put-down that creates nothing: the object goes back
+      // where it was) leaves V* within one of the start's: V*(nx) <= V*(start) + 1 needs no search to be known.
+      bool undoable = true;
       if ((cx.floorp >> tgt) & 1ull) {
         nx.cell = tgt;
         offered[a] = true;
@@ -356,10 +369,13 @@ subtask_q_kernel(const __grid_constant__ GcNavLevels levels, const __grid_consta
         const bool changed = apply_interaction(cx, nx, tgt, made, delivered);
         offered[a] = changed || ((cx.deliv >> tgt) & 1ull);  // a Delivery square may always be faced (:77-78)
         goal_now = changed && is_goal(cx, made, delivered);
+        // chop / merge / deliver cannot be taken back; nor can a pick-up from a cutboard (facing the board again
+        // with something choppable in hand chops it instead of putting it back)
+        undoable = !changed || (made == 0u && !((cx.cut >> tgt) & 1ull));
       }
       if (!offered[a] || v_start >= kInf || cx.over) continue;
       int steps = 0;
-      if (!goal_now) steps = solve(cx, nx, max(0, v_start - 1));
+      if (!goal_now) steps = solve(cx, nx, max(0, v_start - 1), undoable ? v_start + 1 : kInf);
       if (steps < kInf) {
         q_steps[a] = steps + 1;
         best_steps = min(best_steps, steps + 1);

@@ -23,6 +23,8 @@ for v in "$@"; do
     t32w32) build t32w32 -DGC_JOINT_TREE_STATES=32768 -DGC_JOINT_WIDEN_STATES=32768 & ;;
     t64w16) build t64w16 -DGC_JOINT_TREE_STATES=65536 -DGC_JOINT_WIDEN_STATES=16384 & ;;
     t16w8) build t16w8 -DGC_JOINT_TREE_STATES=16384 -DGC_JOINT_WIDEN_STATES=8192 & ;;
+    nb100) build nb100 -DGC_SEARCH_NODE_BUDGET=100000 & ;;
+    nb25) build nb25 -DGC_SEARCH_NODE_BUDGET=25000 & ;;
     t16w2) build t16w2 -DGC_JOINT_TREE_STATES=16384 -DGC_JOINT_WIDEN_STATES=2048 & ;;
   esac
 done
