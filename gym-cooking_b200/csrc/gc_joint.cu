@@ -59,7 +59,7 @@ constexpr uint32_t kMaxStates2 = GC_JOINT_MAX_STATES;   // budget of a per-actio
 #define GC_JOINT_TREE_STATES (32 * 1024)
 #endif
 #ifndef GC_JOINT_WIDEN_STATES
-#define GC_JOINT_WIDEN_STATES (8 * 1024)
+#define GC_JOINT_WIDEN_STATES (32 * 1024)
 #endif
 constexpr uint32_t kTreeStates = GC_JOINT_TREE_STATES;    // the tree search's budget BEYOND its first goal: what it cannot prove inside it
 constexpr uint32_t kWidenStates = GC_JOINT_WIDEN_STATES;  // is cheaper to prove action by action; no widening beyond this
