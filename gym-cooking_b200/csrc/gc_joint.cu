@@ -818,8 +818,9 @@ template <int kTreeThreads>
 __global__ void __launch_bounds__(kTreeThreads)
 joint_astar_kernel(const __grid_constant__ GcNavLevels levels, const __grid_constant__ GcPairs pairs,
                    const uint8_t* __restrict__ level_id, const uint4* __restrict__ state, Arena2* __restrict__ arenas,
-                   float* __restrict__ q_out, int* __restrict__ flags, const uint32_t* __restrict__ todo, int64_t n,
-                   int n_agents, uint32_t max_states) {
+                   float* __restrict__ q_out, int* __restrict__ flags, uint32_t* __restrict__ queue,
+                   const unsigned long long* __restrict__ units, int64_t unit_cap, int64_t n, int n_agents,
+                   uint32_t max_states) {
   __shared__ uint32_t bcount[kRing];
   __shared__ uint32_t n_states, n_pool, n_goals, s_f0, s_cnt;
   __shared__ int over, result;
@@ -828,25 +829,49 @@ joint_astar_kernel(const __grid_constant__ GcNavLevels levels, const __grid_cons
   __shared__ __align__(16) Tables T;
   __shared__ __align__(16) uint4 s_state[kTreeThreads];
   __shared__ uint32_t s_ent[kTreeThreads], s_msk[kTreeThreads];
+  __shared__ unsigned long long s_unit;
   Arena2* A = arenas + blockIdx.x;  // left clean by the tree kernel; every search cleans up after itself
-  const int64_t n_prob = n * pairs.n;
-  for (int64_t prob = blockIdx.x; prob < n_prob; prob += gridDim.x) {
-    uint32_t open = todo[prob];  // uniform; nearly always 0
-    if (open == 0u) continue;
-    const int64_t env = prob / pairs.n;
-    const int pi = (int)(prob - env * pairs.n);
+  // Work units are (problem, action) pairs listed by joint_units_kernel and handed out through one global counter:
+  // the problems with open actions are few and uneven (one can bring 24 searches of 10^4 states), and with a static
+  // stride over problems the launch lasted as long as its unluckiest CTA.
+  const uint32_t n_units = (uint32_t)min((int64_t)queue[0], unit_cap);
+  int64_t last_prob = -1;
+  for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) {
-      PState p;
-      gc_subtask st;
-      setup_problem(levels, pairs, level_id, state, env, pi, n_agents, w, p, st);
-      start = p;
+      unsigned long long un = ~0ull;
+      for (;;) {
+        const uint32_t u = atomicAdd(&queue[1], 1u);
+        if (u >= n_units) {
+          un = ~0ull;
+          break;
+        }
+        un = units[u];
+        // a pair one of whose searches ran out of budget is reported as status 3 whatever its other searches find:
+        // they are skipped (read by one thread, so that the whole CTA sees one answer)
+        if (!(*reinterpret_cast<volatile int*>(&flags[un >> 5]) & 1)) break;
+      }
+      s_unit = un;
     }
     __syncthreads();
-    fill_tables(w, &T);
-    while (open) {
-      const uint32_t act = (uint32_t)__ffs((int)open) - 1u;
-      open &= open - 1u;
+    const unsigned long long unit = s_unit;
+    if (unit == ~0ull) break;
+    const int64_t prob = (int64_t)(unit >> 5);
+    const uint32_t act = (uint32_t)(unit & 31ull);
+    if (prob != last_prob) {
+      const int64_t env = prob / pairs.n;
+      const int pi = (int)(prob - env * pairs.n);
+      if (threadIdx.x == 0) {
+        PState p;
+        gc_subtask st;
+        setup_problem(levels, pairs, level_id, state, env, pi, n_agents, w, p, st);
+        start = p;
+      }
+      __syncthreads();
+      fill_tables(w, &T);
+      last_prob = prob;
+    }
+    {
       const uint32_t a1 = act / 5u, a2 = act % 5u;
       const uint32_t code = (a1 != 4u) + (a2 != 4u);
       __syncthreads();
@@ -886,8 +911,6 @@ joint_astar_kernel(const __grid_constant__ GcNavLevels levels, const __grid_cons
         if (result != 0x7fffffff) q_out[prob * 25 + act] = 1.0f + 0.1f * (float)code + 0.1f * (float)result;
         else if (!complete) atomicOr(&flags[prob], 1);  // budget (or the cost ceiling): this Q stays unknown
       }
-      // the pair is reported as status 3 from here on: its other open actions would most likely burn the budget too
-      if (result == 0x7fffffff && !complete) open = 0u;
       __syncthreads();
       if (n_states <= kTouchedCap) {
         for (uint32_t i = threadIdx.x; i < n_states; i += kTreeThreads) {
@@ -905,8 +928,25 @@ joint_astar_kernel(const __grid_constant__ GcNavLevels levels, const __grid_cons
           A->head[k] = kNil;
         }
       }
-    }  // open actions
+    }  // one (problem, action) search
   }
+}
+
+// the open actions of all problems as a list of (problem << 5 | action) units; a problem whose actions do not fit
+// any more (never seen: the list has one slot per problem, 0.1-0.5 per problem are used) is reported as over budget
+__global__ void joint_units_kernel(const uint32_t* __restrict__ todo, int* __restrict__ flags, uint32_t* __restrict__ queue,
+                                   unsigned long long* __restrict__ units, int64_t n_prob, int64_t unit_cap) {
+  const int64_t prob = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (prob >= n_prob) return;
+  uint32_t m = todo[prob];
+  if (m == 0u) return;
+  const uint32_t k = (uint32_t)__popc(m);
+  const uint32_t base = atomicAdd(&queue[0], k);
+  if ((int64_t)base + k > unit_cap) {
+    atomicOr(&flags[prob], 1);
+    return;
+  }
+  for (uint32_t i = 0; m; i++, m &= m - 1u) units[base + i] = ((unsigned long long)prob << 5) | (uint32_t)(__ffs((int)m) - 1);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -1045,9 +1085,11 @@ __global__ void joint_finalize_kernel(const __grid_constant__ GcPairs pairs, flo
 }
 
 __global__ void joint_init_kernel(const __grid_constant__ GcPairs pairs, float* __restrict__ q_out,
-                                  int* __restrict__ flags, uint32_t* __restrict__ todo, int64_t n) {
+                                  int* __restrict__ flags, uint32_t* __restrict__ todo, uint32_t* __restrict__ queue,
+                                  int64_t n) {
   const int64_t prob = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (prob >= n * pairs.n) return;
+  if (prob == 0) queue[0] = queue[1] = 0u;  // units listed / units handed out (joint_astar_kernel)
   flags[prob] = 0;
   todo[prob] = 0;
   if (pairs.p[prob % pairs.n][2] == 0xFF) return;
@@ -1100,7 +1142,8 @@ int64_t gc_joint_q_scratch_bytes(int64_t n, int n_pairs, int* n_ctas_out) {
   int tree_ctas = 0, act_ctas = 0;
   joint_ctas(n, n_pairs, &tree_ctas, &act_ctas);
   if (n_ctas_out) *n_ctas_out = tree_ctas;
-  return joint_arena_bytes(tree_ctas, act_ctas) + n * n_pairs * (int64_t)(sizeof(int) + sizeof(uint32_t));
+  // + per problem: flags, todo mask, one unit slot; + the two queue counters
+  return joint_arena_bytes(tree_ctas, act_ctas) + n * n_pairs * (int64_t)(sizeof(int) + sizeof(uint32_t) + sizeof(unsigned long long)) + 16;
 }
 
 int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, const uint32_t* state,
@@ -1124,13 +1167,15 @@ int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, co
   char* base = reinterpret_cast<char*>(scratch);
   int* flags = reinterpret_cast<int*>(base + joint_arena_bytes(tree_ctas, act_ctas));
   uint32_t* todo = reinterpret_cast<uint32_t*>(flags + n * n_pairs);
+  unsigned long long* units = reinterpret_cast<unsigned long long*>(todo + n * n_pairs);  // 8 B per problem before it: aligned
+  uint32_t* queue = reinterpret_cast<uint32_t*>(units + n * n_pairs);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t probs = n * n_pairs;
   const unsigned pgrid = (unsigned)((probs + 255) / 256);
   const uint4* s4 = reinterpret_cast<const uint4*>(state);
   const uint8_t* lid = n_levels > 1 ? level_id : nullptr;
   static const bool per_action_only = getenv("GC_JOINT_PER_ACTION") != nullptr;  // the first-generation path, for A/B runs
-  joint_init_kernel<<<pgrid, 256, 0, st>>>(pr, q, flags, todo, n);
+  joint_init_kernel<<<pgrid, 256, 0, st>>>(pr, q, flags, todo, queue, n);
   if (per_action_only) {
     joint_q_kernel<<<(unsigned)act_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, reinterpret_cast<Arena*>(base), q, flags,
                                                             nullptr, n, n_agents);
@@ -1151,21 +1196,27 @@ int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, co
     Arena2* a2 = reinterpret_cast<Arena2*>(base);
     if (probs > wide_limit && narrow) {
       joint_tree_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n, n_agents, budget);
-      if (!ucs_fallback)
-        joint_astar_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n, n_agents, budget);
+      if (!ucs_fallback) {
+        joint_units_kernel<<<pgrid, 256, 0, st>>>(todo, flags, queue, units, probs, probs);
+        joint_astar_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(lv, pr, lid, s4, a2, q, flags, queue, units, probs, n, n_agents, budget);
+      }
     } else if (probs > wide_limit) {
       joint_tree_kernel<kThreads><<<(unsigned)tree_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n, n_agents,
                                                                           budget);
-      if (!ucs_fallback)
-        joint_astar_kernel<kThreads><<<(unsigned)tree_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n,
-                                                                             n_agents, budget);
+      if (!ucs_fallback) {
+        joint_units_kernel<<<pgrid, 256, 0, st>>>(todo, flags, queue, units, probs, probs);
+        joint_astar_kernel<kThreads><<<(unsigned)tree_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, a2, q, flags, queue, units, probs,
+                                                                             n, n_agents, budget);
+      }
     } else {
       const int wide_ctas = tree_ctas < 2 ? tree_ctas : (tree_ctas + 1) / 2;
       joint_tree_kernel<kTreeThreadsWide><<<(unsigned)wide_ctas, kTreeThreadsWide, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo,
                                                                                          n, n_agents, budget);
-      if (!ucs_fallback)
+      if (!ucs_fallback) {
+        joint_units_kernel<<<pgrid, 256, 0, st>>>(todo, flags, queue, units, probs, probs);
         joint_astar_kernel<kTreeThreadsWide><<<(unsigned)wide_ctas, kTreeThreadsWide, 0, st>>>(lv, pr, lid, s4, a2, q, flags,
-                                                                                              todo, n, n_agents, budget);
+                                                                                              queue, units, probs, n, n_agents, budget);
+      }
     }
     if (ucs_fallback)
       joint_q_kernel<<<(unsigned)act_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, reinterpret_cast<Arena*>(base), q, flags, todo,
