@@ -61,6 +61,7 @@ constexpr uint32_t kMaxStates2 = GC_JOINT_MAX_STATES;   // budget of a per-actio
 #ifndef GC_JOINT_WIDEN_STATES
 #define GC_JOINT_WIDEN_STATES (32 * 1024)
 #endif
+constexpr unsigned long long kSkipUnit = ~0ull - 1ull;     // a slot of the per-action work list nobody filled
 constexpr uint32_t kTreeStates = GC_JOINT_TREE_STATES;    // the tree search's budget BEYOND its first goal: what it cannot prove inside it
 constexpr uint32_t kWidenStates = GC_JOINT_WIDEN_STATES;  // is cheaper to prove action by action; no widening beyond this
 constexpr int64_t kWideProblems = 32 * 1024;
@@ -847,6 +848,7 @@ joint_astar_kernel(const __grid_constant__ GcNavLevels levels, const __grid_cons
           break;
         }
         un = units[u];
+        if (un == kSkipUnit) continue;
         // a pair one of whose searches ran out of budget is reported as status 3 whatever its other searches find:
         // they are skipped (read by one thread, so that the whole CTA sees one answer)
         if (!(*reinterpret_cast<volatile int*>(&flags[un >> 5]) & 1)) break;
@@ -932,8 +934,9 @@ joint_astar_kernel(const __grid_constant__ GcNavLevels levels, const __grid_cons
   }
 }
 
-// the open actions of all problems as a list of (problem << 5 | action) units; a problem whose actions do not fit
-// any more (never seen: the list has one slot per problem, 0.1-0.5 per problem are used) is reported as over budget
+// the open actions of all problems as a list of (problem << 5 | action) units.  The list holds every open action
+// of a batch of up to 4 096 problems and at least one slot per problem beyond that (0.1-0.5 per problem are used);
+// a problem whose actions do not fit any more is reported as over budget.
 __global__ void joint_units_kernel(const uint32_t* __restrict__ todo, int* __restrict__ flags, uint32_t* __restrict__ queue,
                                    unsigned long long* __restrict__ units, int64_t n_prob, int64_t unit_cap) {
   const int64_t prob = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -944,6 +947,7 @@ __global__ void joint_units_kernel(const uint32_t* __restrict__ todo, int* __res
   const uint32_t base = atomicAdd(&queue[0], k);
   if ((int64_t)base + k > unit_cap) {
     atomicOr(&flags[prob], 1);
+    for (int64_t i = base; i < unit_cap; i++) units[i] = kSkipUnit;  // the counter has moved past these slots
     return;
   }
   for (uint32_t i = 0; m; i++, m &= m - 1u) units[base + i] = ((unsigned long long)prob << 5) | (uint32_t)(__ffs((int)m) - 1);
@@ -1133,6 +1137,12 @@ static void joint_ctas(int64_t n, int n_pairs, int* tree_ctas, int* act_ctas, bo
   if (wide) *wide = false;
 }
 
+// slots of the per-action work list (joint_units_kernel)
+static int64_t joint_unit_cap(int64_t problems) {
+  const int64_t small = 4096;
+  return problems <= small ? problems * 24 : (problems > small * 24 ? problems : small * 24);
+}
+
 static int64_t joint_arena_bytes(int tree_ctas, int act_ctas) {
   const int64_t a = (int64_t)tree_ctas * (int64_t)sizeof(Arena2), b = (int64_t)act_ctas * (int64_t)sizeof(Arena);
   return ((a > b ? a : b) + 255) & ~(int64_t)255;
@@ -1143,7 +1153,8 @@ int64_t gc_joint_q_scratch_bytes(int64_t n, int n_pairs, int* n_ctas_out) {
   joint_ctas(n, n_pairs, &tree_ctas, &act_ctas);
   if (n_ctas_out) *n_ctas_out = tree_ctas;
   // + per problem: flags, todo mask, one unit slot; + the two queue counters
-  return joint_arena_bytes(tree_ctas, act_ctas) + n * n_pairs * (int64_t)(sizeof(int) + sizeof(uint32_t) + sizeof(unsigned long long)) + 16;
+  return joint_arena_bytes(tree_ctas, act_ctas) + n * n_pairs * (int64_t)(sizeof(int) + sizeof(uint32_t)) +
+         joint_unit_cap(n * n_pairs) * (int64_t)sizeof(unsigned long long) + 16;
 }
 
 int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, const uint32_t* state,
@@ -1168,7 +1179,8 @@ int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, co
   int* flags = reinterpret_cast<int*>(base + joint_arena_bytes(tree_ctas, act_ctas));
   uint32_t* todo = reinterpret_cast<uint32_t*>(flags + n * n_pairs);
   unsigned long long* units = reinterpret_cast<unsigned long long*>(todo + n * n_pairs);  // 8 B per problem before it: aligned
-  uint32_t* queue = reinterpret_cast<uint32_t*>(units + n * n_pairs);
+  const int64_t unit_cap = joint_unit_cap(n * n_pairs);
+  uint32_t* queue = reinterpret_cast<uint32_t*>(units + unit_cap);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t probs = n * n_pairs;
   const unsigned pgrid = (unsigned)((probs + 255) / 256);
@@ -1197,15 +1209,15 @@ int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, co
     if (probs > wide_limit && narrow) {
       joint_tree_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n, n_agents, budget);
       if (!ucs_fallback) {
-        joint_units_kernel<<<pgrid, 256, 0, st>>>(todo, flags, queue, units, probs, probs);
-        joint_astar_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(lv, pr, lid, s4, a2, q, flags, queue, units, probs, n, n_agents, budget);
+        joint_units_kernel<<<pgrid, 256, 0, st>>>(todo, flags, queue, units, probs, unit_cap);
+        joint_astar_kernel<64><<<(unsigned)tree_ctas, 64, 0, st>>>(lv, pr, lid, s4, a2, q, flags, queue, units, unit_cap, n, n_agents, budget);
       }
     } else if (probs > wide_limit) {
       joint_tree_kernel<kThreads><<<(unsigned)tree_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo, n, n_agents,
                                                                           budget);
       if (!ucs_fallback) {
-        joint_units_kernel<<<pgrid, 256, 0, st>>>(todo, flags, queue, units, probs, probs);
-        joint_astar_kernel<kThreads><<<(unsigned)tree_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, a2, q, flags, queue, units, probs,
+        joint_units_kernel<<<pgrid, 256, 0, st>>>(todo, flags, queue, units, probs, unit_cap);
+        joint_astar_kernel<kThreads><<<(unsigned)tree_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, a2, q, flags, queue, units, unit_cap,
                                                                              n, n_agents, budget);
       }
     } else {
@@ -1213,9 +1225,9 @@ int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, co
       joint_tree_kernel<kTreeThreadsWide><<<(unsigned)wide_ctas, kTreeThreadsWide, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo,
                                                                                          n, n_agents, budget);
       if (!ucs_fallback) {
-        joint_units_kernel<<<pgrid, 256, 0, st>>>(todo, flags, queue, units, probs, probs);
+        joint_units_kernel<<<pgrid, 256, 0, st>>>(todo, flags, queue, units, probs, unit_cap);
         joint_astar_kernel<kTreeThreadsWide><<<(unsigned)wide_ctas, kTreeThreadsWide, 0, st>>>(lv, pr, lid, s4, a2, q, flags,
-                                                                                              queue, units, probs, n, n_agents, budget);
+                                                                                              queue, units, unit_cap, n, n_agents, budget);
       }
     }
     if (ucs_fallback)

@@ -327,3 +327,29 @@ def test_subtask_q_unique_equals_subtask_q():
     ok = st == 0  # budget-limited searches (status 3) may prove different subsets of Q
     assert torch.equal(torch.nan_to_num(v[ok], posinf=1e9), torch.nan_to_num(v2[ok], posinf=1e9))
     assert torch.equal(torch.nan_to_num(q[ok], nan=-1.0, posinf=1e9), torch.nan_to_num(q2[ok], nan=-1.0, posinf=1e9))
+
+
+def test_tiny_batches_on_recycled_memory_equal_the_big_batch():
+    """One env at a time (a handful of problems per launch: every open action must fit the per-action work list,
+    whose size follows the problem count), each on a scratch arena that held garbage, against the same envs solved
+    as one batch."""
+    n = 48
+    kb = gcb.KitchenBatch("partial-divider_tl", 2, n, 100)
+    acts = kb.random_actions(30, seed=21)
+    idx = torch.arange(n, device=kb.device) % 31
+    for s in range(30):
+        a = acts[s].clone()
+        a[idx <= s] = 4
+        kb.step(a)
+    ns = len(kb.subtasks[0])
+    pairs = [(s, 0, 1) for s in range(ns)] + [(s, 0, 1, True) for s in range(ns)]
+    v, q, st = gcb.subtask_q(kb, pairs)
+    assert int((st == 0).sum()) >= n  # something to compare
+    for e in range(n):
+        one = gcb.KitchenBatch("partial-divider_tl", 2, 1, 100)
+        one.state.copy_(kb.state[e:e + 1])
+        need = gcb._lib.load().gc_joint_q_scratch_bytes(1, len(pairs), None)
+        one._joint_scratch = torch.full((need,), 0xAB, dtype=torch.uint8, device=kb.device)
+        v1, q1, st1 = gcb.subtask_q(one, pairs)
+        assert torch.equal(st1[0], st[e]), e
+        assert torch.equal(torch.nan_to_num(q1[0], nan=-1.0, posinf=1e9), torch.nan_to_num(q[e], nan=-1.0, posinf=1e9)), e
