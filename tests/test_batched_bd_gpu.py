@@ -51,7 +51,8 @@ def deterministic_facade(monkeypatch):
                                           ("partial-divider_tomato", ("bd", "up", "dc")),
                                           ("open-divider_tl", ("greedy", "bd", "fb")),
                                           ("open-divider_tomato", ("bd", "up", "dc", "greedy")),
-                                          ("full-divider_salad", ("bd", "dc", "bd"))])  # 2 457-row table: lists
+                                          ("full-divider_salad", ("bd", "dc", "bd")),  # 2 457-row table: lists
+                                          ("partial-divider_tl", ("up", "bd", "greedy", "dc"))])  # 8 028 rows
 def test_batched_loop_equals_facade_loop(level, models, deterministic_facade):
     _compare_with_facade(level, models, deterministic_facade)
 
