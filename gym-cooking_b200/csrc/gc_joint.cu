@@ -52,7 +52,7 @@ constexpr uint32_t kSlots2 = 1u << 17;
 #define GC_JOINT_MAX_SLACK 48
 #endif
 #ifndef GC_JOINT_CTAS_PER_SM_DEFAULT
-#define GC_JOINT_CTAS_PER_SM_DEFAULT 16
+#define GC_JOINT_CTAS_PER_SM_DEFAULT 8
 #endif
 constexpr uint32_t kMaxStates2 = GC_JOINT_MAX_STATES;   // budget of a per-action A* (and the arenas' capacity)
 #ifndef GC_JOINT_TREE_STATES
@@ -64,7 +64,7 @@ constexpr uint32_t kMaxStates2 = GC_JOINT_MAX_STATES;   // budget of a per-actio
 constexpr unsigned long long kSkipUnit = ~0ull - 1ull;     // a slot of the per-action work list nobody filled
 constexpr uint32_t kTreeStates = GC_JOINT_TREE_STATES;    // the tree search's budget BEYOND its first goal: what it cannot prove inside it
 constexpr uint32_t kWidenStates = GC_JOINT_WIDEN_STATES;  // is cheaper to prove action by action; no widening beyond this
-constexpr int64_t kWideProblems = 32 * 1024;
+constexpr int64_t kWideProblems = INT64_MAX;  // every launch: see the note at the launch site
 // one search per CTA: large batches run 4 CTAs of 128 threads per SM (throughput); small ones
 // (the delegation loop solving the few states it has not seen yet) run 2 CTAs of 512 threads so
 // that more hash / edge atomics are in flight per search (latency)
@@ -1109,12 +1109,10 @@ static void joint_ctas(int64_t n, int n_pairs, int* tree_ctas, int* act_ctas, bo
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
-  // resident searches per SM: the searches are latency-bound on their global-memory arenas (3.5 % issue
-  // utilisation at 4 CTAs of 128 threads per SM, profiles/r02_planner_kernels_ncu.csv), so more of them in
-  // flight per SM hide more of that latency: 16 CTAs of 64 threads (64 registers each) solve cfg-3's states
-  // 2.0x faster than 4 x 128 (6.4 -> 3.2 s for 2^18 envs, scripts/joint_ctas_probe.sh).  Each search owns an
-  // 18 MB arena: 43 GB of the 180 GB at full width, capped at a quarter of the device memory.
-  // GC_JOINT_CTAS_PER_SM=k overrides.
+  // searches (CTAs, each with its own 18 MB arena) per SM: 8, of which 2 of the default 512-thread shape are
+  // resident at a time (21 GB of arenas, capped at a quarter of the device memory).  History: 4 x 128 threads in
+  // round 1; 16 x 64 when a thread still expanded whole entries (2.0x on cfg-3, scripts/joint_ctas_probe.sh);
+  // the wide shape since the (entry x action) expansion (note at the launch site).  GC_JOINT_CTAS_PER_SM=k overrides.
   static const int per_sm = [] {
     const char* e = getenv("GC_JOINT_CTAS_PER_SM");
     const int v = e ? atoi(e) : GC_JOINT_CTAS_PER_SM_DEFAULT;
@@ -1192,9 +1190,12 @@ int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, co
     joint_q_kernel<<<(unsigned)act_ctas, kThreads, 0, st>>>(lv, pr, lid, s4, reinterpret_cast<Arena*>(base), q, flags,
                                                             nullptr, n, n_agents);
   } else {
-    // many problems: 4 CTAs of 128 threads per SM (throughput).  Few (the delegation loop solving the
-    // states it has not seen yet): 2 CTAs of 512 threads per SM, so that more hash / edge atomics are in
-    // flight per search (a 96 K-state search is latency bound: 1.6x faster on the wide CTA)
+    // CTA shape.  While a thread expanded a whole open-list entry the searches were latency-bound with a handful of
+    // busy lanes, and many small CTAs (16 of 64 threads per SM) beat few large ones for big batches.  With the
+    // (entry x action) expansion a search keeps 512 threads busy, and the wide shape - 2 resident CTAs of 512
+    // threads per SM, a grid of 8 per SM - is as fast or faster everywhere: cfg-4 loop 3.2 -> 2.3 s, cfg-3 chunk
+    // equal, 4 096 x 11 problems 0.09 -> 0.06 s, and it needs half the arenas (21 GB instead of 43 GB).
+    // GC_JOINT_WIDE_PROBLEMS=<n> restores the narrow shape for launches of more than n problems (A/B runs).
     static const int64_t wide_limit = getenv("GC_JOINT_WIDE_PROBLEMS") ? atoll(getenv("GC_JOINT_WIDE_PROBLEMS")) : kWideProblems;
     static const bool narrow = !(getenv("GC_JOINT_THREADS") && atoi(getenv("GC_JOINT_THREADS")) == 128);  // 128: the round-1 shape
     // GC_JOINT_UCS_FALLBACK=1: the open actions go to the first-generation uniform-cost search instead (A/B runs)
@@ -1221,7 +1222,7 @@ int gc_joint_q(const gc_level* levels, int n_levels, const uint8_t* level_id, co
                                                                              n, n_agents, budget);
       }
     } else {
-      const int wide_ctas = tree_ctas < 2 ? tree_ctas : (tree_ctas + 1) / 2;
+      const int wide_ctas = tree_ctas;
       joint_tree_kernel<kTreeThreadsWide><<<(unsigned)wide_ctas, kTreeThreadsWide, 0, st>>>(lv, pr, lid, s4, a2, q, flags, todo,
                                                                                          n, n_agents, budget);
       if (!ucs_fallback) {

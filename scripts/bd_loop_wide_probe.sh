@@ -2,7 +2,7 @@
 # cfg-4 loop time vs the joint solver's wide/narrow switch (GC_JOINT_WIDE_PROBLEMS: problem count up to which a
 # launch uses 2 CTAs of 512 threads per SM instead of 16 of 64)
 cd "$(dirname "$0")/.."
-for w in 32768 4096 1024 128 0; do
+for w in ${GC_WIDE_LIST:-32768 4096 1024 128 0}; do
   echo "== GC_JOINT_WIDE_PROBLEMS=$w"
   GC_JOINT_WIDE_PROBLEMS=$w python - <<'PY'
 import time, torch, sys, os
