@@ -78,6 +78,9 @@ _SIGNATURES = {
     "gc_bd_update_lists_f64": (C.c_int, [_VOIDP, _VOIDP, _VOIDP, C.c_int, _VOIDP, C.c_int, C.c_int, _VOIDP, _VOIDP, _VOIDP,
                                          C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, C.c_int, C.c_double,
                                          C.c_double, C.c_double, C.c_int64, C.c_int, C.c_int, _VOIDP]),
+    "gc_offered_actions": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, C.c_int64, C.c_int, _VOIDP]),
+    "gc_subtasks_completed": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, C.c_int64, C.c_int,
+                                        _VOIDP]),
     "gc_lower_bound": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, C.c_int, _VOIDP,
                                  C.c_int64, C.c_int, _VOIDP]),
     "gc_subtask_q": (C.c_int, [C.POINTER(Level), C.c_int, _VOIDP, _VOIDP, _VOIDP, C.c_int, _VOIDP, _VOIDP,

@@ -254,6 +254,7 @@ class BatchedDelegation:
         mg = [[(not (a & b & 8)) and done_food(a | b) for b in range(128)] for a in range(128)]  # core.mergeable
         self.mergeable = torch.tensor(mg, dtype=torch.bool, device=dev)
         self.delta = torch.tensor([8, -8, -1, 1], dtype=torch.int64, device=dev)
+        self._four = torch.arange(4, dtype=torch.uint8, device=dev)[None, None, :]
         self.gen = torch.Generator(device=dev)
         self.gen.manual_seed(int(seed))
         self.reset()
@@ -606,16 +607,15 @@ class BatchedDelegation:
         state = kb.state
         ci = self.cache.lookup(state)
         doable = planning.lower_bound(kb, self.lpairs) < self.perimeter  # bd:156
-        offered = self.single_actions(state)
+        bits = planning.offered_actions(kb)  # get_single_actions on the real env; `single_actions` is its torch twin
+        offered = ((bits[:, :, None] >> self._four) & 1).bool()
         actions = torch.stack([self._select_action(i, ci, doable, offered) for i in range(self.NA)], dim=1)
         self.prev = dict(state=state.clone(), ci=ci, doable=doable, offered=offered)
         self.last_actions = actions.contiguous()
         kb.step(self.last_actions, executed_out=self.executed)
-        for i in range(self.NA):  # refresh_subtasks :151-171
-            sub = self.cur_sub[:, i]
-            subc = sub.clamp(max=self.S - 1)
-            complete = (sub < self.S) & (self.goal_count(kb.state, subc) > self.goal_count(self.prev["state"], subc))
-            self.incomplete[:, i] &= ~(complete.long() << subc)
+        # refresh_subtasks :151-171 (gc_subtasks_completed; `goal_count` is its torch twin)
+        done = planning.subtasks_completed(kb, self.prev["state"], self.cur_sub.to(torch.uint8).contiguous())
+        self.incomplete &= ~(done.long() << self.cur_sub.clamp(max=self.S - 1))
         self.t += 1
         return kb.reward_done
 

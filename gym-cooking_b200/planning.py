@@ -78,6 +78,29 @@ def bd_update_lists(probs, alive, rid, hyp_pair, pair_w, q_table, q_row, row_pai
     return probs
 
 
+def offered_actions(batch):
+    """nav_utils.get_single_actions (navigation_planner/utils.py:55-90) for every env and agent of `batch`:
+    uint8[N][n_agents], bit a = move a is offered (staying always is)."""
+    lib = _lib.load()
+    with torch.cuda.device(batch.device):
+        out = torch.empty((batch.num_envs, batch.num_agents), dtype=torch.uint8, device=batch.device)
+        _lib.check(lib.gc_offered_actions(batch._lv(), batch.n_levels, _lib.ptr(batch.level_id), _lib.ptr(batch.state),
+                                          _lib.ptr(out), batch.num_envs, batch.num_agents, batch._stream()))
+    return out
+
+
+def subtasks_completed(batch, before, subtask):
+    """RealAgent.def_subtask_completion (utils/agent.py:286-368): uint8[N][n_agents], 1 where batch.state holds more
+    goal objects of subtask[env][agent] (uint8, >= the subtask count = none) than `before` (int32[N][4])."""
+    lib = _lib.load()
+    with torch.cuda.device(batch.device):
+        out = torch.empty((batch.num_envs, batch.num_agents), dtype=torch.uint8, device=batch.device)
+        _lib.check(lib.gc_subtasks_completed(batch._lv(), batch.n_levels, _lib.ptr(batch.level_id), _lib.ptr(before),
+                                             _lib.ptr(batch.state), _lib.ptr(subtask, torch.uint8), _lib.ptr(out),
+                                             batch.num_envs, batch.num_agents, batch._stream()))
+    return out
+
+
 def _pairs_array(pairs):
     """[(subtask index, agent i, agent j or None[, level1])] -> host uint8[n_pairs][3]; a truthy
     fourth element selects the level-1 planning world (bit 7 of the subtask byte, gymcook.h)."""

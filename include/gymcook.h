@@ -324,6 +324,21 @@ int gc_bd_update_lists_f64(double* probs, const uint8_t* alive, const int64_t* r
                            double none_action_prob, double q_cap, double beta, int64_t n, int P, int n_agents,
                            void* stream);
 
+/* What a RealAgent reads off the real env each step (utils/agent.py), per env and agent:
+ *   gc_offered_actions     nav_utils.get_single_actions (navigation_planner/utils.py:55-90): bit a of
+ *                          offered[env][agent] = move a (0..3) is offered (staying always is): the square faced holds
+ *                          no agent and is floor / a delivery square, or a counter the agent can put its object on,
+ *                          pick an object from, or merge with (core.mergeable)
+ *   gc_subtasks_completed  RealAgent.def_subtask_completion (utils/agent.py:286-368): completed[env][agent] = the env
+ *                          holds more objects equal to the goal of subtask[env][agent] after the step than before
+ *                          (Deliver: lying on a delivery square); subtask >= the level's subtask count = none -> 0
+ *   state/before/after device uint32[n][4]; offered, subtask, completed device uint8[n][n_agents] */
+int gc_offered_actions(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/, const uint32_t* state,
+                       uint8_t* offered, int64_t n, int n_agents, void* stream);
+int gc_subtasks_completed(const gc_level* levels, int n_levels, const uint8_t* level_id /*device*/,
+                          const uint32_t* before, const uint32_t* after, const uint8_t* subtask, uint8_t* completed,
+                          int64_t n, int n_agents, void* stream);
+
 /* ---- (B) navigation planner ------------------------------------------------------------
  * Distance lower bound of env.get_lower_bound_for_subtask_given_objs (env:594-664) =
  * World.get_lower_bound_between (utils/world.py:115-264) + holding penalty, for every

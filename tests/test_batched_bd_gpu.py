@@ -156,3 +156,34 @@ def test_mixed_four_agent_grid_runs():
     assert r["delivered"] >= 36 and r["posterior_updates"] > 0
     assert r["per_level"][2]["hypotheses"][2] == 10 and max(r["per_level"][2]["hypotheses"]) == 39906  # greedy / bd tables
     assert all(rec["loop_steps"] <= 61 for rec in r["per_level"])
+
+
+@pytest.mark.parametrize("level,models", [("open-divider_salad", ("bd", "bd")), ("partial-divider_tl", ("bd", "up", "dc", "greedy")),
+                                          ("full-divider_tomato", ("greedy", "bd", "fb"))])
+def test_agent_view_kernels_equal_their_torch_twins(level, models):
+    """gc_offered_actions / gc_subtasks_completed (what a RealAgent reads off the env each step) against the tensor-op
+    restatements `single_actions` / `goal_count`, on the states of a running loop"""
+    from gym_cooking_b200 import planning
+    loop = batched_agents.BatchedDelegation(level, 1024, models, seed=9)
+    offered_rows = completed = 0
+    for step in range(30):
+        before = loop.kb.state.clone()
+        loop.step()
+        kb = loop.kb
+        bits = planning.offered_actions(kb)
+        want = loop.single_actions(kb.state)  # bool[N][NA][4]
+        got = ((bits[:, :, None] >> torch.arange(4, dtype=torch.uint8, device=bits.device)[None, None, :]) & 1).bool()
+        assert torch.equal(got, want), step
+        offered_rows += int(want.numel())
+        # every subtask index for every agent, not only the ones the agents happen to follow
+        for s in range(loop.S + 1):
+            sub = torch.full((kb.num_envs, loop.NA), s, dtype=torch.uint8, device=kb.device)
+            done = planning.subtasks_completed(kb, before, sub)
+            if s < loop.S:
+                idx = torch.full((kb.num_envs,), s, dtype=torch.int64, device=kb.device)
+                ref = loop.goal_count(kb.state, idx) > loop.goal_count(before, idx)
+            else:
+                ref = torch.zeros(kb.num_envs, dtype=torch.bool, device=kb.device)
+            assert torch.equal(done.bool(), ref[:, None].expand(-1, loop.NA)), (step, s)
+            completed += int(ref.sum())
+    assert offered_rows > 0 and completed > 100
