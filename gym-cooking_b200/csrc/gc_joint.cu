@@ -63,7 +63,8 @@ constexpr uint32_t kMaxStates2 = GC_JOINT_MAX_STATES;   // budget of a per-actio
 #endif
 constexpr unsigned long long kSkipUnit = ~0ull - 1ull;     // a slot of the per-action work list nobody filled
 constexpr uint32_t kTreeStates = GC_JOINT_TREE_STATES;    // the tree search's budget BEYOND its first goal: what it cannot prove inside it
-constexpr uint32_t kWidenStates = GC_JOINT_WIDEN_STATES;  // is cheaper to prove action by action; no widening beyond this
+constexpr uint32_t kWidenStates = GC_JOINT_WIDEN_STATES;
+constexpr uint32_t kSeedStates = 16 * 1024;                // room the seeded per-action searches of a problem may add  // is cheaper to prove action by action; no widening beyond this
 constexpr int64_t kWideProblems = INT64_MAX;  // every launch: see the note at the launch site
 // one search per CTA: large batches run 4 CTAs of 128 threads per SM (throughput); small ones
 // (the delegation loop solving the few states it has not seen yet) run 2 CTAs of 512 threads so
@@ -465,7 +466,7 @@ __device__ uint32_t heuristic(const World& w, const Tables* T, const PState& p) 
 template <bool kRecord = true>
 __device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* A, uint32_t* bcount, uint32_t* n_states,
                                        uint32_t* n_pool, int* over, const PState& p, uint32_t g, uint32_t fmin,
-                                       uint32_t pred, uint32_t code, uint32_t max_states) {
+                                       uint32_t pred, uint32_t code, uint32_t max_states, uint32_t gbase = 0u) {
   const unsigned long long k = compact_key(w, p);
   uint32_t h = hash_key2(k);
   for (uint32_t probe = 0; probe < kSlots2; probe++, h = (h + 1u) & (kSlots2 - 1u)) {
@@ -480,7 +481,8 @@ __device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* 
     }
     // (the cost min and the list-head exchange do not depend on each other: both are issued before either
     // result is used, one global round trip instead of two)
-    const uint32_t prev = atomicMin(&A->gcost[h], 2u * g);
+    // gbase: the tag of a seeded per-action search (0 in the forward pass), see seeded searches in the tree kernel
+    const uint32_t prev = atomicMin(&A->gcost[h], gbase + 2u * g);
     if (kRecord && pred != kNil) {  // (the per-action A* needs no backward pass: no edges)
       const uint32_t node = atomicAdd(n_pool, 1u);
       if (node < kPool) {
@@ -493,7 +495,7 @@ __device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* 
     // strictly cheaper only: `prev == 2g + 1` is this state already SETTLED at the same cost - re-opening it would
     // expand it a second time and record every one of its edges twice.  (The min has cleared its settled bit by
     // then, which is harmless: the one open-list entry that carried this cost has been consumed.)
-    if (prev > 2u * g + 1u) {
+    if (prev > gbase + 2u * g + 1u) {
       const uint32_t est = is_goal(w, p) ? 0u : heuristic(w, T, p);
       if (est == kInfCost) return;  // dead end: recorded (it has a slot and its edge) but never expanded
       const uint32_t f = max(fmin, g + est);
@@ -521,17 +523,26 @@ __device__ __forceinline__ void relax2(const World& w, const Tables* T, Arena2* 
 // returns 0 when there is nothing to expand, else bit 10 | the two agents' offered single actions (5 bits each)
 // and the state itself in `packed`.
 __device__ __forceinline__ uint32_t settle_entry(const World& w, Arena2* A, uint32_t* n_goals, int* over, int* result,
-                                                 uint32_t entry, uint4& packed) {
+                                                 uint32_t entry, uint4& packed, uint32_t gbase = 0u, bool seeded = false) {
   const uint32_t h = entry & (kSlots2 - 1u), g = entry >> 17;
-  if (atomicCAS(&A->gcost[h], 2u * g, 2u * g + 1u) != 2u * g) return 0u;
+  if (atomicCAS(&A->gcost[h], gbase + 2u * g, gbase + 2u * g + 1u) != gbase + 2u * g) return 0u;
+  if (seeded) {  // a state whose exact cost-to-go the backward pass left behind ends the path right here
+    const uint32_t v = A->val[h];
+    if (v != kInfCost) {
+      atomicMin(result, (int)(g + v));
+      return 0u;
+    }
+  }
   packed = A->states[h];
   const PState p = unpack_state(packed);
   if (is_goal(w, p)) {
     atomicMin(result, (int)g);
     A->val[h] = 0u;
-    const uint32_t gi = atomicAdd(n_goals, 1u);
-    if (gi < kGoalCap) A->goals[gi] = h;
-    else atomicExch(over, 1);
+    if (!seeded) {
+      const uint32_t gi = atomicAdd(n_goals, 1u);
+      if (gi < kGoalCap) A->goals[gi] = h;
+      else atomicExch(over, 1);
+    }
     return 0u;
   }
   return (1u << 10) | single_actions(w, p, 0) | (single_actions(w, p, 1) << 5);
@@ -542,7 +553,7 @@ template <bool kRecord>
 __device__ __forceinline__ void expand_action(const World& w, const Tables* T, Arena2* A, uint32_t* bcount,
                                               uint32_t* n_states, uint32_t* n_pool, int* over, uint32_t entry,
                                               const uint4& packed, uint32_t masks, uint32_t act, uint32_t cur,
-                                              uint32_t max_states) {
+                                              uint32_t max_states, uint32_t gbase = 0u) {
   const uint32_t h = entry & (kSlots2 - 1u), g = entry >> 17;
   const uint32_t b1 = act / 5u, b2 = act % 5u;
   if (!((masks >> b1) & 1u) || !((masks >> (5u + b2)) & 1u)) return;
@@ -552,7 +563,7 @@ __device__ __forceinline__ void expand_action(const World& w, const Tables* T, A
   interact(w, nx, 0, b1);
   interact(w, nx, 1, b2);
   const uint32_t code = (b1 != 4u) + (b2 != 4u);
-  relax2<kRecord>(w, T, A, bcount, n_states, n_pool, over, nx, g + 10u + code, cur, h, code, max_states);
+  relax2<kRecord>(w, T, A, bcount, n_states, n_pool, over, nx, g + 10u + code, cur, h, code, max_states, gbase);
 }
 
 // One key bucket of the forward pass, swept until it stops growing (children on the same plateau - pathmax - land in
@@ -561,7 +572,7 @@ template <int kTreeThreads, bool kRecord>
 __device__ __forceinline__ void sweep_bucket(const World& w, const Tables& T, Arena2* A, uint32_t* bcount, uint32_t b,
                                              uint32_t cur, uint32_t* n_states, uint32_t* n_pool, uint32_t* n_goals, int* over,
                                              int* result, uint32_t* s_cnt, uint4* s_state, uint32_t* s_ent, uint32_t* s_msk,
-                                             uint32_t max_states) {
+                                             uint32_t max_states, uint32_t gbase = 0u, bool seeded = false) {
   for (uint32_t done = 0;;) {
     __syncthreads();
     if (threadIdx.x == 0) *s_cnt = min(bcount[b], kRingCap);
@@ -572,10 +583,10 @@ __device__ __forceinline__ void sweep_bucket(const World& w, const Tables& T, Ar
     for (uint32_t e = done + threadIdx.x; e < cnt; e += kTreeThreads) {
       uint4 packed;
       const uint32_t entry = A->bucket[b][e];
-      const uint32_t masks = settle_entry(w, A, n_goals, over, result, entry, packed);
+      const uint32_t masks = settle_entry(w, A, n_goals, over, result, entry, packed, gbase, seeded);
       if (masks)
         for (uint32_t act = 0; act < 24u; act++)
-          expand_action<kRecord>(w, &T, A, bcount, n_states, n_pool, over, entry, packed, masks, act, cur, max_states);
+          expand_action<kRecord>(w, &T, A, bcount, n_states, n_pool, over, entry, packed, masks, act, cur, max_states, gbase);
     }
 #else
     // chunks of one entry per thread: settle (phase A, state and action masks parked in shared memory), then
@@ -585,14 +596,14 @@ __device__ __forceinline__ void sweep_bucket(const World& w, const Tables& T, Ar
       if (threadIdx.x < m) {
         uint4 packed = make_uint4(0u, 0u, 0u, 0u);
         const uint32_t entry = A->bucket[b][base + threadIdx.x];
-        s_msk[threadIdx.x] = settle_entry(w, A, n_goals, over, result, entry, packed);
+        s_msk[threadIdx.x] = settle_entry(w, A, n_goals, over, result, entry, packed, gbase, seeded);
         s_ent[threadIdx.x] = entry;
         s_state[threadIdx.x] = packed;
       }
       __syncthreads();
       for (uint32_t item = threadIdx.x; item < m * 24u; item += kTreeThreads) {
         const uint32_t i = item / 24u, masks = s_msk[i];
-        if (masks) expand_action<kRecord>(w, &T, A, bcount, n_states, n_pool, over, s_ent[i], s_state[i], masks, item % 24u, cur, max_states);
+        if (masks) expand_action<kRecord>(w, &T, A, bcount, n_states, n_pool, over, s_ent[i], s_state[i], masks, item % 24u, cur, max_states, gbase);
       }
       __syncthreads();
     }
@@ -779,7 +790,75 @@ joint_tree_kernel(const __grid_constant__ GcNavLevels levels, const __grid_const
       // that far above V* - explodes with every step of slack (a partner's idle move costs 0.1).  over == 2 (the
       // backward pass overflowed a bucket) leaves nothing proven beyond doubt: the open actions go the same way.
       if (open_actions == 0u || complete || over || slack >= kMaxSlack || limit >= kMaxCost || n_states > kWidenStates) {
-        if (threadIdx.x == 0) todo[prob] = open_actions;
+        uint32_t left = open_actions;
+#ifdef GC_JOINT_SEEDED
+        // ---- seeded per-action searches, in this arena (opt-in build: -DGC_JOINT_SEEDED) ----
+        // Measured at the end of round 2: the full GPU suite passes with it (the two solvers still agree bit for bit),
+        // but cfg-5's partial-divider batches run 2.66 / 7.27 s with it against 2.31 / 6.86 s without - the open actions
+        // mostly come from problems that stopped on their state budget, where few ball states are provably exact and
+        // the seeded search ends up handing over to joint_astar_kernel anyway.  Kept for the next round to instrument.
+        // After the backward pass a state x of the explored ball with g(x) + val(x) <= radius carries its EXACT
+        // cost-to-go (its optimal plan stays among the expanded states: the argument of `proven` above).  An A* from
+        // T(start, a) may therefore stop at the first such state it settles - f = g + val(x) is a finished plan - and
+        // the plan of an action that was not proven re-enters the ball within a step or two, where the per-action A*
+        // of joint_astar_kernel walks all the way to a goal.  The forward costs are no longer needed: `gcost` is wiped
+        // once and reused with a per-action tag in its high bits, descending, so that what an earlier action left
+        // behind always compares as "not reached yet".
+        if (left && over != 2 && n_states + kSeedStates <= max_states && n_states <= kTouchedCap) {
+          for (uint32_t i = threadIdx.x; i < n_states; i += kTreeThreads) {
+            const uint32_t h = A->touched[i], v = A->val[h];
+            if (v != kInfCost && (A->gcost[h] >> 1) + v > (uint32_t)radius) A->val[h] = kInfCost;  // not proven exact
+            A->gcost[h] = kInfCost;
+          }
+          const uint32_t seed_budget = n_states + kSeedStates;
+          const int over_before = over;
+          __syncthreads();
+          if (threadIdx.x == 0) over = 0;
+          uint32_t tag = 24u;
+          for (uint32_t m = left; m; m &= m - 1u, tag--) {
+            const uint32_t act = (uint32_t)__ffs((int)m) - 1u, b1 = act / 5u, b2 = act % 5u;
+            const uint32_t gbase = tag << 20;
+            __syncthreads();
+            if (threadIdx.x < kRing) bcount[threadIdx.x] = 0;
+            if (threadIdx.x == 0) result = 0x7fffffff;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+              PState nx = start;
+              interact(w, nx, 0, b1);
+              interact(w, nx, 1, b2);
+              relax2<false>(w, &T, A, bcount, &n_states, &n_pool, &over, nx, 0u, 0u, kNil, 0u, seed_budget, gbase);
+              s_f0 = n_pool;  // the root's key
+            }
+            __syncthreads();
+            int run = 0;
+            bool exhausted = false;
+            for (int c = (int)s_f0; c <= kMaxCost; c++) {
+              const uint32_t b = (uint32_t)c & (kRing - 1);
+              if (bcount[b] == 0) {
+                if (++run >= kRing) {
+                  exhausted = true;
+                  break;
+                }
+                continue;
+              }
+              run = 0;
+              sweep_bucket<kTreeThreads, false>(w, T, A, bcount, b, (uint32_t)c, &n_states, &n_pool, &n_goals, &over, &result,
+                                                &s_cnt, s_state, s_ent, s_msk, seed_budget, gbase, true);
+              if (over || (result != 0x7fffffff && result <= c + 1)) break;  // every open key is >= c + 1 now
+            }
+            if (over) break;  // out of room: this action and the ones after it go to joint_astar_kernel
+            if (result != 0x7fffffff) {
+              if (threadIdx.x == 0) q_out[prob * 25 + act] = 1.0f + 0.1f * (float)((b1 != 4u) + (b2 != 4u)) + 0.1f * (float)result;
+              left &= ~(1u << act);
+            } else if (exhausted) {
+              left &= ~(1u << act);  // no plan at all: the +inf written for an offered action is exact
+            }
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) over = over_before;
+        }
+#endif
+        if (threadIdx.x == 0) todo[prob] = left;
         break;
       }
       // widen: the forward pass resumes where it stopped; cost-to-go values are rebuilt from the goals

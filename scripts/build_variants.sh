@@ -25,6 +25,7 @@ for v in "$@"; do
     t16w8) build t16w8 -DGC_JOINT_TREE_STATES=16384 -DGC_JOINT_WIDEN_STATES=8192 & ;;
     nb100) build nb100 -DGC_SEARCH_NODE_BUDGET=100000 & ;;
     nb25) build nb25 -DGC_SEARCH_NODE_BUDGET=25000 & ;;
+    seeded) build seeded -DGC_JOINT_SEEDED & ;;
     t16w2) build t16w2 -DGC_JOINT_TREE_STATES=16384 -DGC_JOINT_WIDEN_STATES=2048 & ;;
   esac
 done
