@@ -362,14 +362,10 @@ def run_ours(args):
     if not args.no_secondary and args.cfg5_envs > 0:
         from gym_cooking_b200 import batched_agents
         r5 = batched_agents.run_mixed(args.cfg5_envs, 4, shard=rank, device=dev)
-        tot = torch.tensor([r5["envs"], r5["agent_steps"], r5["posterior_updates"], r5["delivered"],
-                            r5["planning_states_solved"], r5["planner_lookups"], r5["completed_subtasks"]],
-                           dtype=torch.int64, device=dev)
-        tmax = torch.tensor([r5["seconds"]], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tot, tmax = tot.cpu().tolist(), float(tmax.item())
+        from gym_cooking_b200 import sharding
+        t5 = sharding.reduce_mixed_totals(r5, device=dev)  # counts summed over ranks, time of the slowest rank
+        tot = [t5[k] for k in sharding.MIXED_TOTALS]
+        tmax = t5["seconds"]
         cfg5 = {"metric": "cfg5_agent_steps_per_sec", "value": tot[1] / tmax, "unit": "agent-steps/s",
                 "config": "cfg-5: 4 agents, model types bd/up/dc/fb/greedy rotated over seats and levels, all nine levels, "
                           "%d envs per level per GPU x %d GPU(s), horizon 100, full delegation loop from reset with a cold "

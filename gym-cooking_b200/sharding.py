@@ -30,3 +30,20 @@ def stats_dict(stats):
     out["t_histogram"] = v[5:133]
     out["completed_subtasks"] = v[133] if len(v) > 133 else 0
     return out
+
+
+MIXED_TOTALS = ("envs", "agent_steps", "posterior_updates", "delivered", "planning_states_solved", "planner_lookups",
+                "completed_subtasks")
+
+
+def reduce_mixed_totals(totals, device=None):
+    """Whole-job totals of batched_agents.run_mixed when every rank ran its own shard of episodes (cfg-5): the counts
+    are summed over ranks, the wall time is the slowest rank's.  Returns a dict with MIXED_TOTALS + "seconds"."""
+    counts = torch.tensor([int(totals[k]) for k in MIXED_TOTALS], dtype=torch.int64, device=device)
+    seconds = torch.tensor([float(totals["seconds"])], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        dist.all_reduce(seconds, op=dist.ReduceOp.MAX)
+    out = dict(zip(MIXED_TOTALS, counts.cpu().tolist()))
+    out["seconds"] = float(seconds.item())
+    return out

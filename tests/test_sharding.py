@@ -41,6 +41,40 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _totals_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = dict(envs=100 + rank, agent_steps=1000 * (rank + 1), posterior_updates=7 * rank, delivered=90 - rank,
+                planning_states_solved=50 + rank, planner_lookups=400, completed_subtasks=3 * (rank + 2),
+                seconds=1.5 + 2.0 * rank, per_level=[])
+    got = sharding.reduce_mixed_totals(mine)
+    if rank == 0:
+        q.put(got)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_reduction_of_the_cfg5_totals():
+    """what bench.py reports for cfg-5 at N > 1: counts summed over ranks, wall time of the slowest rank"""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_totals_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == dict(envs=201, agent_steps=3000, posterior_updates=7, delivered=179, planning_states_solved=101,
+                       planner_lookups=800, completed_subtasks=15, seconds=3.5)
+    single = sharding.reduce_mixed_totals(dict(envs=5, agent_steps=6, posterior_updates=7, delivered=1,
+                                               planning_states_solved=2, planner_lookups=3, completed_subtasks=4, seconds=0.25))
+    assert single["agent_steps"] == 6 and single["seconds"] == 0.25  # no process group: unchanged
+
+
 def test_shard_ranges_cover_exactly():
     for n, w in ((10, 3), (8, 8), (5, 8), (1 << 23, 8), (6001, 2)):
         r = [sharding.shard_range(n, k, w) for k in range(w)]
